@@ -1,0 +1,337 @@
+"""Workload -> pod expansion (host side), mirroring pkg/utils/utils.go and pkg/simulator/utils.go.
+
+  MakeValidPod                         pkg/utils/utils.go:378-463
+  MakeValidPodsBy{Deployment,ReplicaSet,StatefulSet,Job,CronJob,Daemonset}
+                                       pkg/utils/utils.go:132-247, 337-361
+  SetDaemonSetPodNodeNameByNodeAffinity pkg/utils/utils.go:770-815
+  NodeShouldRunPod / daemon.Predicates pkg/utils/utils.go:325-335,
+                                       vendor/k8s.io/kubernetes/pkg/controller/daemon/daemon_controller.go:1251-1258
+  GetValidPodExcludeDaemonSet          pkg/simulator/utils.go:79-230
+  GenerateValidPodsFromAppResources    pkg/simulator/utils.go:37-75
+  NewFakeNodes / MakeValidNodeByNode   pkg/utils/utils.go:466-492, 885-901
+
+Replicas of one workload share ONE PodTemplate object (the engine deduplicates pods into classes);
+a pod is identified by (workload kind, namespace, name, ordinal) because the reference's generated
+names carry a random suffix (pkg/utils/utils.go:312).
+
+Determinism contract (SURVEY.md §7 hard part 3): the reference appends the per-kind pod lists from
+concurrent goroutines (pkg/simulator/utils.go:85-228); we use the source order Pods, Deployments,
+ReplicaSets, StatefulSets, Jobs, CronJobs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+from . import objects as O
+from .objects import Obj, ResourceTypes, deep_copy
+from .selectors import pod_matches_node_selector_and_affinity, tolerations_tolerate_taint
+
+DEFAULT_SCHEDULER_NAME = "default-scheduler"
+
+
+@dataclass
+class PodTemplate:
+    """A valid pod (metadata + spec) shared by all replicas of a workload."""
+    pod: Obj
+    workload_kind: str = "Pod"
+    workload_name: str = ""
+    workload_namespace: str = ""
+    class_id: int = -1          # filled by the snapshot compiler
+    guard_node_name: str = ""   # DaemonSet pods: the node this pod was generated for
+
+    @property
+    def namespace(self) -> str:
+        return O.namespace_of(self.pod)
+
+    @property
+    def labels(self) -> Dict[str, str]:
+        return O.labels_of(self.pod)
+
+    @property
+    def spec(self) -> Obj:
+        return self.pod.get("spec") or {}
+
+
+@dataclass
+class PodRec:
+    """One pod instance: template + identity. node_name is filled with the placement result."""
+    tmpl: PodTemplate
+    name: str
+    ordinal: int
+    node_name: str = ""     # spec.nodeName (preset or result)
+    phase: str = ""
+    app_name: str = ""
+
+    def key(self):
+        t = self.tmpl
+        return (t.workload_kind, t.workload_namespace, t.workload_name, self.ordinal)
+
+
+def make_valid_pod(old: Obj) -> Obj:
+    """utils.MakeValidPod (pkg/utils/utils.go:378-463). Fields that cannot influence scheduling
+    (env, probes, mounts, image pull policy) are dropped the same way; PVC volumes become hostPath."""
+    pod = deep_copy(old)
+    md = pod.setdefault("metadata", {}) or {}
+    pod["metadata"] = md
+    if md.get("labels") is None:
+        md["labels"] = {}
+    if not md.get("namespace"):
+        md["namespace"] = "default"
+    if md.get("annotations") is None:
+        md["annotations"] = {}
+    md.pop("managedFields", None)
+    spec = pod.setdefault("spec", {}) or {}
+    pod["spec"] = spec
+    spec.setdefault("dnsPolicy", "ClusterFirst")
+    spec.setdefault("restartPolicy", "Always")
+    if not spec.get("schedulerName"):
+        spec["schedulerName"] = DEFAULT_SCHEDULER_NAME
+    spec.pop("imagePullSecrets", None)
+    for key in ("initContainers", "containers"):
+        for c in spec.get(key) or []:
+            c.pop("volumeMounts", None)
+            c.pop("env", None)
+            if key == "containers":
+                c.pop("livenessProbe", None)
+                c.pop("readinessProbe", None)
+                c.pop("startupProbe", None)
+    for v in spec.get("volumes") or []:
+        if v.get("persistentVolumeClaim") is not None:
+            v["hostPath"] = {"path": "/tmp"}
+            v.pop("persistentVolumeClaim", None)
+    pod["status"] = {}
+    if not spec.get("containers"):
+        raise ValueError(f"invalid pod {md.get('namespace')}/{md.get('name')}: spec.containers: Required value")
+    return pod
+
+
+def _object_meta_from(owner: Obj, template: Obj, owner_kind: str) -> Obj:
+    """utils.SetObjectMetaFromObject (pkg/utils/utils.go:294-322); the name suffix is left to PodRec."""
+    tm = (template.get("metadata") or {})
+    return {
+        "name": O.name_of(owner),
+        "namespace": O.namespace_of(owner),
+        "generateName": O.name_of(owner),
+        "annotations": deep_copy(tm.get("annotations")) if tm.get("annotations") else None,
+        "labels": deep_copy(tm.get("labels")) if tm.get("labels") else None,
+        "ownerReferences": [{"kind": owner_kind, "name": O.name_of(owner),
+                             "uid": (owner.get("metadata") or {}).get("uid", ""), "controller": True}],
+    }
+
+
+def _add_workload_info(pod: Obj, kind: str, name: str, namespace: str) -> None:
+    a = pod["metadata"]["annotations"]
+    a[O.ANNO_WORKLOAD_KIND] = kind
+    a[O.ANNO_WORKLOAD_NAME] = name
+    a[O.ANNO_WORKLOAD_NAMESPACE] = namespace
+
+
+def _replicated(owner: Obj, owner_kind: str, template: Obj, count: int, wl_kind: str,
+                name_fmt=None, extra_annotations: Optional[Dict[str, str]] = None) -> List[PodRec]:
+    if count <= 0:
+        return []
+    pod = {"metadata": _object_meta_from(owner, template, owner_kind), "spec": deep_copy(template.get("spec") or {})}
+    valid = make_valid_pod(pod)
+    _add_workload_info(valid, wl_kind, O.name_of(owner), O.namespace_of(owner))
+    if extra_annotations:
+        valid["metadata"]["annotations"].update(extra_annotations)
+    tmpl = PodTemplate(valid, wl_kind, O.name_of(owner), valid["metadata"]["namespace"])
+    base = O.name_of(owner)
+    recs = []
+    for i in range(count):
+        nm = name_fmt(base, i) if name_fmt else f"{base}-{i:05d}"
+        recs.append(PodRec(tmpl, nm, i))
+    return recs
+
+
+def _replicas(spec: Obj, key: str) -> int:
+    v = spec.get(key)
+    return 1 if v is None else int(v)
+
+
+def make_valid_pods_by_replicaset(rs: Obj) -> List[PodRec]:
+    spec = rs.get("spec") or {}
+    return _replicated(rs, "ReplicaSet", spec.get("template") or {}, _replicas(spec, "replicas"), "ReplicaSet")
+
+
+def make_valid_pods_by_deployment(deploy: Obj) -> List[PodRec]:
+    """Deployment -> generated ReplicaSet named after the deployment (pkg/utils/utils.go:132-171);
+    pods are owned by (and annotated with) the ReplicaSet."""
+    spec = deploy.get("spec") or {}
+    return _replicated(deploy, "ReplicaSet", spec.get("template") or {}, _replicas(spec, "replicas"), "ReplicaSet")
+
+
+def make_valid_pods_by_statefulset(sts: Obj) -> List[PodRec]:
+    spec = sts.get("spec") or {}
+    extra = {}
+    vols = _storage_volumes(spec.get("volumeClaimTemplates") or [])
+    import json
+    extra[O.ANNO_POD_LOCAL_STORAGE] = json.dumps({"volumes": vols})
+    return _replicated(sts, "StatefulSet", spec.get("template") or {}, _replicas(spec, "replicas"), "StatefulSet",
+                       name_fmt=lambda b, i: f"{b}-{i}", extra_annotations=extra)
+
+
+_LVM_SC = ("open-local-lvm", "yoda-lvm-default")
+_SSD_SC = ("open-local-device-ssd", "open-local-mountpoint-ssd", "yoda-mountpoint-ssd", "yoda-device-ssd")
+_HDD_SC = ("open-local-device-hdd", "open-local-mountpoint-hdd", "yoda-mountpoint-hdd", "yoda-device-hdd")
+
+
+def _storage_volumes(vcts: List[Obj]) -> List[Obj]:
+    """utils.SetStorageAnnotationOnPods (pkg/utils/utils.go:249-292)."""
+    from .quantity import Quantity
+    out = []
+    for pvc in vcts:
+        sc = (pvc.get("spec") or {}).get("storageClassName")
+        if sc is None:
+            continue
+        kind = "LVM" if sc in _LVM_SC else "SSD" if sc in _SSD_SC else "HDD" if sc in _HDD_SC else None
+        if kind is None:
+            continue
+        req = (((pvc.get("spec") or {}).get("resources") or {}).get("requests") or {}).get("storage", "0")
+        out.append({"size": str(Quantity.parse(req).int_value()), "kind": kind, "scName": sc})
+    return out
+
+
+def make_valid_pod_by_job(job: Obj) -> List[PodRec]:
+    spec = job.get("spec") or {}
+    return _replicated(job, "Job", spec.get("template") or {}, _replicas(spec, "completions"), "Job")
+
+
+def make_valid_pod_by_cronjob(cj: Obj) -> List[PodRec]:
+    """generateJobFromCronJob (pkg/utils/utils.go:200-214): a Job named after the CronJob."""
+    jt = ((cj.get("spec") or {}).get("jobTemplate") or {}).get("spec") or {}
+    return _replicated(cj, "Job", jt.get("template") or {}, _replicas(jt, "completions"), "Job")
+
+
+def make_valid_pod_by_pod(pod: Obj) -> PodRec:
+    valid = make_valid_pod(pod)
+    tmpl = PodTemplate(valid, "Pod", O.name_of(valid), valid["metadata"]["namespace"])
+    rec = PodRec(tmpl, O.name_of(valid), 0)
+    rec.node_name = (valid.get("spec") or {}).get("nodeName", "") or ""
+    return rec
+
+
+def _daemon_affinity(affinity: Optional[Obj], nodename: str) -> Obj:
+    """utils.SetDaemonSetPodNodeNameByNodeAffinity (pkg/utils/utils.go:770-815)."""
+    req = {"key": "metadata.name", "operator": "In", "values": [nodename]}
+    sel = {"nodeSelectorTerms": [{"matchFields": [req]}]}
+    R = "requiredDuringSchedulingIgnoredDuringExecution"
+    if affinity is None:
+        return {"nodeAffinity": {R: sel}}
+    affinity = deep_copy(affinity)
+    na = affinity.get("nodeAffinity")
+    if na is None:
+        affinity["nodeAffinity"] = {R: sel}
+        return affinity
+    if na.get(R) is None:
+        na[R] = sel
+        return affinity
+    for term in na[R].get("nodeSelectorTerms") or []:
+        term["matchFields"] = [deep_copy(req)]
+    return affinity
+
+
+def node_should_run_pod(node: Obj, pod: Obj) -> bool:
+    """utils.NodeShouldRunPod -> daemon.Predicates."""
+    spec = pod.get("spec") or {}
+    nn = spec.get("nodeName") or ""
+    if nn and nn != O.name_of(node):
+        return False
+    if not pod_matches_node_selector_and_affinity(spec, node):
+        return False
+    tols = spec.get("tolerations") or []
+    for t in ((node.get("spec") or {}).get("taints") or []):
+        if t.get("effect") in ("NoExecute", "NoSchedule") and not tolerations_tolerate_taint(tols, t):
+            return False
+    return True
+
+
+def make_valid_pods_by_daemonset(ds: Obj, nodes: List[Obj]) -> List[PodRec]:
+    """utils.MakeValidPodsByDaemonset (pkg/utils/utils.go:337-351): one pod per eligible node, in node order,
+    each pinned with a required matchFields metadata.name node affinity."""
+    spec = ds.get("spec") or {}
+    template = spec.get("template") or {}
+    recs = []
+    ordinal = 0
+    for node in nodes:
+        pod = {"metadata": _object_meta_from(ds, template, "DaemonSet"), "spec": deep_copy(template.get("spec") or {})}
+        pod["spec"]["affinity"] = _daemon_affinity(pod["spec"].get("affinity"), O.name_of(node))
+        valid = make_valid_pod(pod)
+        _add_workload_info(valid, "DaemonSet", O.name_of(ds), O.namespace_of(ds))
+        if node_should_run_pod(node, valid):
+            tmpl = PodTemplate(valid, "DaemonSet", O.name_of(ds), valid["metadata"]["namespace"],
+                               guard_node_name=O.name_of(node))
+            recs.append(PodRec(tmpl, f"{O.name_of(ds)}-{O.name_of(node)}", ordinal))
+            ordinal += 1
+    return recs
+
+
+def get_valid_pod_exclude_daemonset(res: ResourceTypes) -> List[PodRec]:
+    """simulator.GetValidPodExcludeDaemonSet (pkg/simulator/utils.go:79-230)."""
+    pods: List[PodRec] = []
+    for p in res.Pods:
+        pods.append(make_valid_pod_by_pod(p))
+    for d in res.Deployments:
+        pods.extend(make_valid_pods_by_deployment(d))
+    for rs in res.ReplicaSets:
+        pods.extend(make_valid_pods_by_replicaset(rs))
+    for s in res.StatefulSets:
+        pods.extend(make_valid_pods_by_statefulset(s))
+    for j in res.Jobs:
+        pods.extend(make_valid_pod_by_job(j))
+    for c in res.CronJobs:
+        pods.extend(make_valid_pod_by_cronjob(c))
+    return pods
+
+
+def generate_valid_pods_from_app_resources(nodes: List[Obj], appname: str, res: ResourceTypes) -> List[PodRec]:
+    """simulator.GenerateValidPodsFromAppResources (pkg/simulator/utils.go:37-75): `nodes` is the node list
+    of the fake client at this moment; every pod gets the label simon/app-name=<appname>."""
+    pods = get_valid_pod_exclude_daemonset(res)
+    for ds in res.DaemonSets:
+        pods.extend(make_valid_pods_by_daemonset(ds, nodes))
+    seen = set()
+    for r in pods:
+        if id(r.tmpl) not in seen:
+            seen.add(id(r.tmpl))
+            r.tmpl.pod["metadata"]["labels"][O.LABEL_APP_NAME] = appname
+        r.app_name = appname
+    return pods
+
+
+def make_valid_node_by_node(node: Obj, nodename: str) -> Obj:
+    """utils.MakeValidNodeByNode (pkg/utils/utils.go:466-492): mutates AND returns `node`;
+    the hostname label is set only when Labels != nil."""
+    md = node.setdefault("metadata", {})
+    md["name"] = nodename
+    if md.get("labels") is None:
+        md["labels"] = {}
+    else:
+        md["labels"][O.LABEL_HOSTNAME] = nodename
+    if md.get("annotations") is None:
+        md["annotations"] = {}
+    md.pop("managedFields", None)
+    return node
+
+
+def new_fake_nodes(node: Optional[Obj], count: int) -> List[Obj]:
+    """utils.NewFakeNodes (pkg/utils/utils.go:885-901). Like the reference, the template node is mutated
+    across iterations (so a template without labels yields a first copy without the hostname label and
+    later copies with it). Reference names are simon-<rand5>; we use a zero-padded ordinal."""
+    if node is None and count != 0:
+        raise ValueError("new node is nil when adding node to cluster, please check whether newNode in configuration file is empty")
+    out = []
+    work = deep_copy(node) if node is not None else None
+    for i in range(count):
+        n = make_valid_node_by_node(work, f"{O.NEW_NODE_NAME_PREFIX}-{i:05d}")
+        n["metadata"]["labels"][O.LABEL_NEW_NODE] = ""
+        out.append(deep_copy(n))
+    return out
+
+
+def new_fake_node(node: Obj) -> Obj:
+    """utils.NewFakeNode (pkg/utils/utils.go:903-915)."""
+    n = make_valid_node_by_node(deep_copy(node), O.name_of(node))
+    n["metadata"]["labels"][O.LABEL_NEW_NODE] = ""
+    return n

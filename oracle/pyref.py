@@ -1,0 +1,688 @@
+"""pyref — object-level restatement of the reference scheduling path (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+
+Unlike oracle/simon_oracle.c (which consumes the compiled SoA columns and therefore shares the snapshot
+compiler with the product), this restatement works directly on Kubernetes objects (dicts) with string
+labels, maps and per-pod lists, the way the vendored kube-scheduler does, so that it cross-checks the
+compiler + C oracle + GPU engine chain end to end.  Pure-Python loops: small cases only.
+
+Parity status: "parity unpinned" against the reference binary (no Go toolchain).
+
+Followed code (paths relative to the reference tree, PL = vendor/k8s.io/kubernetes/pkg/scheduler/framework/plugins):
+  generic_scheduler.go:131-180, 271-343, 470-564   framework/runtime/framework.go:527-552, 635-710
+  PL/nodeunschedulable, nodename, tainttoleration, nodeaffinity, nodeports, noderesources (fit, least, balanced),
+  PL/podtopologyspread (filtering.go, scoring.go, common.go), PL/interpodaffinity (filtering.go, scoring.go),
+  PL/helper (normalize_score.go, spread.go, node_affinity.go), pkg/simulator/plugin/simon.go, open-gpu-share.go
+It reuses the product's Quantity / go_log restatements (simon_b200.quantity, simon_b200.gomath).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+from simon_b200.gomath import go_log
+from simon_b200.quantity import Quantity
+
+HOSTNAME = "kubernetes.io/hostname"
+ZONE = "topology.kubernetes.io/zone"
+MAXI64 = (1 << 63) - 1
+
+
+def _f2i(x: float) -> int:
+    if x != x or x >= 9.223372036854775807e18 or x < -9.223372036854775808e18:
+        return -(1 << 63)
+    return int(x)
+
+
+def _go_div(a: int, b: int) -> int:
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+# ---- selectors -------------------------------------------------------------------------------------
+
+def _sel_reqs(sel):
+    if sel is None:
+        return None
+    out = [(k, "In", [str(v)]) for k, v in (sel.get("matchLabels") or {}).items()]
+    for e in sel.get("matchExpressions") or []:
+        out.append((e["key"], e["operator"], [str(x) for x in (e.get("values") or [])]))
+    return out
+
+
+def _req_match(r, labels) -> bool:
+    k, op, vals = r
+    if op == "In":
+        return k in labels and str(labels[k]) in vals
+    if op == "NotIn":
+        return k not in labels or str(labels[k]) not in vals
+    if op == "Exists":
+        return k in labels
+    if op == "DoesNotExist":
+        return k not in labels
+    if op in ("Gt", "Lt"):
+        if k not in labels or len(vals) != 1:
+            return False
+        try:
+            a, b = int(str(labels[k])), int(vals[0])
+        except ValueError:
+            return False
+        return a > b if op == "Gt" else a < b
+    return False
+
+
+def _sel_match(reqs, labels) -> bool:
+    return reqs is not None and all(_req_match(r, labels) for r in reqs)
+
+
+def _node_term_match(term, node) -> bool:
+    labels = node["metadata"].get("labels") or {}
+    ex = term.get("matchExpressions") or []
+    fl = term.get("matchFields") or []
+    for e in ex:
+        vals = [str(x) for x in (e.get("values") or [])]
+        op = e.get("operator")
+        if op in ("In", "NotIn") and not vals:
+            return False
+        if op in ("Exists", "DoesNotExist") and vals:
+            return False
+        if op in ("Gt", "Lt") and len(vals) != 1:
+            return False
+        if op not in ("In", "NotIn", "Exists", "DoesNotExist", "Gt", "Lt"):
+            return False
+    for e in fl:
+        if e.get("operator") not in ("In", "NotIn") or len(e.get("values") or []) != 1:
+            return False
+    for e in ex:
+        if not _req_match((e["key"], e["operator"], [str(x) for x in (e.get("values") or [])]), labels):
+            return False
+    name = node["metadata"].get("name", "")
+    if fl and name:
+        for e in fl:
+            have = name if e["key"] == "metadata.name" else ""
+            v = str(e["values"][0])
+            if e["operator"] == "In" and have != v:
+                return False
+            if e["operator"] == "NotIn" and have == v:
+                return False
+    return True
+
+
+def _node_sel_ok(spec, node) -> bool:
+    labels = node["metadata"].get("labels") or {}
+    for k, v in (spec.get("nodeSelector") or {}).items():
+        if k not in labels or str(labels[k]) != str(v):
+            return False
+    aff = spec.get("affinity")
+    if not aff or not aff.get("nodeAffinity"):
+        return True
+    req = aff["nodeAffinity"].get("requiredDuringSchedulingIgnoredDuringExecution")
+    if req is None:
+        return True
+    for term in req.get("nodeSelectorTerms") or []:
+        if not (term.get("matchExpressions") or term.get("matchFields")):
+            continue
+        if _node_term_match(term, node):
+            return True
+    return False
+
+
+def _tolerates(tol, taint) -> bool:
+    if tol.get("effect") and tol["effect"] != taint.get("effect", ""):
+        return False
+    if tol.get("key") and tol["key"] != taint.get("key", ""):
+        return False
+    op = tol.get("operator") or ""
+    if op in ("", "Equal"):
+        return (tol.get("value") or "") == (taint.get("value") or "")
+    return op == "Exists"
+
+
+# ---- pod resource arithmetic ---------------------------------------------------------------------------
+
+def _is_scalar(name: str) -> bool:
+    if name.startswith("hugepages-") or name.startswith("attachable-volumes-") or "kubernetes.io/" in name:
+        return True
+    return "/" in name and not name.startswith("requests.")
+
+
+def _rl(c):
+    return {k: Quantity.parse(v) for k, v in (((c.get("resources") or {}).get("requests")) or {}).items()}
+
+
+def _val(name, q):
+    return q.milli_value() if name == "cpu" else q.int_value()
+
+
+def pod_request(spec):
+    """(fit request dict incl. scalars, non0 cpu, non0 mem, score cpu, score mem, has_request)."""
+    res: Dict[str, int] = {"cpu": 0, "memory": 0, "ephemeral-storage": 0}
+    scal: Dict[str, int] = {}
+    n0c = n0m = scc = scm = 0
+    for c in spec.get("containers") or []:
+        rl = _rl(c)
+        for k, q in rl.items():
+            if k in res:
+                res[k] += _val(k, q)
+            elif _is_scalar(k):
+                scal[k] = scal.get(k, 0) + q.int_value()
+        a = rl["cpu"].milli_value() if "cpu" in rl else 100
+        b = rl["memory"].int_value() if "memory" in rl else 200 * 1024 * 1024
+        n0c += a; n0m += b; scc += a; scm += b
+    for c in spec.get("initContainers") or []:
+        rl = _rl(c)
+        for k, q in rl.items():
+            if k in res:
+                res[k] = max(res[k], _val(k, q))
+            elif _is_scalar(k) and q.int_value() > scal.get(k, 0):
+                scal[k] = q.int_value()
+        a = rl["cpu"].milli_value() if "cpu" in rl else 100
+        b = rl["memory"].int_value() if "memory" in rl else 200 * 1024 * 1024
+        n0c = max(n0c, a); n0m = max(n0m, b); scc = max(scc, a); scm = max(scm, b)
+    ov = spec.get("overhead")
+    if ov:
+        for k, v in ov.items():
+            q = Quantity.parse(v)
+            if k in res:
+                res[k] += _val(k, q)
+            elif _is_scalar(k):
+                scal[k] = scal.get(k, 0) + q.int_value()
+            if k == "cpu":
+                n0c += q.milli_value(); scc += q.int_value()
+            if k == "memory":
+                n0m += q.int_value(); scm += q.int_value()
+    has = res["cpu"] != 0 or res["memory"] != 0 or res["ephemeral-storage"] != 0 or len(scal) > 0
+    return res, scal, n0c, n0m, scc, scm, has
+
+
+def pod_requests_and_limits(spec) -> Dict[str, Quantity]:
+    reqs: Dict[str, Quantity] = {}
+    for c in spec.get("containers") or []:
+        for k, q in _rl(c).items():
+            if k in reqs:
+                reqs[k].add(q)
+            else:
+                reqs[k] = q.copy()
+    for c in spec.get("initContainers") or []:
+        for k, q in _rl(c).items():
+            if k not in reqs or q.cmp(reqs[k]) > 0:
+                reqs[k] = q.copy()
+    for k, v in (spec.get("overhead") or {}).items():
+        q = Quantity.parse(v)
+        if k in reqs:
+            reqs[k].add(q)
+        else:
+            reqs[k] = q.copy()
+    return reqs
+
+
+def simon_raw(reqs: Dict[str, Quantity], node) -> int:
+    if not reqs:
+        return 100
+    res = 0.0
+    for name, v in ((node.get("status") or {}).get("allocatable") or {}).items():
+        aq = Quantity.parse(v)
+        pq = reqs.get(name) or Quantity()
+        aq.sub(pq)
+        a, t = pq.as_approximate_float64(), aq.as_approximate_float64()
+        share = (0.0 if a == 0 else 1.0) if t == 0 else a / t
+        if share > res:
+            res = share
+    return _f2i(100.0 * res)
+
+
+# ---- the simulator -----------------------------------------------------------------------------------------
+
+class NodeState:
+    def __init__(self, node):
+        self.node = node
+        self.name = node["metadata"].get("name", "")
+        self.labels = node["metadata"].get("labels") or {}
+        st = node.get("status") or {}
+        al = {k: Quantity.parse(v) for k, v in (st.get("allocatable") or {}).items()}
+        self.alloc = {"cpu": 0, "memory": 0, "ephemeral-storage": 0}
+        self.alloc_scalar: Dict[str, int] = {}
+        self.alloc_pods = 0
+        for k, q in al.items():
+            if k in self.alloc:
+                self.alloc[k] += _val(k, q)
+            elif k == "pods":
+                self.alloc_pods += q.int_value()
+            elif _is_scalar(k):
+                self.alloc_scalar[k] = self.alloc_scalar.get(k, 0) + q.int_value()
+        self.req = {"cpu": 0, "memory": 0, "ephemeral-storage": 0}
+        self.req_scalar: Dict[str, int] = {}
+        self.nz_cpu = 0
+        self.nz_mem = 0
+        self.pods: List = []      # list of pod dicts (templates) placed here
+        self.ports = set()
+        cap = {k: Quantity.parse(v) for k, v in (st.get("capacity") or {}).items()}
+        self.gpu_total = cap["alibabacloud.com/gpu-mem"].int_value() if "alibabacloud.com/gpu-mem" in cap else 0
+        self.gpu_n = cap["alibabacloud.com/gpu-count"].int_value() if "alibabacloud.com/gpu-count" in cap else 0
+        self.gpu_dev = self.gpu_total // self.gpu_n if self.gpu_n else 0
+        self.gpu_used = [0] * self.gpu_n
+        self.taints = (node.get("spec") or {}).get("taints") or []
+        self.unschedulable = bool((node.get("spec") or {}).get("unschedulable"))
+
+
+def _ports(spec):
+    out = []
+    for c in spec.get("containers") or []:
+        for p in c.get("ports") or []:
+            hp = int(p.get("hostPort") or 0)
+            if hp > 0:
+                out.append((p.get("hostIP") or "0.0.0.0", p.get("protocol") or "TCP", hp))
+    return out
+
+
+def _port_conflict(used, want) -> bool:
+    ip, proto, port = want
+    if ip == "0.0.0.0":
+        return any(pr == proto and po == port for (_i, pr, po) in used)
+    return ("0.0.0.0", proto, port) in used or (ip, proto, port) in used
+
+
+def _terms(pod, kind, req=True):
+    aff = (pod.get("spec") or {}).get("affinity") or {}
+    a = aff.get(kind) or {}
+    ns0 = pod["metadata"].get("namespace") or "default"
+    if req:
+        lst = a.get("requiredDuringSchedulingIgnoredDuringExecution") or []
+        return [((set(t.get("namespaces") or []) or {ns0}), _sel_reqs(t.get("labelSelector")), t.get("topologyKey", "")) for t in lst]
+    lst = a.get("preferredDuringSchedulingIgnoredDuringExecution") or []
+    out = []
+    for wt in lst:
+        t = wt.get("podAffinityTerm") or {}
+        out.append(((set(t.get("namespaces") or []) or {ns0}), _sel_reqs(t.get("labelSelector")), t.get("topologyKey", ""), int(wt.get("weight") or 0)))
+    return out
+
+
+def _pod_matches(pod, nsset, reqs) -> bool:
+    return (pod["metadata"].get("namespace") or "default") in nsset and _sel_match(reqs, pod["metadata"].get("labels") or {})
+
+
+def _gpu_req(pod):
+    ann = pod["metadata"].get("annotations") or {}
+    mem = num = 0
+    if "alibabacloud.com/gpu-mem" in ann:
+        try:
+            mem = Quantity.parse(str(ann["alibabacloud.com/gpu-mem"])).int_value()
+        except Exception:
+            mem = 0
+    if "alibabacloud.com/gpu-count" in ann:
+        try:
+            v = int(str(ann["alibabacloud.com/gpu-count"]))
+            num = v if v >= 0 else 0
+        except ValueError:
+            pass
+    return mem, num
+
+
+def _gpu_allocate(ns: NodeState, mem, num):
+    if mem <= 0 or num <= 0 or ns.gpu_n <= 0:
+        return None
+    avail = [ns.gpu_dev - u for u in ns.gpu_used]
+    if num == 1:
+        cand = None
+        for d, a in enumerate(avail):
+            if a >= mem and (cand is None or a < avail[cand]):
+                cand = d
+        return None if cand is None else [cand]
+    out = []
+    d = 0
+    while d < ns.gpu_n and len(out) < num:
+        if avail[d] >= mem:
+            out.append(d)
+            avail[d] -= mem
+        else:
+            d += 1
+    return out if len(out) == num else None
+
+
+class PyRef:
+    """Schedules pods one at a time over dict objects. nodes must already be in snapshot (nodeTree.list) order."""
+
+    def __init__(self, nodes: List[dict], services=None, replicasets=None, statefulsets=None):
+        self.nodes = [NodeState(n) for n in nodes]
+        self.by_name = {n.name: n for n in self.nodes}
+        self.services = services or []
+        self.replicasets = replicasets or []
+        self.statefulsets = statefulsets or []
+
+    # -- helper.DefaultSelector
+    def default_selector(self, pod):
+        ns = pod["metadata"].get("namespace") or "default"
+        labels = pod["metadata"].get("labels") or {}
+        merged = {}
+        for s in self.services:
+            if (s["metadata"].get("namespace") or "default") != ns:
+                continue
+            sel = (s.get("spec") or {}).get("selector")
+            if sel is None:
+                continue
+            if all(k in labels and str(labels[k]) == str(v) for k, v in sel.items()):
+                merged.update({k: str(v) for k, v in sel.items()})
+        reqs = [(k, "In", [v]) for k, v in sorted(merged.items())]
+        if labels:
+            for owners in (self.replicasets, self.statefulsets):
+                for o in owners:
+                    if (o["metadata"].get("namespace") or "default") != ns:
+                        continue
+                    r = _sel_reqs((o.get("spec") or {}).get("selector"))
+                    if not r or not _sel_match(r, labels):
+                        continue
+                    reqs.extend(r)
+        return reqs
+
+    def constraints(self, pod, action):
+        spec = pod.get("spec") or {}
+        tsc = spec.get("topologySpreadConstraints") or []
+        if tsc:
+            return [(c.get("topologyKey", ""), int(c.get("maxSkew") or 0), _sel_reqs(c.get("labelSelector")))
+                    for c in tsc if c.get("whenUnsatisfiable") == action]
+        if action != "ScheduleAnyway":
+            return []
+        sel = self.default_selector(pod)
+        if not sel:
+            return []
+        return [(HOSTNAME, 3, sel), (ZONE, 5, sel)]
+
+    @staticmethod
+    def count_match(ns: NodeState, reqs, namespace) -> int:
+        return sum(1 for p in ns.pods if (p["metadata"].get("namespace") or "default") == namespace
+                   and _sel_match(reqs, p["metadata"].get("labels") or {}))
+
+    def commit(self, pod, ns: NodeState):
+        spec = pod.get("spec") or {}
+        res, scal, n0c, n0m, _, _, _ = pod_request(spec)
+        for k in ns.req:
+            ns.req[k] += res[k]
+        for k, v in scal.items():
+            ns.req_scalar[k] = ns.req_scalar.get(k, 0) + v
+        ns.nz_cpu += n0c
+        ns.nz_mem += n0m
+        for p in _ports(spec):
+            ns.ports.add(p)
+        mem, num = _gpu_req(pod)
+        if mem > 0:
+            slots = _gpu_allocate(ns, mem, num)
+            for d in slots or []:
+                ns.gpu_used[d] += mem
+        ns.pods.append(pod)
+
+    def schedule_one(self, pod, detail: Optional[dict] = None):
+        """-> (node index or -1, total score, fail reasons histogram)."""
+        spec = pod.get("spec") or {}
+        pns = pod["metadata"].get("namespace") or "default"
+        plabels = pod["metadata"].get("labels") or {}
+        tols = spec.get("tolerations") or []
+        res, scal, _n0c, _n0m, scc, scm, has_req = pod_request(spec)
+        want_ports = _ports(spec)
+        gmem, gnum = _gpu_req(pod)
+        nodes = self.nodes
+        sel_ok = [_node_sel_ok(spec, n.node) for n in nodes]
+
+        # PodTopologySpread PreFilter
+        hard = self.constraints(pod, "DoNotSchedule")
+        tp_cnt: Dict = {}
+        crit: Dict[str, int] = {}
+        if hard:
+            for i, n in enumerate(nodes):
+                if not sel_ok[i] or not all(k in n.labels for (k, _, _) in hard):
+                    continue
+                for (k, _, _) in hard:
+                    tp_cnt[(k, str(n.labels[k]))] = 0
+            for n in nodes:
+                for (k, _, reqs) in hard:
+                    pair = (k, str(n.labels.get(k, "")))
+                    if pair in tp_cnt:
+                        tp_cnt[pair] += self.count_match(n, reqs, pns)
+            for (k, _, _) in hard:
+                crit[k] = min([v for (kk, _v), v in tp_cnt.items() if kk == k] or [(1 << 31) - 1])
+        # InterPodAffinity PreFilter
+        aff_terms = _terms(pod, "podAffinity")
+        anti_terms = _terms(pod, "podAntiAffinity")
+        exist_map: Dict = {}
+        aff_map: Dict = {}
+        anti_map: Dict = {}
+        for n in nodes:
+            for ep in n.pods:
+                for (nsset, reqs, key) in _terms(ep, "podAntiAffinity"):
+                    if _pod_matches(pod, nsset, reqs) and key in n.labels:
+                        exist_map[(key, str(n.labels[key]))] = exist_map.get((key, str(n.labels[key])), 0) + 1
+                if aff_terms and all(_pod_matches(ep, nsset, reqs) for (nsset, reqs, _k) in aff_terms):
+                    for (_ns, _r, key) in aff_terms:
+                        if key in n.labels:
+                            aff_map[(key, str(n.labels[key]))] = aff_map.get((key, str(n.labels[key])), 0) + 1
+                for (nsset, reqs, key) in anti_terms:
+                    if _pod_matches(ep, nsset, reqs) and key in n.labels:
+                        anti_map[(key, str(n.labels[key]))] = anti_map.get((key, str(n.labels[key])), 0) + 1
+        self_match_all = bool(aff_terms) and all(_pod_matches(pod, nsset, reqs) for (nsset, reqs, _k) in aff_terms)
+
+        codes = []
+        reasons_all = []
+        for i, n in enumerate(nodes):
+            reasons: List[str] = []
+            tol_unsched = any(_tolerates(t, {"key": "node.kubernetes.io/unschedulable", "effect": "NoSchedule"}) for t in tols)
+            if n.unschedulable and not tol_unsched:
+                reasons = ["static"]
+            elif (spec.get("nodeName") or "") and spec["nodeName"] != n.name:
+                reasons = ["static"]
+            elif any(t.get("effect") in ("NoSchedule", "NoExecute") and not any(_tolerates(x, t) for x in tols) for t in n.taints):
+                reasons = ["static"]
+            elif not sel_ok[i]:
+                reasons = ["static"]
+            elif any(_port_conflict(n.ports, w) for w in want_ports):
+                reasons = ["ports"]
+            else:
+                if len(n.pods) + 1 > n.alloc_pods:
+                    reasons.append("Too many pods")
+                if has_req:
+                    if n.alloc["cpu"] < res["cpu"] + n.req["cpu"]:
+                        reasons.append("Insufficient cpu")
+                    if n.alloc["memory"] < res["memory"] + n.req["memory"]:
+                        reasons.append("Insufficient memory")
+                    if n.alloc["ephemeral-storage"] < res["ephemeral-storage"] + n.req["ephemeral-storage"]:
+                        reasons.append("Insufficient ephemeral-storage")
+                    for k, v in scal.items():
+                        if n.alloc_scalar.get(k, 0) < v + n.req_scalar.get(k, 0):
+                            reasons.append("Insufficient " + k)
+            if not reasons:
+                for (k, skew, reqs) in hard:
+                    if k not in n.labels:
+                        reasons = ["pts-missing"]
+                        break
+                    selfm = 1 if _sel_match(reqs, plabels) else 0
+                    m = tp_cnt.get((k, str(n.labels[k])), 0)
+                    if m + selfm - crit[k] > skew:
+                        reasons = ["pts-skew"]
+                        break
+            if not reasons and aff_terms:
+                ok = True
+                pods_exist = True
+                for (_ns, _r, key) in aff_terms:
+                    if key in n.labels:
+                        if aff_map.get((key, str(n.labels[key])), 0) <= 0:
+                            pods_exist = False
+                    else:
+                        ok = False
+                        break
+                if ok and not pods_exist:
+                    ok = len(aff_map) == 0 and self_match_all
+                if not ok:
+                    reasons = ["ipa-aff"]
+            if not reasons:
+                for (_ns, _r, key) in anti_terms:
+                    if key in n.labels and anti_map.get((key, str(n.labels[key])), 0) > 0:
+                        reasons = ["ipa-anti"]
+                        break
+            if not reasons and exist_map:
+                for k, v in n.labels.items():
+                    if exist_map.get((k, str(v)), 0) > 0:
+                        reasons = ["ipa-exist"]
+                        break
+            if not reasons and gmem > 0:
+                if n.gpu_total < gmem or _gpu_allocate(n, gmem, gnum) is None:
+                    reasons = ["gpu"]
+            codes.append(0 if not reasons else 1)
+            reasons_all.append(reasons)
+        feas = [i for i, c in enumerate(codes) if c == 0]
+        if not feas:
+            hist: Dict[str, int] = {}
+            for rs in reasons_all:
+                for r in rs:
+                    hist[r] = hist.get(r, 0) + 1
+            return -1, 0, hist
+        # ---- scoring ----
+        soft = self.constraints(pod, "ScheduleAnyway")
+        ignored = set()
+        pair_cnt: Dict = {}
+        topo_size = [0] * len(soft)
+        if soft:
+            for i in feas:
+                n = nodes[i]
+                if not all(k in n.labels for (k, _, _) in soft):
+                    ignored.add(i)
+                    continue
+                for j, (k, _, _) in enumerate(soft):
+                    if k == HOSTNAME:
+                        continue
+                    pair = (k, str(n.labels[k]))
+                    if pair not in pair_cnt:
+                        pair_cnt[pair] = 0
+                        topo_size[j] += 1
+            for i, n in enumerate(nodes):
+                if not sel_ok[i] or not all(k in n.labels for (k, _, _) in soft):
+                    continue
+                for (k, _, reqs) in soft:
+                    pair = (k, str(n.labels[k]))
+                    if pair in pair_cnt:
+                        pair_cnt[pair] += self.count_match(n, reqs, pns)
+        weights = []
+        for j, (k, _, _) in enumerate(soft):
+            sz = topo_size[j]
+            if k == HOSTNAME:
+                sz = len(feas) - len(ignored)
+            weights.append(go_log(float(sz + 2)))
+        # InterPodAffinity PreScore
+        topo_score: Dict = {}
+        paff = _terms(pod, "podAffinity", req=False)
+        panti = _terms(pod, "podAntiAffinity", req=False)
+
+        def add(key, n, w):
+            if len(n.labels) == 0 or key not in n.labels:
+                return
+            d = topo_score.setdefault(key, {})
+            d[str(n.labels[key])] = d.get(str(n.labels[key]), 0) + w
+
+        for n in nodes:
+            for ep in n.pods:
+                for (nsset, reqs, key, w) in paff:
+                    if _pod_matches(ep, nsset, reqs):
+                        add(key, n, w)
+                for (nsset, reqs, key, w) in panti:
+                    if _pod_matches(ep, nsset, reqs):
+                        add(key, n, -w)
+                for (nsset, reqs, key) in _terms(ep, "podAffinity"):
+                    if _pod_matches(pod, nsset, reqs):
+                        add(key, n, 1)
+                for (nsset, reqs, key, w) in _terms(ep, "podAffinity", req=False):
+                    if _pod_matches(pod, nsset, reqs):
+                        add(key, n, w)
+                for (nsset, reqs, key, w) in _terms(ep, "podAntiAffinity", req=False):
+                    if _pod_matches(pod, nsset, reqs):
+                        add(key, n, -w)
+        sreqs = pod_requests_and_limits(spec)
+        soft_tols = [t for t in tols if not t.get("effect") or t.get("effect") == "PreferNoSchedule"]
+        raw = {}
+        for i in feas:
+            n = nodes[i]
+            r = {}
+            # PTS
+            s = 0
+            if soft and i not in ignored:
+                score = 0.0
+                for j, (k, ms, reqs) in enumerate(soft):
+                    if k in n.labels:
+                        cnt = self.count_match(n, reqs, pns) if k == HOSTNAME else pair_cnt[(k, str(n.labels[k]))]
+                        score += float(cnt) * weights[j] + float(ms - 1)
+                s = _f2i(score)
+            r["pts"] = s
+            # node affinity preferred
+            na = 0
+            aff = spec.get("affinity") or {}
+            for p in ((aff.get("nodeAffinity") or {}).get("preferredDuringSchedulingIgnoredDuringExecution") or []):
+                w = int(p.get("weight") or 0)
+                pref = p.get("preference") or {}
+                if w == 0 or not (pref.get("matchExpressions") or pref.get("matchFields")):
+                    continue
+                if _node_term_match(pref, n.node):
+                    na += w
+            r["na"] = na
+            r["tt"] = sum(1 for t in n.taints if t.get("effect") == "PreferNoSchedule" and not any(_tolerates(x, t) for x in soft_tols))
+            r["simon"] = simon_raw(sreqs, n.node)
+            ip = 0
+            for key, vals in topo_score.items():
+                if key in n.labels:
+                    ip += vals.get(str(n.labels[key]), 0)
+            r["ipa"] = ip
+            raw[i] = r
+        na_max = max([0] + [raw[i]["na"] for i in feas])
+        tt_max = max([0] + [raw[i]["tt"] for i in feas])
+        s_min = min(raw[i]["simon"] for i in feas)
+        s_max = max(raw[i]["simon"] for i in feas)
+        ip_min = min([0] + [raw[i]["ipa"] for i in feas])
+        ip_max = max([0] + [raw[i]["ipa"] for i in feas])
+        pts_vals = [raw[i]["pts"] for i in feas if i not in ignored]
+        pts_min = min(pts_vals) if pts_vals else MAXI64
+        pts_max = max([0] + pts_vals)
+        best, best_i = None, -1
+        for i in feas:
+            n = nodes[i]
+            r = raw[i]
+            cap, rq = n.alloc["cpu"], n.nz_cpu + scc
+            s1 = 0 if cap == 0 or rq > cap else ((cap - rq) * 100) // cap
+            capm, rqm = n.alloc["memory"], n.nz_mem + scm
+            s2 = 0 if capm == 0 or rqm > capm else ((capm - rqm) * 100) // capm
+            la = (s1 + s2) // 2
+            cf = 1.0 if cap == 0 else float(rq) / float(cap)
+            mf = 1.0 if capm == 0 else float(rqm) / float(capm)
+            ba = 0 if cf >= 1 or mf >= 1 else _f2i((1 - abs(cf - mf)) * 100.0)
+            na = r["na"] if na_max == 0 else (100 * r["na"]) // na_max
+            tt = 100 if tt_max == 0 else 100 - (100 * r["tt"]) // tt_max
+            sm = 0 if s_max == s_min else _go_div((r["simon"] - s_min) * 100, s_max - s_min)
+            ip = 0
+            if topo_score and ip_max - ip_min > 0:
+                ip = _f2i(100.0 * (float(r["ipa"] - ip_min) / float(ip_max - ip_min)))
+            if i in ignored:
+                pts = 0
+            elif pts_max == 0:
+                pts = 100
+            else:
+                pts = (100 * (pts_max + pts_min - r["pts"])) // pts_max
+            total = ba + la + ip + na + 2 * pts + tt + 2 * sm + 100 * 10000
+            if detail is not None:
+                detail[i] = dict(ba=ba, la=la, ip=ip, na=na, pts=pts, tt=tt, sm=sm, total=total)
+            if best is None or total > best:
+                best, best_i = total, i
+        return best_i, best, {}
+
+    def run(self, pods: List[dict], fixed: Optional[List[str]] = None):
+        """pods: pod dicts in order. fixed[i]: preset spec.nodeName or ''. -> list of node indices (-1 failed)."""
+        out = []
+        for i, pod in enumerate(pods):
+            nn = fixed[i] if fixed else ""
+            if nn:
+                ns = self.by_name.get(nn)
+                if ns is not None:
+                    self.commit(pod, ns)
+                    out.append(self.nodes.index(ns))
+                else:
+                    out.append(-2)
+                continue
+            idx, _score, _h = self.schedule_one(pod)
+            if idx >= 0:
+                self.commit(pod, self.nodes[idx])
+            out.append(idx)
+        return out
