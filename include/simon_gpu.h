@@ -125,7 +125,9 @@ enum simon_class_word {
     SCW_N_PORTS,
     SCW_OFF_PTS_HARD,   /* DoNotSchedule constraints, 4 words each: counter, topo, maxSkew, selfMatch */
     SCW_N_PTS_HARD,
-    SCW_OFF_PTS_SOFT,   /* ScheduleAnyway constraints, 4 words each: node counter, topo, maxSkew, is_hostname */
+    SCW_OFF_PTS_SOFT,   /* ScheduleAnyway constraints, 5 words each: node counter, topo, maxSkew, is_hostname,
+                           domain counter (-1 for hostname): the same count aggregated per domain over the nodes
+                           eligible for this class (scoring.go:140-166), maintained at commit time */
     SCW_N_PTS_SOFT,
     SCW_OFF_IPA_AFF,    /* required affinity terms, 2 words each: counter (pods matching ALL terms), topo */
     SCW_N_IPA_AFF,
@@ -135,7 +137,9 @@ enum simon_class_word {
     SCW_N_IPA_EXIST,
     SCW_OFF_IPA_SCORE,  /* score terms, 3 words each: counter, topo, weight (signed) */
     SCW_N_IPA_SCORE,
-    SCW_OFF_INC,        /* counters this class's pods increment when placed, 2 words each: counter, topo */
+    SCW_OFF_INC,        /* counters this class's pods increment when placed, 3 words each: counter, topo, sig:
+                           sig = -1, or a class id: increment only if the node is eligible for THAT class
+                           (passes its node selection program and carries all its soft topology keys) */
     SCW_N_INC,
     SCW_HDR_WORDS
 };
@@ -244,6 +248,10 @@ int simon_schedule(simon_ctx *ctx, uint32_t first, uint32_t count,
 
 /* Copy results of the last simon_schedule back (for callers that passed NULL outputs). */
 int simon_results_download(simon_ctx *ctx, uint32_t first, uint32_t count, int32_t *out_node, int64_t *out_score);
+
+/* Run `steps` full passes back to back, each = reset to the empty state + place all uploaded pods, results left on
+ * the device; *out_ms_total = device time of the whole sequence (CUDA events on the ctx stream). */
+int simon_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total);
 
 /* Device time (CUDA events on the ctx stream) of the last simon_schedule / simon_scenarios_run kernel, ms. */
 float simon_last_kernel_ms(simon_ctx *ctx);

@@ -1,0 +1,521 @@
+// simon_api.cu — C ABI of libsimon_gpu.so (include/simon_gpu.h): device memory, uploads, cluster launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "simon_kernel.cuh"
+
+#include "simon_kernel.cu"   // single translation unit: kernel + host API
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T *h, size_t count, cudaStream_t st) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess) return e;
+        if (count && h) return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct ScenState {
+    DevBuf<int64_t> req_mcpu, req_mem, req_eph, nz_mcpu, nz_mem, req_scalar, gpu_used;
+    DevBuf<int32_t> num_pods, cnt, cnt_total, tp, fcount, size;
+    DevBuf<uint8_t> hard_reg;
+    DevBuf<int32_t> out_node;
+    DevBuf<int64_t> out_score;
+    DevBuf<uint32_t> fail_counts, fail_pod, counters;   // counters: [0]=n_fail [1]=n_sched
+    DevBuf<unsigned long long> clk;
+    DevBuf<uint32_t> order;
+    DevBuf<int32_t> rank_of;
+};
+
+}  // namespace
+
+struct simon_ctx {
+    int device = 0;
+    uint32_t opt_cluster = 0, opt_threads = 0, opt_flags = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+    std::string err;
+    bool have_snap = false, have_pods = false;
+    // snapshot
+    uint32_t N = 0, K = 0, WL = 0, WT = 0, T = 0, NC = 0, n_log = 0, max_dom = 1;
+    std::vector<uint32_t> topo_ndom;
+    std::vector<int64_t> h_alloc_mcpu, h_alloc_mem;
+    DevBuf<uint32_t> d_topo_ndom, d_node_flags;
+    DevBuf<int64_t> d_alloc_mcpu, d_alloc_mem, d_alloc_eph, d_alloc_scalar, d_gpu_dev_mem, d_gpu_total_mem;
+    DevBuf<int32_t> d_alloc_pods, d_topo_dom, d_node_class, d_gpu_count;
+    DevBuf<uint64_t> d_label_bits, d_taint_hard, d_taint_soft;
+    DevBuf<double> d_log;
+    // pods
+    uint32_t n_classes = 0, n_pods = 0, n_counters = 0, max_blob_words = 0, emax = 0;
+    uint64_t cnt_words = 0;
+    DevBuf<uint64_t> d_class_off, d_cnt_off;
+    DevBuf<int64_t> d_class_blob, d_simon_raw;
+    DevBuf<int32_t> d_pod_class, d_pod_fixed, d_pod_guard, d_extra;
+    // single-scenario state
+    ScenState st;
+    uint32_t max_fail = 0;
+    DevBuf<SkScenario> d_scen;
+    // multi-scenario state
+    std::vector<ScenState *> scen_states;
+};
+
+namespace {
+
+int fail(simon_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+int alloc_state(simon_ctx *ctx, ScenState &s, uint32_t max_fail, bool scores) {
+    const uint32_t N = ctx->N, K = ctx->K ? ctx->K : 1;
+    CU(s.req_mcpu.alloc(N)); CU(s.req_mem.alloc(N)); CU(s.req_eph.alloc(N)); CU(s.nz_mcpu.alloc(N)); CU(s.nz_mem.alloc(N));
+    CU(s.req_scalar.alloc((size_t)K * N)); CU(s.gpu_used.alloc((size_t)SIMON_MAX_GPU_DEV * N)); CU(s.num_pods.alloc(N));
+    CU(s.cnt.alloc(ctx->cnt_words)); CU(s.cnt_total.alloc(ctx->n_counters));
+    CU(s.tp.alloc((size_t)SK_MAX_SOFT * ctx->max_dom)); CU(s.fcount.alloc((size_t)SK_MAX_SOFT * ctx->max_dom));
+    CU(s.size.alloc(SK_MAX_SOFT)); CU(s.hard_reg.alloc((size_t)SK_MAX_HARD * ctx->max_dom));
+    CU(s.out_node.alloc(ctx->n_pods));
+    if (scores) CU(s.out_score.alloc(ctx->n_pods));
+    CU(s.fail_counts.alloc((size_t)max_fail * SIMON_N_FAIL_CODES)); CU(s.fail_pod.alloc(max_fail)); CU(s.counters.alloc(2));
+    CU(s.clk.alloc(2));
+    return SIMON_OK;
+}
+
+int reset_state(simon_ctx *ctx, ScenState &s) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t N = ctx->N, K = ctx->K ? ctx->K : 1;
+    CU(cudaMemsetAsync(s.req_mcpu.p, 0, 8ull * N, st)); CU(cudaMemsetAsync(s.req_mem.p, 0, 8ull * N, st));
+    CU(cudaMemsetAsync(s.req_eph.p, 0, 8ull * N, st)); CU(cudaMemsetAsync(s.nz_mcpu.p, 0, 8ull * N, st));
+    CU(cudaMemsetAsync(s.nz_mem.p, 0, 8ull * N, st)); CU(cudaMemsetAsync(s.req_scalar.p, 0, 8ull * K * N, st));
+    CU(cudaMemsetAsync(s.gpu_used.p, 0, 8ull * SIMON_MAX_GPU_DEV * N, st)); CU(cudaMemsetAsync(s.num_pods.p, 0, 4ull * N, st));
+    CU(cudaMemsetAsync(s.cnt.p, 0, 4ull * (ctx->cnt_words ? ctx->cnt_words : 1), st));
+    CU(cudaMemsetAsync(s.cnt_total.p, 0, 4ull * (ctx->n_counters ? ctx->n_counters : 1), st));
+    return SIMON_OK;
+}
+
+void fill_scen(simon_ctx *ctx, ScenState &s, SkScenario &o, uint32_t n_active, bool identity) {
+    o.order = identity ? nullptr : s.order.p;
+    o.rank_of = identity ? nullptr : s.rank_of.p;
+    o.n_active = n_active;
+    o.pad = 0;
+    o.req_mcpu = s.req_mcpu.p; o.req_mem = s.req_mem.p; o.req_eph = s.req_eph.p; o.nz_mcpu = s.nz_mcpu.p; o.nz_mem = s.nz_mem.p;
+    o.req_scalar = s.req_scalar.p; o.gpu_used = s.gpu_used.p; o.num_pods = s.num_pods.p; o.cnt = s.cnt.p; o.cnt_total = s.cnt_total.p;
+    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p;
+    o.out_node = s.out_node.p; o.out_score = s.out_score.p;
+    o.fail_counts = s.fail_counts.p; o.fail_pod = s.fail_pod.p; o.n_fail = s.counters.p; o.n_sched = s.counters.p + 1;
+    o.clk = s.clk.p;
+    (void)ctx;
+}
+
+void fill_params(simon_ctx *ctx, SkParams &P) {
+    memset(&P, 0, sizeof(P));
+    P.N = ctx->N; P.K = ctx->K; P.WL = ctx->WL; P.WT = ctx->WT; P.T = ctx->T; P.NC = ctx->NC; P.n_log = ctx->n_log; P.max_dom = ctx->max_dom;
+    P.topo_ndom = ctx->d_topo_ndom.p; P.alloc_mcpu = ctx->d_alloc_mcpu.p; P.alloc_mem = ctx->d_alloc_mem.p; P.alloc_eph = ctx->d_alloc_eph.p;
+    P.alloc_scalar = ctx->d_alloc_scalar.p; P.alloc_pods = ctx->d_alloc_pods.p; P.node_flags = ctx->d_node_flags.p;
+    P.label_bits = ctx->d_label_bits.p; P.taint_hard = ctx->d_taint_hard.p; P.taint_soft = ctx->d_taint_soft.p;
+    P.topo_dom = ctx->d_topo_dom.p; P.node_class = ctx->d_node_class.p; P.gpu_count = ctx->d_gpu_count.p;
+    P.gpu_dev_mem = ctx->d_gpu_dev_mem.p; P.gpu_total_mem = ctx->d_gpu_total_mem.p; P.log_table = ctx->d_log.p;
+    P.n_classes = ctx->n_classes; P.n_pods = ctx->n_pods; P.n_counters = ctx->n_counters; P.max_blob_words = ctx->max_blob_words;
+    P.class_off = ctx->d_class_off.p; P.class_blob = ctx->d_class_blob.p; P.pod_class = ctx->d_pod_class.p;
+    P.pod_fixed = ctx->d_pod_fixed.p; P.pod_guard = ctx->d_pod_guard.p; P.cnt_off = ctx->d_cnt_off.p;
+    P.simon_raw = ctx->d_simon_raw.p; P.extra_score = ctx->d_extra.p;
+    P.emax = ctx->emax;
+}
+
+// choose cluster size / threads / nodes-per-thread for n_active nodes
+int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &TPB, uint32_t &NPT, size_t &smem) {
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    const uint32_t cs_opts[5] = {16, 8, 4, 2, 1};
+    uint32_t want_cs = ctx->opt_cluster;
+    uint32_t tpb = ctx->opt_threads ? ctx->opt_threads : 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (uint32_t ci = 0; ci < 5; ci++) {
+            uint32_t cs = cs_opts[ci];
+            if (want_cs && cs != want_cs) continue;
+            if (!want_cs && pass == 0) {
+                // auto: smallest cluster that keeps <= 2 nodes per thread at 1024 threads
+                if (cs > 1 && (uint64_t)(cs / 2) * 1024 * 2 >= n_active) continue;
+            }
+            uint32_t t = tpb;
+            if (!t) {
+                uint32_t per_cta = (n_active + cs - 1) / cs;
+                t = ((per_cta + 31) / 32) * 32;
+                if (t < 64) t = 64;
+                if (t > 1024) t = 1024;
+            }
+            uint32_t npt = (n_active + cs * t - 1) / (cs * t);
+            if (npt == 0) npt = 1;
+            size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words);
+            if (b <= (size_t)max_smem) { CS = cs; TPB = t; NPT = npt; smem = b; return SIMON_OK; }
+        }
+    }
+    return fail(ctx, SIMON_ERR_LIMIT, "cluster of %u nodes does not fit the shared memory of one 16-CTA cluster", n_active);
+}
+
+int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t TPB, size_t smem, bool record = true) {
+    CU(cudaFuncSetAttribute(simon_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) CU(cudaFuncSetAttribute(simon_place_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_scen * CS, 1, 1);
+    cfg.blockDim = dim3(TPB, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (record) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaLaunchKernelEx(&cfg, simon_place_kernel, P));
+    if (record) CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches++;
+    return SIMON_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int simon_gpu_version(void) { return SIMON_ABI_VERSION; }
+
+const char *simon_last_error(simon_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int simon_ctx_create(const simon_ctx_opts *opts, simon_ctx **out) {
+    if (!out) return SIMON_ERR_INVALID;
+    *out = nullptr;
+    simon_ctx *ctx = new (std::nothrow) simon_ctx();
+    if (!ctx) return SIMON_ERR_NOMEM;
+    if (opts) { ctx->device = opts->device; ctx->opt_cluster = opts->cluster_ctas; ctx->opt_threads = opts->threads_per_cta; ctx->opt_flags = opts->flags; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || ctx->device >= ndev) {
+        // the engine has no CPU path: without a CUDA device the context cannot exist
+        delete ctx;
+        return SIMON_ERR_CUDA;
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return SIMON_ERR_CUDA;
+    }
+    *out = ctx;
+    return SIMON_OK;
+}
+
+void simon_ctx_destroy(simon_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto *s : ctx->scen_states) delete s;
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int simon_snapshot_upload(simon_ctx *ctx, const simon_snapshot *s) {
+    if (!ctx || !s) return SIMON_ERR_INVALID;
+    if (s->n_scalars > SIMON_MAX_SCALARS || s->n_label_words > SIMON_MAX_LABEL_WORDS || s->n_taint_words > SIMON_MAX_TAINT_WORDS ||
+        s->n_topos > SIMON_MAX_TOPOS || s->n_topos == 0)
+        return fail(ctx, SIMON_ERR_LIMIT, "snapshot exceeds compiled-in limits");
+    if (s->n_nodes >= (1u << 24)) return fail(ctx, SIMON_ERR_LIMIT, "too many nodes");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t N = s->n_nodes;
+    ctx->N = N; ctx->K = s->n_scalars; ctx->WL = s->n_label_words; ctx->WT = s->n_taint_words; ctx->T = s->n_topos;
+    ctx->NC = s->n_node_classes; ctx->n_log = s->n_log;
+    ctx->topo_ndom.assign(s->topo_ndom, s->topo_ndom + s->n_topos);
+    ctx->max_dom = 1;
+    for (uint32_t t = 0; t < s->n_topos; t++) ctx->max_dom = std::max(ctx->max_dom, s->topo_ndom[t]);
+    ctx->h_alloc_mcpu.assign(s->alloc_mcpu, s->alloc_mcpu + N);
+    ctx->h_alloc_mem.assign(s->alloc_mem, s->alloc_mem + N);
+    const uint32_t K1 = ctx->K ? ctx->K : 1;
+    CU(ctx->d_topo_ndom.upload(s->topo_ndom, s->n_topos, st));
+    CU(ctx->d_alloc_mcpu.upload(s->alloc_mcpu, N, st)); CU(ctx->d_alloc_mem.upload(s->alloc_mem, N, st));
+    CU(ctx->d_alloc_eph.upload(s->alloc_eph, N, st)); CU(ctx->d_alloc_scalar.upload(s->alloc_scalar, (size_t)K1 * N, st));
+    CU(ctx->d_alloc_pods.upload(s->alloc_pods, N, st)); CU(ctx->d_node_flags.upload(s->node_flags, N, st));
+    CU(ctx->d_label_bits.upload(s->label_bits, (size_t)ctx->WL * N, st));
+    CU(ctx->d_taint_hard.upload(s->taint_hard, (size_t)ctx->WT * N, st)); CU(ctx->d_taint_soft.upload(s->taint_soft, (size_t)ctx->WT * N, st));
+    CU(ctx->d_topo_dom.upload(s->topo_dom, (size_t)ctx->T * N, st)); CU(ctx->d_node_class.upload(s->node_class, N, st));
+    CU(ctx->d_gpu_count.upload(s->gpu_count, N, st)); CU(ctx->d_gpu_dev_mem.upload(s->gpu_dev_mem, N, st));
+    CU(ctx->d_gpu_total_mem.upload(s->gpu_total_mem, N, st)); CU(ctx->d_log.upload(s->log_table, s->n_log, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->have_snap = true;
+    ctx->have_pods = false;
+    return SIMON_OK;
+}
+
+int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
+    if (!ctx || !p) return SIMON_ERR_INVALID;
+    if (!ctx->have_snap) return fail(ctx, SIMON_ERR_STATE, "simon_pods_upload before simon_snapshot_upload");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->n_classes = p->n_classes; ctx->n_pods = p->n_pods; ctx->n_counters = p->n_counters;
+    // validate classes; derive limits
+    uint32_t max_words = SCW_HDR_WORDS, emax = 0;
+    std::vector<int32_t> guard(p->n_pods ? p->n_pods : 1, -1);
+    for (uint32_t c = 0; c < p->n_classes; c++) {
+        const int64_t *cw = p->class_blob + p->class_off[c];
+        uint64_t words = p->class_off[c + 1] - p->class_off[c];
+        if (words < SCW_HDR_WORDS) return fail(ctx, SIMON_ERR_INVALID, "class %u: truncated record", c);
+        max_words = std::max<uint32_t>(max_words, (uint32_t)words);
+        int64_t e = cw[SCW_N_PORTS] + cw[SCW_N_PTS_HARD] + cw[SCW_N_PTS_SOFT] + cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] +
+                    cw[SCW_N_IPA_EXIST] + cw[SCW_N_IPA_SCORE];
+        if (e > SK_MAX_ENT || cw[SCW_N_PTS_HARD] > SK_MAX_HARD || cw[SCW_N_PTS_SOFT] > SK_MAX_SOFT)
+            return fail(ctx, SIMON_ERR_LIMIT, "class %u: %lld constraint/term entries exceed the engine limit (%d)", c, (long long)e, SK_MAX_ENT);
+        emax = std::max<uint32_t>(emax, (uint32_t)e);
+    }
+    if (max_words > 16384) return fail(ctx, SIMON_ERR_LIMIT, "class record too large");
+    for (uint32_t i = 0; i < p->n_pods; i++) {
+        int32_t c = p->pod_class[i];
+        if (c < 0 || (uint32_t)c >= p->n_classes) return fail(ctx, SIMON_ERR_INVALID, "pod %u: bad class", i);
+        guard[i] = (int32_t)p->class_blob[p->class_off[c] + SCW_GUARD_NODE];
+    }
+    ctx->max_blob_words = max_words;
+    ctx->emax = emax;
+    std::vector<uint64_t> cnt_off(p->n_counters + 1, 0);
+    uint64_t tot = 0;
+    for (uint32_t k = 0; k < p->n_counters; k++) {
+        if (p->counter_topo[k] >= ctx->T) return fail(ctx, SIMON_ERR_INVALID, "counter %u: bad topology", k);
+        cnt_off[k] = tot;
+        tot += ctx->topo_ndom[p->counter_topo[k]];
+    }
+    cnt_off[p->n_counters] = tot;
+    ctx->cnt_words = tot;
+    const uint64_t blob_words = p->class_off[p->n_classes];
+    CU(ctx->d_class_off.upload(p->class_off, p->n_classes + 1, st)); CU(ctx->d_class_blob.upload(p->class_blob, blob_words, st));
+    CU(ctx->d_pod_class.upload(p->pod_class, p->n_pods, st)); CU(ctx->d_pod_fixed.upload(p->pod_fixed_node, p->n_pods, st));
+    CU(ctx->d_pod_guard.upload(guard.data(), p->n_pods, st)); CU(ctx->d_cnt_off.upload(cnt_off.data(), cnt_off.size(), st));
+    CU(ctx->d_simon_raw.upload(p->simon_raw, (size_t)std::max(1u, p->n_static_rows) * ctx->NC, st));
+    CU(ctx->d_extra.upload(p->extra_score, (size_t)std::max(1u, p->n_extra_rows) * std::max(1u, ctx->N), st));
+    CU(cudaStreamSynchronize(st));
+    ctx->max_fail = std::min<uint32_t>(std::max(1u, p->n_pods), 1u << 16);
+    int rc = alloc_state(ctx, ctx->st, ctx->max_fail, (ctx->opt_flags & SIMON_OPT_RECORD_SCORES) != 0);
+    if (rc) return rc;
+    rc = reset_state(ctx, ctx->st);
+    if (rc) return rc;
+    CU(ctx->d_scen.alloc(1));
+    CU(cudaStreamSynchronize(st));
+    ctx->have_pods = true;
+    return SIMON_OK;
+}
+
+int simon_state_reset(simon_ctx *ctx) {
+    if (!ctx || !ctx->have_pods) return ctx ? fail(ctx, SIMON_ERR_STATE, "no pods uploaded") : SIMON_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = reset_state(ctx, ctx->st);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SIMON_OK;
+}
+
+int simon_results_download(simon_ctx *ctx, uint32_t first, uint32_t count, int32_t *out_node, int64_t *out_score) {
+    if (!ctx || !ctx->have_pods) return SIMON_ERR_STATE;
+    if ((uint64_t)first + count > ctx->n_pods) return fail(ctx, SIMON_ERR_INVALID, "range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    if (out_node) CU(cudaMemcpyAsync(out_node, ctx->st.out_node.p + first, 4ull * count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_score && ctx->st.out_score.p)
+        CU(cudaMemcpyAsync(out_score, ctx->st.out_score.p + first, 8ull * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SIMON_OK;
+}
+
+int simon_schedule(simon_ctx *ctx, uint32_t first, uint32_t count, int32_t *out_node, int64_t *out_score,
+                   uint32_t *out_fail_counts, uint32_t *out_fail_pod, uint32_t max_fail, uint32_t *out_n_fail) {
+    if (!ctx) return SIMON_ERR_INVALID;
+    if (!ctx->have_pods) return fail(ctx, SIMON_ERR_STATE, "simon_schedule before uploads");
+    if ((uint64_t)first + count > ctx->n_pods) return fail(ctx, SIMON_ERR_INVALID, "pod range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    if (count == 0) { if (out_n_fail) *out_n_fail = 0; return SIMON_OK; }
+    cudaStream_t st = ctx->stream;
+    uint32_t CS, TPB, NPT;
+    size_t smem;
+    int rc = choose_geometry(ctx, ctx->N, CS, TPB, NPT, smem);
+    if (rc) return rc;
+    SkScenario sc;
+    fill_scen(ctx, ctx->st, sc, ctx->N, true);
+    CU(cudaMemcpyAsync(ctx->d_scen.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->st.fail_counts.p, 0, 4ull * ctx->max_fail * SIMON_N_FAIL_CODES, st));
+    CU(cudaMemsetAsync(ctx->st.counters.p, 0, 8, st));
+    SkParams P;
+    fill_params(ctx, P);
+    P.first = first; P.count = count; P.max_fail = ctx->max_fail; P.npt = NPT; P.scen = ctx->d_scen.p;
+    rc = launch(ctx, P, 1, CS, TPB, smem);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    uint32_t counters[2] = {0, 0};
+    CU(cudaMemcpy(counters, ctx->st.counters.p, 8, cudaMemcpyDeviceToHost));
+    if (out_n_fail) *out_n_fail = counters[0];
+    if (out_node) CU(cudaMemcpy(out_node, ctx->st.out_node.p + first, 4ull * count, cudaMemcpyDeviceToHost));
+    if (out_score && ctx->st.out_score.p) CU(cudaMemcpy(out_score, ctx->st.out_score.p + first, 8ull * count, cudaMemcpyDeviceToHost));
+    uint32_t nf = std::min(std::min(counters[0], max_fail), ctx->max_fail);
+    if (nf && out_fail_counts) CU(cudaMemcpy(out_fail_counts, ctx->st.fail_counts.p, 4ull * nf * SIMON_N_FAIL_CODES, cudaMemcpyDeviceToHost));
+    if (nf && out_fail_pod) CU(cudaMemcpy(out_fail_pod, ctx->st.fail_pod.p, 4ull * nf, cudaMemcpyDeviceToHost));
+    return SIMON_OK;
+}
+
+int simon_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total) {
+    if (!ctx) return SIMON_ERR_INVALID;
+    if (!ctx->have_pods) return fail(ctx, SIMON_ERR_STATE, "simon_replay before uploads");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint32_t CS, TPB, NPT;
+    size_t smem;
+    int rc = choose_geometry(ctx, ctx->N, CS, TPB, NPT, smem);
+    if (rc) return rc;
+    SkScenario sc;
+    fill_scen(ctx, ctx->st, sc, ctx->N, true);
+    CU(cudaMemcpyAsync(ctx->d_scen.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, st));
+    SkParams P;
+    fill_params(ctx, P);
+    P.first = 0; P.count = ctx->n_pods; P.max_fail = ctx->max_fail; P.npt = NPT; P.scen = ctx->d_scen.p;
+    CU(cudaEventRecord(ctx->ev0, st));
+    for (uint32_t s = 0; s < steps; s++) {
+        rc = reset_state(ctx, ctx->st);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(ctx->st.fail_counts.p, 0, 4ull * ctx->max_fail * SIMON_N_FAIL_CODES, st));
+        CU(cudaMemsetAsync(ctx->st.counters.p, 0, 8, st));
+        rc = launch(ctx, P, 1, CS, TPB, smem, false);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev1, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (out_ms_total) *out_ms_total = ctx->last_ms;
+    return SIMON_OK;
+}
+
+float simon_last_kernel_ms(simon_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+uint64_t simon_launch_count(simon_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int simon_state_download(simon_ctx *ctx, int64_t *req_mcpu, int64_t *req_mem, int64_t *req_eph, int64_t *nz_mcpu,
+                         int64_t *nz_mem, int32_t *num_pods) {
+    if (!ctx || !ctx->have_pods) return SIMON_ERR_STATE;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t N = ctx->N;
+    if (req_mcpu) CU(cudaMemcpy(req_mcpu, ctx->st.req_mcpu.p, 8ull * N, cudaMemcpyDeviceToHost));
+    if (req_mem) CU(cudaMemcpy(req_mem, ctx->st.req_mem.p, 8ull * N, cudaMemcpyDeviceToHost));
+    if (req_eph) CU(cudaMemcpy(req_eph, ctx->st.req_eph.p, 8ull * N, cudaMemcpyDeviceToHost));
+    if (nz_mcpu) CU(cudaMemcpy(nz_mcpu, ctx->st.nz_mcpu.p, 8ull * N, cudaMemcpyDeviceToHost));
+    if (nz_mem) CU(cudaMemcpy(nz_mem, ctx->st.nz_mem.p, 8ull * N, cudaMemcpyDeviceToHost));
+    if (num_pods) CU(cudaMemcpy(num_pods, ctx->st.num_pods.p, 4ull * N, cudaMemcpyDeviceToHost));
+    return SIMON_OK;
+}
+
+int simon_scenarios_run(simon_ctx *ctx, const simon_scenario *scen, uint32_t n, simon_scenario_result *out, int32_t *out_node) {
+    if (!ctx || !scen || !out) return SIMON_ERR_INVALID;
+    if (!ctx->have_pods) return fail(ctx, SIMON_ERR_STATE, "simon_scenarios_run before uploads");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n == 0) return SIMON_OK;
+    while (ctx->scen_states.size() < n) {
+        ScenState *s = new (std::nothrow) ScenState();
+        if (!s) return SIMON_ERR_NOMEM;
+        ctx->scen_states.push_back(s);
+        int rc = alloc_state(ctx, *s, 1, false);
+        if (rc) return rc;
+        CU(s->order.alloc(ctx->N)); CU(s->rank_of.alloc(ctx->N));
+    }
+    uint32_t max_active = 0;
+    std::vector<SkScenario> h(n);
+    std::vector<int32_t> rank(ctx->N);
+    for (uint32_t i = 0; i < n; i++) {
+        ScenState &s = *ctx->scen_states[i];
+        if (scen[i].n_nodes > ctx->N) return fail(ctx, SIMON_ERR_INVALID, "scenario %u: too many nodes", i);
+        std::fill(rank.begin(), rank.end(), -1);
+        for (uint32_t r = 0; r < scen[i].n_nodes; r++) {
+            uint32_t g = scen[i].nodes[r];
+            if (g >= ctx->N || rank[g] != -1) return fail(ctx, SIMON_ERR_INVALID, "scenario %u: bad node list", i);
+            rank[g] = (int32_t)r;
+        }
+        CU(cudaMemcpyAsync(s.order.p, scen[i].nodes, 4ull * scen[i].n_nodes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s.rank_of.p, rank.data(), 4ull * ctx->N, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        int rc = reset_state(ctx, s);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(s.counters.p, 0, 8, st));
+        CU(cudaMemsetAsync(s.clk.p, 0, 16, st));
+        fill_scen(ctx, s, h[i], scen[i].n_nodes, false);
+        h[i].fail_counts = nullptr;
+        max_active = std::max(max_active, scen[i].n_nodes);
+    }
+    CU(ctx->d_scen.upload(h.data(), n, st));
+    uint32_t CS, TPB, NPT;
+    size_t smem;
+    int rc = choose_geometry(ctx, max_active, CS, TPB, NPT, smem);
+    if (rc) return rc;
+    SkParams P;
+    fill_params(ctx, P);
+    P.first = 0; P.count = ctx->n_pods; P.max_fail = 0; P.npt = NPT; P.scen = ctx->d_scen.p;
+    rc = launch(ctx, P, n, CS, TPB, smem);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    std::vector<int64_t> rq(ctx->N), rm(ctx->N);
+    for (uint32_t i = 0; i < n; i++) {
+        ScenState &s = *ctx->scen_states[i];
+        uint32_t counters[2];
+        unsigned long long clk[2];
+        CU(cudaMemcpy(counters, s.counters.p, 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(clk, s.clk.p, 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(rq.data(), s.req_mcpu.p, 8ull * ctx->N, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(rm.data(), s.req_mem.p, 8ull * ctx->N, cudaMemcpyDeviceToHost));
+        simon_scenario_result &o = out[i];
+        memset(&o, 0, sizeof(o));
+        o.n_unscheduled = counters[0];
+        o.n_scheduled = counters[1];
+        for (uint32_t r = 0; r < scen[i].n_nodes; r++) {
+            uint32_t g = scen[i].nodes[r];
+            o.req_mcpu += rq[g]; o.req_mem += rm[g];
+            o.alloc_mcpu += ctx->h_alloc_mcpu[g]; o.alloc_mem += ctx->h_alloc_mem[g];
+        }
+        o.elapsed_ms = (float)((double)(clk[1] - clk[0]) * 1e-6);
+        if (out_node) CU(cudaMemcpy(out_node + (size_t)i * ctx->n_pods, s.out_node.p, 4ull * ctx->n_pods, cudaMemcpyDeviceToHost));
+    }
+    return SIMON_OK;
+}
+
+}  // extern "C"

@@ -690,10 +690,25 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
         group_cache[key] = got
         return got
 
-    counters = _Interner()   # (frozenset S, topo)
+    counters = _Interner()   # (frozenset S, topo, eligibility signature class | None)
 
-    def counter(S: frozenset, t: int) -> int:
-        return counters.get((S, t))
+    def counter(S: frozenset, t: int, sig=None) -> int:
+        return counters.get((S, t, sig))
+
+    # eligibility signature of a class for PodTopologySpread scoring counts (scoring.go:140-166): only pods on
+    # nodes that pass the class's nodeSelector/required node affinity AND carry every soft topology key count.
+    topo_all_present = [bool((topo_dom[t] >= 0).all()) for t in range(T)]
+    elig_rep: Dict[str, int] = {}
+
+    def elig_sig(c: ClassInfo):
+        soft_topos = sorted({topo.ids[k] for (k, _, _) in c.soft})
+        na = ((c.spec.get("affinity") or {}).get("nodeAffinity") or {})
+        restricted = bool(c.spec.get("nodeSelector")) or na.get("requiredDuringSchedulingIgnoredDuringExecution") is not None
+        if not restricted and all(topo_all_present[t] for t in soft_topos):
+            return None
+        key = json.dumps([c.spec.get("nodeSelector"), na.get("requiredDuringSchedulingIgnoredDuringExecution"), soft_topos],
+                         sort_keys=True, default=str)
+        return elig_rep.setdefault(key, c.cid)
 
     # hostname key -> per-node counting for PodTopologySpread scoring (scoring.go:195-198)
     # ---- per-class lists ----
@@ -724,7 +739,9 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
             L["hard"].append((counter(S, topo.ids[key]), topo.ids[key], skew, selfm))
         for (key, skew, reqs) in c.soft:
             S = members(((frozenset([c.namespace]), reqs),))
-            L["soft"].append((counter(S, 0), topo.ids[key], skew, 1 if key == O.LABEL_HOSTNAME else 0))
+            host = 1 if key == O.LABEL_HOSTNAME else 0
+            domk = -1 if host else counter(S, topo.ids[key], elig_sig(c))
+            L["soft"].append((counter(S, 0), topo.ids[key], skew, host, domk))
         if c.aff_req:
             clauses = tuple((ns, reqs) for (ns, reqs, _k) in c.aff_req)
             S = members(clauses)
@@ -762,11 +779,11 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
                     sc[kk] = sc.get(kk, 0) + sign * w
 
     n_counters = len(counters.items)
-    inc_lists: List[List[Tuple[int, int]]] = [[] for _ in range(C)]
-    for kid, (S, t) in enumerate(counters.items):
+    inc_lists: List[List[Tuple[int, int, int]]] = [[] for _ in range(C)]
+    for kid, (S, t, sig) in enumerate(counters.items):
         for cid in S:
-            inc_lists[cid].append((kid, t))
-    counter_topo = np.array([t for (_S, t) in counters.items] or [0], dtype=np.uint32)
+            inc_lists[cid].append((kid, t, -1 if sig is None else sig))
+    counter_topo = np.array([t for (_S, t, _sig) in counters.items] or [0], dtype=np.uint32)
 
     # ---- Simon rows ----
     simon_rows = _Interner()

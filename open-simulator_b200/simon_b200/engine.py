@@ -1,0 +1,170 @@
+"""ctypes binding of libsimon_gpu.so — the C-ABI engine (include/simon_gpu.h).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device can be opened, constructing an
+Engine raises EngineUnavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsimon_gpu.so")
+_LIB = None
+
+EXPORTS = ["simon_gpu_version", "simon_ctx_create", "simon_ctx_destroy", "simon_last_error", "simon_snapshot_upload",
+           "simon_pods_upload", "simon_state_reset", "simon_schedule", "simon_results_download", "simon_last_kernel_ms",
+           "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay"]
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise EngineUnavailable(f"{LIB_PATH} not built: run __graft_entry__.build() (nvcc, sm_100a)")
+    L = C.CDLL(LIB_PATH)
+    L.simon_gpu_version.restype = C.c_int
+    L.simon_ctx_create.restype = C.c_int
+    L.simon_ctx_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.simon_ctx_destroy.argtypes = [C.c_void_p]
+    L.simon_last_error.restype = C.c_char_p
+    L.simon_last_error.argtypes = [C.c_void_p]
+    L.simon_snapshot_upload.restype = C.c_int
+    L.simon_snapshot_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.simon_pods_upload.restype = C.c_int
+    L.simon_pods_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.simon_state_reset.restype = C.c_int
+    L.simon_state_reset.argtypes = [C.c_void_p]
+    L.simon_schedule.restype = C.c_int
+    L.simon_schedule.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_uint32, C.c_void_p]
+    L.simon_results_download.restype = C.c_int
+    L.simon_results_download.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.simon_replay.restype = C.c_int
+    L.simon_replay.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    L.simon_last_kernel_ms.restype = C.c_float
+    L.simon_last_kernel_ms.argtypes = [C.c_void_p]
+    L.simon_launch_count.restype = C.c_uint64
+    L.simon_launch_count.argtypes = [C.c_void_p]
+    L.simon_state_download.restype = C.c_int
+    L.simon_state_download.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.simon_scenarios_run.restype = C.c_int
+    L.simon_scenarios_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    _LIB = L
+    return L
+
+
+class Engine:
+    """One device context holding one compiled cluster (snapshot + ordered pod list)."""
+
+    def __init__(self, compiled, device: int = 0, record_scores: bool = False, cluster_ctas: int = 0,
+                 threads_per_cta: int = 0):
+        L = lib()
+        self.c = compiled
+        self.h = C.c_void_p()
+        opts = abi.SimonCtxOpts(device, cluster_ctas, threads_per_cta, abi.OPT_RECORD_SCORES if record_scores else 0)
+        rc = L.simon_ctx_create(C.byref(opts), C.byref(self.h))
+        if rc != 0 or not self.h:
+            raise EngineUnavailable(f"simon_ctx_create failed (rc={rc}): no usable CUDA device {device}; "
+                                    "the engine has no CPU path")
+        self.record_scores = record_scores
+        self.snap, self.pods, self._keep = abi.marshal(compiled)
+        self._check(L.simon_snapshot_upload(self.h, C.byref(self.snap)))
+        self._check(L.simon_pods_upload(self.h, C.byref(self.pods)))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = lib().simon_last_error(self.h)
+            raise RuntimeError(f"simon engine error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().simon_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._check(lib().simon_state_reset(self.h))
+
+    def schedule(self, first: int = 0, count: Optional[int] = None, max_fail: Optional[int] = None, download: bool = True):
+        """Place pods [first, first+count). Returns (out_node, out_score, fail_counts, fail_pod)."""
+        P = self.c.pods_dims["n_pods"]
+        count = P - first if count is None else count
+        max_fail = min(count, 1 << 16) if max_fail is None else max_fail
+        n_fail = C.c_uint32(0)
+        if not download:
+            self._check(lib().simon_schedule(self.h, first, count, None, None, None, None, 0, C.byref(n_fail)))
+            return None, None, None, None
+        out_node = np.full(count, -9, np.int32)
+        out_score = np.zeros(count, np.int64)
+        fail_counts = np.zeros((max(max_fail, 1), abi.N_FAIL_CODES), np.uint32)
+        fail_pod = np.zeros(max(max_fail, 1), np.uint32)
+        self._check(lib().simon_schedule(self.h, first, count, out_node.ctypes.data,
+                                         out_score.ctypes.data if self.record_scores else None,
+                                         fail_counts.ctypes.data, fail_pod.ctypes.data, max_fail, C.byref(n_fail)))
+        nf = min(n_fail.value, max_fail)
+        return out_node, out_score, fail_counts[:nf], fail_pod[:nf]
+
+    def results(self, first: int = 0, count: Optional[int] = None):
+        P = self.c.pods_dims["n_pods"]
+        count = P - first if count is None else count
+        out_node = np.full(count, -9, np.int32)
+        self._check(lib().simon_results_download(self.h, first, count, out_node.ctypes.data, None))
+        return out_node
+
+    def replay(self, steps: int = 1) -> float:
+        """steps x (reset + place every pod), device-timed; returns total ms. Results stay on the device."""
+        ms = C.c_float(0)
+        self._check(lib().simon_replay(self.h, steps, C.byref(ms)))
+        return float(ms.value)
+
+    def last_kernel_ms(self) -> float:
+        return float(lib().simon_last_kernel_ms(self.h))
+
+    def launch_count(self) -> int:
+        return int(lib().simon_launch_count(self.h))
+
+    def state(self):
+        N = self.c.n_nodes
+        arrs = [np.zeros(N, np.int64) for _ in range(5)] + [np.zeros(N, np.int32)]
+        self._check(lib().simon_state_download(self.h, *[a.ctypes.data for a in arrs]))
+        return dict(zip(["req_mcpu", "req_mem", "req_eph", "nz_mcpu", "nz_mem", "num_pods"], arrs))
+
+    def run_scenarios(self, scenarios: List[np.ndarray], want_nodes: bool = False):
+        """scenarios: list of uint32 arrays (active node indices in scenario order)."""
+        n = len(scenarios)
+        arr = (abi.SimonScenario * n)()
+        keep = []
+        for i, nodes in enumerate(scenarios):
+            a = np.ascontiguousarray(nodes, dtype=np.uint32)
+            keep.append(a)
+            arr[i].n_nodes = len(a)
+            arr[i].nodes = a.ctypes.data
+        res = (abi.SimonScenarioResult * n)()
+        P = self.c.pods_dims["n_pods"]
+        out_node = np.full((n, P), -9, np.int32) if want_nodes else None
+        self._check(lib().simon_scenarios_run(self.h, arr, n, res, out_node.ctypes.data if want_nodes else None))
+        out = [dict(n_unscheduled=r.n_unscheduled, n_scheduled=r.n_scheduled, req_mcpu=r.req_mcpu, alloc_mcpu=r.alloc_mcpu,
+                    req_mem=r.req_mem, alloc_mem=r.alloc_mem, elapsed_ms=r.elapsed_ms) for r in res]
+        return out, out_node

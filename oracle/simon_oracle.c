@@ -178,8 +178,10 @@ static void commit(simon_oracle *o, const int64_t *cw, uint32_t n) {
     for (uint32_t k = 0; k < o->s.n_scalars; k++) o->req_scalar[(uint64_t)k * N + n] += sc[k];
     const int64_t *inc = cw + cw[SCW_OFF_INC];
     for (int64_t i = 0; i < cw[SCW_N_INC]; i++) {
-        int64_t k = inc[2 * i], t = inc[2 * i + 1];
+        int64_t k = inc[3 * i], t = inc[3 * i + 1], sig = inc[3 * i + 2];
         int32_t d = dom_of(o, t, n);
+        if (sig >= 0) continue;   /* eligibility-restricted domain counters are an engine-side cache the oracle
+                                     never reads: it re-aggregates per pod like the reference (scoring.go:140-166) */
         if (d >= 0) { o->cnt[o->cnt_off[k] + (uint32_t)d] += 1; o->cnt_total[k] += 1; }
     }
     if (cw[SCW_GPU_MEM] > 0) {
@@ -336,6 +338,11 @@ static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, u
         return -1;
     }
 
+    if (F == 1) {   /* "When only one node after predicate, just use it." generic_scheduler.go:159-165 */
+        for (uint32_t r = 0; r < NA; r++)
+            if (!o->code[o->order[r]]) { if (out_score) *out_score = 0; return (int64_t)o->order[r]; }
+    }
+
     /* ---- scores over the feasible set ---- */
     /* PodTopologySpread soft constraints (scoring.go:60-250) */
     uint32_t n_ignored = 0;
@@ -347,11 +354,11 @@ static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, u
         o->ignored[n] = 0;
         if (o->code[n]) continue;
         for (int64_t j = 0; j < n_soft; j++)
-            if (dom_of(o, soft[4 * j + 1], n) < 0) o->ignored[n] = 1;
+            if (dom_of(o, soft[5 * j + 1], n) < 0) o->ignored[n] = 1;
         if (o->ignored[n]) n_ignored++;
     }
     for (int64_t j = 0; j < n_soft; j++) {
-        int64_t k = soft[4 * j], t = soft[4 * j + 1], is_host = soft[4 * j + 3];
+        int64_t k = soft[5 * j], t = soft[5 * j + 1], is_host = soft[5 * j + 3];
         int64_t size;
         soft_cnt[j] = NULL;
         if (is_host) {
@@ -374,7 +381,7 @@ static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, u
                 if (!o->sel_ok[n]) continue;
                 int all = 1;
                 for (int64_t jj = 0; jj < n_soft; jj++)
-                    if (dom_of(o, soft[4 * jj + 1], n) < 0) all = 0;
+                    if (dom_of(o, soft[5 * jj + 1], n) < 0) all = 0;
                 if (!all) continue;
                 int32_t d = dom_of(o, t, n);
                 if (reg[d]) tp[d] += cnt_at(o, k, (int32_t)n);
@@ -394,7 +401,7 @@ static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, u
         if (!o->ignored[n] && n_soft > 0) {
             double score = 0.0;
             for (int64_t j = 0; j < n_soft; j++) {
-                int64_t k = soft[4 * j], t = soft[4 * j + 1], ms = soft[4 * j + 2], is_host = soft[4 * j + 3];
+                int64_t k = soft[5 * j], t = soft[5 * j + 1], ms = soft[5 * j + 2], is_host = soft[5 * j + 3];
                 int64_t c = is_host ? (int64_t)cnt_at(o, k, (int32_t)n) : soft_cnt[j][dom_of(o, t, n)];
                 double sfc = (double)c * soft_w[j] + (double)(ms - 1);
                 score = score + sfc;

@@ -1,0 +1,27 @@
+"""Shared helpers for the tests: build a plan + compiled cluster from a synthetic config."""
+import numpy as np
+
+from simon_b200 import simulator, synth
+from simon_b200.compiler import compile_cluster
+
+
+def make_case(kind="c3", **kw):
+    cluster, apps = (synth.make_c3 if kind == "c3" else synth.make_c2)(**kw)
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    return p, c
+
+
+def run_oracle(c):
+    from oracle.binding import Oracle
+    o = Oracle(c)
+    out = o.schedule()
+    st = o.state()
+    o.close()
+    return out, st
+
+
+def run_pyref(p, c):
+    from oracle.pyref import PyRef
+    ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets)
+    return np.array(ref.run([x.tmpl.pod for x in p.pods], [x.node_name for x in p.pods]), dtype=np.int32)
