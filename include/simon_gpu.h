@@ -116,6 +116,8 @@ enum simon_class_word {
     SCW_EXTRA_ROW,      /* row of extra_score or -1 (ImageLocality 0, NodePreferAvoidPods 100) */
     SCW_GUARD_NODE,     /* -1, or the node a DaemonSet pod was generated for: in a scenario where that node is
                            inactive the pod does not exist (pkg/utils/utils.go:337-351) */
+    SCW_STATIC_SIG,     /* id of the class's static signature (tolerations, node selection + preference programs,
+                           nodeName, topology keys): classes sharing it share the per-node static verdicts */
     SCW_OFF_SCALARS,    /* K words: dense scalar requests */
     SCW_OFF_TOL,        /* 2*WT words: tolerated hard taint atoms, tolerated soft taint atoms */
     SCW_OFF_SEL,        /* node selection program (nodeSelector + required node affinity), see below */
@@ -141,6 +143,12 @@ enum simon_class_word {
                            sig = -1, or a class id: increment only if the node is eligible for THAT class
                            (passes its node selection program and carries all its soft topology keys) */
     SCW_N_INC,
+    SCW_OFF_ENT,        /* engine entry table, 8 words per entry in the order ports, hard, soft, aff, anti, exist, score:
+                           kind, counter, topo, a (maxSkew | weight), b (selfMatch | is_hostname), inc (this class's pods
+                           increment the counter), bitmask word offset (-1: table method), offset of the counter in the
+                           engine's counter array (prefix sum of topo_ndom over counter ids) */
+    SCW_N_ENT,
+    SCW_ANY_TABLE,      /* some soft constraint's topology is too large for the per-decision domain bitmask */
     SCW_HDR_WORDS
 };
 
@@ -168,7 +176,7 @@ typedef struct simon_podset {
     uint32_t n_counters;
     uint32_t n_static_rows;
     uint32_t n_extra_rows;
-    uint32_t reserved;
+    uint32_t n_static_sigs;   /* distinct SCW_STATIC_SIG values */
     const uint64_t *class_off;     /* [n_classes+1] offsets into class_blob, in words */
     const int64_t *class_blob;
     const int32_t *pod_class;      /* [P] */
@@ -252,6 +260,11 @@ int simon_results_download(simon_ctx *ctx, uint32_t first, uint32_t count, int32
 /* Run `steps` full passes back to back, each = reset to the empty state + place all uploaded pods, results left on
  * the device; *out_ms_total = device time of the whole sequence (CUDA events on the ctx stream). */
 int simon_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total);
+
+/* Counters of the last single-scenario kernel: out8[0] decisions, [1] pod-class switches, [2] feasible-set summary
+ * rebuilds, [3] decisions redone after a feasibility flip, [4] static evaluations; [8..19] SM cycles spent per
+ * kernel phase by the leader thread. out32 must hold 32 words. */
+int simon_stats(simon_ctx *ctx, uint64_t *out32);
 
 /* Device time (CUDA events on the ctx stream) of the last simon_schedule / simon_scenarios_run kernel, ms. */
 float simon_last_kernel_ms(simon_ctx *ctx);

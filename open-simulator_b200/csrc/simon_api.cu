@@ -42,6 +42,7 @@ struct DevBuf {
 struct ScenState {
     DevBuf<int64_t> req_mcpu, req_mem, req_eph, nz_mcpu, nz_mem, req_scalar, gpu_used;
     DevBuf<int32_t> num_pods, cnt, cnt_total, tp, fcount, size;
+    DevBuf<long long> csum;
     DevBuf<uint8_t> hard_reg;
     DevBuf<int32_t> out_node;
     DevBuf<int64_t> out_score;
@@ -81,6 +82,8 @@ struct simon_ctx {
     ScenState st;
     uint32_t max_fail = 0;
     DevBuf<SkScenario> d_scen;
+    DevBuf<unsigned long long> d_stats, d_scache;
+    uint32_t n_sigs = 1, use_scache = 0;
     // multi-scenario state
     std::vector<ScenState *> scen_states;
 };
@@ -110,6 +113,8 @@ int alloc_state(simon_ctx *ctx, ScenState &s, uint32_t max_fail, bool scores) {
     CU(s.cnt.alloc(ctx->cnt_words)); CU(s.cnt_total.alloc(ctx->n_counters));
     CU(s.tp.alloc((size_t)SK_MAX_SOFT * ctx->max_dom)); CU(s.fcount.alloc((size_t)SK_MAX_SOFT * ctx->max_dom));
     CU(s.size.alloc(SK_MAX_SOFT)); CU(s.hard_reg.alloc((size_t)SK_MAX_HARD * ctx->max_dom));
+    CU(s.csum.alloc((size_t)ctx->n_classes * SK_CSUM_W));
+    CU(cudaMemsetAsync(s.csum.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * SK_CSUM_W), ctx->stream));
     CU(s.out_node.alloc(ctx->n_pods));
     if (scores) CU(s.out_score.alloc(ctx->n_pods));
     CU(s.fail_counts.alloc((size_t)max_fail * SIMON_N_FAIL_CODES)); CU(s.fail_pod.alloc(max_fail)); CU(s.counters.alloc(2));
@@ -136,7 +141,7 @@ void fill_scen(simon_ctx *ctx, ScenState &s, SkScenario &o, uint32_t n_active, b
     o.pad = 0;
     o.req_mcpu = s.req_mcpu.p; o.req_mem = s.req_mem.p; o.req_eph = s.req_eph.p; o.nz_mcpu = s.nz_mcpu.p; o.nz_mem = s.nz_mem.p;
     o.req_scalar = s.req_scalar.p; o.gpu_used = s.gpu_used.p; o.num_pods = s.num_pods.p; o.cnt = s.cnt.p; o.cnt_total = s.cnt_total.p;
-    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p;
+    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p; o.csum = s.csum.p;
     o.out_node = s.out_node.p; o.out_score = s.out_score.p;
     o.fail_counts = s.fail_counts.p; o.fail_pod = s.fail_pod.p; o.n_fail = s.counters.p; o.n_sched = s.counters.p + 1;
     o.clk = s.clk.p;
@@ -156,6 +161,8 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.pod_fixed = ctx->d_pod_fixed.p; P.pod_guard = ctx->d_pod_guard.p; P.cnt_off = ctx->d_cnt_off.p;
     P.simon_raw = ctx->d_simon_raw.p; P.extra_score = ctx->d_extra.p;
     P.emax = ctx->emax;
+    P.stats = ctx->d_stats.p;
+    P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.scache = ctx->d_scache.p; P.scache_ready = nullptr;
 }
 
 // choose cluster size / threads / nodes-per-thread for n_active nodes
@@ -163,35 +170,42 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     const uint32_t cs_opts[5] = {16, 8, 4, 2, 1};
-    uint32_t want_cs = ctx->opt_cluster;
-    uint32_t tpb = ctx->opt_threads ? ctx->opt_threads : 0;
-    for (int pass = 0; pass < 2; pass++) {
-        for (uint32_t ci = 0; ci < 5; ci++) {
-            uint32_t cs = cs_opts[ci];
-            if (want_cs && cs != want_cs) continue;
-            if (!want_cs && pass == 0) {
-                // auto: smallest cluster that keeps <= 2 nodes per thread at 1024 threads
-                if (cs > 1 && (uint64_t)(cs / 2) * 1024 * 2 >= n_active) continue;
-            }
-            uint32_t t = tpb;
-            if (!t) {
-                uint32_t per_cta = (n_active + cs - 1) / cs;
-                t = ((per_cta + 31) / 32) * 32;
+    const uint32_t want_cs = ctx->opt_cluster, want_t = ctx->opt_threads;
+    if (n_active == 0) n_active = 1;
+    for (uint32_t ci = 0; ci < 5; ci++) {
+        uint32_t cs = cs_opts[ci];
+        if (want_cs) { if (cs != want_cs) continue; }
+        else if (cs > 1 && (uint64_t)(cs / 2) * 256 * 3 >= n_active) continue;   // smallest cluster with <= 3 nodes/thread at 256 threads
+        for (uint32_t npt = 1; npt <= 64; npt++) {
+            uint32_t t;
+            if (want_t) {
+                t = want_t;
+                npt = (n_active + cs * t - 1) / (cs * t);
+            } else {
+                uint32_t per_thread_cta = (n_active + cs * npt - 1) / (cs * npt);
+                t = ((per_thread_cta + 31) / 32) * 32;
                 if (t < 64) t = 64;
-                if (t > 1024) t = 1024;
+                if (t > 256) continue;            // the 256-thread variants keep >= 200 registers/thread (no spills)
             }
-            uint32_t npt = (n_active + cs * t - 1) / (cs * t);
-            if (npt == 0) npt = 1;
             size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words);
             if (b <= (size_t)max_smem) { CS = cs; TPB = t; NPT = npt; smem = b; return SIMON_OK; }
+            if (want_t) break;
         }
     }
     return fail(ctx, SIMON_ERR_LIMIT, "cluster of %u nodes does not fit the shared memory of one 16-CTA cluster", n_active);
 }
 
+typedef void (*sk_kernel_fn)(const SkParams);
+static_assert(sizeof(SkScenario) % 8 == 0, "SkScenario is copied in 8-byte words");
+
 int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t TPB, size_t smem, bool record = true) {
-    CU(cudaFuncSetAttribute(simon_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CS > 8) CU(cudaFuncSetAttribute(simon_place_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    sk_kernel_fn fn;
+    const uint32_t npt = P.npt;
+    if (TPB <= 256) fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
+    else if (TPB <= 512) fn = npt == 1 ? simon_place_kernel_512_1 : npt == 2 ? simon_place_kernel_512_2 : simon_place_kernel_512_0;
+    else fn = npt == 1 ? simon_place_kernel_1024_1 : simon_place_kernel_1024_0;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(n_scen * CS, 1, 1);
@@ -206,7 +220,7 @@ int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t T
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (record) CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    CU(cudaLaunchKernelEx(&cfg, simon_place_kernel, P));
+    CU(cudaLaunchKernelEx(&cfg, fn, P));
     if (record) CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches++;
     return SIMON_OK;
@@ -334,6 +348,16 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     rc = reset_state(ctx, ctx->st);
     if (rc) return rc;
     CU(ctx->d_scen.alloc(1));
+    ctx->n_sigs = std::max(1u, p->n_static_sigs);
+    {
+        size_t words = (size_t)ctx->n_sigs * std::max(1u, ctx->N);
+        ctx->use_scache = words * 8 <= (2ull << 30) ? 1 : 0;      // per-(signature, node) verdict cache, capped at 2 GiB
+        if (!ctx->use_scache) words = 1;
+        CU(ctx->d_scache.alloc(words));
+        CU(cudaMemsetAsync(ctx->d_scache.p, 0, 8ull * words, st));
+    }
+    CU(ctx->d_stats.alloc(32));
+    CU(cudaMemsetAsync(ctx->d_stats.p, 0, 256, st));
     CU(cudaStreamSynchronize(st));
     ctx->have_pods = true;
     return SIMON_OK;
@@ -424,6 +448,13 @@ int simon_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total) {
     if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
     CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     if (out_ms_total) *out_ms_total = ctx->last_ms;
+    return SIMON_OK;
+}
+
+int simon_stats(simon_ctx *ctx, uint64_t *out8) {
+    if (!ctx || !out8 || !ctx->have_pods) return SIMON_ERR_STATE;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(out8, ctx->d_stats.p, 256, cudaMemcpyDeviceToHost));
     return SIMON_OK;
 }
 

@@ -1,4 +1,16 @@
 // simon_kernel.cu — the placement kernel (see simon_kernel.cuh for the design summary).
+//
+// Per pod class the kernel keeps, per node, in shared memory:
+//   static     : first failing static filter, node-selection / topology-key flags, raw NodeAffinity / TaintToleration /
+//                Simon scores (reloaded from a per-(static signature, node) cache in HBM/L2 filled on first use)
+//   own-state  : NodeResourcesFit verdict and LeastAllocated+BalancedAllocation score  -> recomputed only for the
+//                node that just received a pod
+//   counters   : the value of every constraint/term counter at the node's domain       -> bumped by every thread
+//                from the winner's domain vector that travels with the arg-max
+// and, per class, the summary of the feasible set (F, normaliser inputs, topology sizes).  The spread score of a
+// decision is computed speculatively with the summary predicted from the previous decision / previous visit of
+// the class and verified by the same all-reduce that produces its min/max, so the steady state is two cluster
+// all-reduces per decision: {verify + min/max} and {arg-max}.
 #include "simon_kernel.cuh"
 
 // ---- small helpers --------------------------------------------------------------------------------------
@@ -16,6 +28,15 @@ __device__ __forceinline__ unsigned long long sk_globaltimer() {
     return t;
 }
 
+// exact floor(x / d) for 0 <= x < 2^52, d > 0, via the rounded reciprocal inv = 1.0/d and one fix-up step
+__device__ __forceinline__ int64_t div_by(int64_t x, int64_t d, double inv) {
+    int64_t q = (int64_t)((double)x * inv);
+    int64_t r = x - q * d;
+    if (r < 0) q--;
+    else if (r >= d) q++;
+    return q;
+}
+
 struct ReqCtx {
     const uint64_t *label_bits;
     uint32_t N;
@@ -30,6 +51,7 @@ __device__ inline bool req_eval(const int64_t *&p, const ReqCtx &c, uint32_t g) 
     }
     int nw = (int)((head >> 8) & 0xff);
     bool any = false;
+    #pragma unroll 1
     for (int i = 0; i < nw; i++) {
         int64_t wi = *p++;
         uint64_t mask = (uint64_t)*p++;
@@ -41,6 +63,7 @@ __device__ inline bool req_eval(const int64_t *&p, const ReqCtx &c, uint32_t g) 
 __device__ inline bool term_eval(const int64_t *&p, const ReqCtx &c, uint32_t g) {
     int64_t nreq = *p++;
     bool ok = true;
+    #pragma unroll 1
     for (int64_t i = 0; i < nreq; i++)
         if (!req_eval(p, c, g)) ok = false;
     return ok;
@@ -51,29 +74,31 @@ __device__ inline bool selection_ok(const int64_t *cw, const ReqCtx &c, uint32_t
     const int64_t *p = cw + cw[SCW_OFF_SEL];
     bool ok = true;
     int64_t n_ns = *p++;
+    #pragma unroll 1
     for (int64_t q = 0; q < n_ns; q++)
         if (!req_eval(p, c, g)) ok = false;
     int64_t has_required = *p++, n_terms = *p++;
     bool any = false;
+    #pragma unroll 1
     for (int64_t q = 0; q < n_terms; q++)
         if (term_eval(p, c, g)) any = true;
     if (has_required && !any) ok = false;
     return ok;
 }
 
-// eligibility of node g for the spreading counts of class `sig` (scoring.go:140-148): passes the class's node
-// selection and carries every soft topology key of that class
-__device__ inline bool elig_eval(const SkParams &P, int64_t sig, const ReqCtx &c, uint32_t g) {
+// eligibility of node g for the spreading counts of class `sig` (scoring.go:140-148)
+__device__ __noinline__ bool elig_eval(const SkParams &P, int64_t sig, const ReqCtx &c, uint32_t g) {
     const int64_t *cw = P.class_blob + P.class_off[sig];
     if (!selection_ok(cw, c, g)) return false;
     const int64_t *soft = cw + cw[SCW_OFF_PTS_SOFT];
+    #pragma unroll 1
     for (int64_t j = 0; j < cw[SCW_N_PTS_SOFT]; j++)
         if (P.topo_dom[(uint64_t)soft[5 * j + 1] * P.N + g] < 0) return false;
     return true;
 }
 
 // GpuNodeInfo.AllocateGpuId (pkg/type/open-gpu-share/cache/gpunodeinfo.go:232-290); returns slot count, 0 = none
-__device__ inline int gpu_allocate(const SkParams &P, const SkScenario &SC, int64_t req_mem, int64_t req_num, uint32_t g, int *out) {
+__device__ __noinline__ int gpu_allocate(const SkParams &P, const SkScenario &SC, int64_t req_mem, int64_t req_num, uint32_t g, int *out) {
     int ndev = P.gpu_count ? P.gpu_count[g] : 0;
     if (req_mem <= 0 || req_num <= 0 || ndev <= 0) return 0;
     int64_t avail[SIMON_MAX_GPU_DEV];
@@ -82,6 +107,7 @@ __device__ inline int gpu_allocate(const SkParams &P, const SkScenario &SC, int6
     if (req_num == 1) {
         int cand = -1;
         int64_t cm = 0;
+        #pragma unroll 1
         for (int d = 0; d < ndev; d++)
             if (avail[d] >= req_mem && (cand < 0 || avail[d] < cm)) { cand = d; cm = avail[d]; }
         if (cand < 0) return 0;
@@ -97,31 +123,61 @@ __device__ inline int gpu_allocate(const SkParams &P, const SkScenario &SC, int6
 }
 
 #define ENT(row, e) S.ent[(row) * SK_MAX_ENT + (e)]
-enum { ER_KIND = 0, ER_K, ER_T, ER_A, ER_B, ER_INC, ER_WOFF };
+#define A64(k, idx) S.a64[(k) * L + (idx)]
+#define A32(k, idx) S.a32[(k) * L + (idx)]
+#define DOM(t, idx) S.a32[(B_N32 + (t)) * L + (idx)]
+#define VAL(e, idx) S.a32[(B_N32 + T + (e)) * L + (idx)]
+#define A8(k, idx) S.a8[(k) * L + (idx)]
+
+// Per-class uniform state (identical in every thread of the cluster)
+struct ClassState {
+    uint32_t E, n_ports, n_hard, n_soft, n_aff, n_isc;
+    uint32_t e_hard, e_soft, e_aff, e_anti, e_exist, e_isc;
+    uint32_t cflags;
+    bool any_table, has_gpu;
+    int64_t aff_total;
+    // summary of the feasible set
+    bool sum_valid;      // exact for the current feasibility bits
+    bool have_pred;      // soft_sz holds a prediction (previous visit of the class)
+    int64_t F, n_ign, na_max, tt_max, simon_min, simon_max;
+    int64_t nm_na_max, nm_tt_max, nm_simon_min, nm_simon_max;   // normalisers B_SNORM was computed with
+    bool snorm_valid;
+};
 
 // ---------------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const SkParams P) {
+template <int MAXT, int NPT_T>
+__device__ __forceinline__ void simon_place_body(const SkParams &P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t CS = cluster.num_blocks();
     const uint32_t crank = cluster.block_rank();
     const uint32_t scen_id = blockIdx.x / CS;
-    const SkScenario SC = P.scen[scen_id];
     const uint32_t TPB = blockDim.x, tid = threadIdx.x;
     const uint32_t CT = CS * TPB;
     const uint32_t gtid = crank * TPB + tid;
-    const uint32_t NPT = P.npt, L = NPT * TPB;
-    const uint32_t N = P.N, NA = SC.n_active, T = P.T, K = P.K, WT = P.WT;
+    const uint32_t NPT = NPT_T > 0 ? (uint32_t)NPT_T : P.npt, L = NPT * TPB;
+    const uint32_t N = P.N, T = P.T, K = P.K, WT = P.WT;
 
     SkSmem S;
     sk_carve(S, smem_raw, L, T, P.emax, P.max_blob_words);
+    // the scenario descriptor lives in shared memory (kernel-lifetime constant, read after every barrier)
+    if (tid < sizeof(SkScenario) / 8) ((unsigned long long *)S.scen)[tid] = ((const unsigned long long *)(P.scen + scen_id))[tid];
+    __syncthreads();
+    const SkScenario &SC = *S.scen;
+    const uint32_t NA = SC.n_active;
     SkRed R{&S, &cluster, crank, CS, 0};
     const ReqCtx RC{P.label_bits, N};
     const bool leader = (gtid == 0);
+    unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0;
+    long long tk[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#define TICK(slot) do { long long t_now = clock64(); tk[slot] += t_now - t_prev; t_prev = t_now; } while (0)
 
     if (leader && SC.clk) SC.clk[0] = sk_globaltimer();
 
     // ---- load node state into shared memory -----------------------------------------------------------
+    if (tid < SIMON_MAX_TOPOS) S.tnd[tid] = tid < T ? P.topo_ndom[tid] : 0;
+    #pragma unroll 1
     for (uint32_t s = 0; s < NPT; s++) {
         uint32_t idx = s * TPB + tid;
         uint32_t r = s * CT + gtid;
@@ -130,27 +186,168 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
         if (r < NA) {
             g = SC.order ? (int32_t)SC.order[r] : (int32_t)r;
             nf = NF_VALID;
-            S.alloc_mcpu[idx] = P.alloc_mcpu[g]; S.alloc_mem[idx] = P.alloc_mem[g]; S.alloc_eph[idx] = P.alloc_eph[g];
-            S.alloc_pods[idx] = P.alloc_pods[g];
-            S.req_mcpu[idx] = SC.req_mcpu[g]; S.req_mem[idx] = SC.req_mem[g]; S.req_eph[idx] = SC.req_eph[g];
-            S.nz_mcpu[idx] = SC.nz_mcpu[g]; S.nz_mem[idx] = SC.nz_mem[g]; S.num_pods[idx] = SC.num_pods[g];
-            for (uint32_t t = 0; t < T; t++) S.dom[t * L + idx] = P.topo_dom[(uint64_t)t * N + g];
+            int64_t ac = P.alloc_mcpu[g], am = P.alloc_mem[g];
+            A64(A_ALLOC_MCPU, idx) = ac; A64(A_ALLOC_MEM, idx) = am; A64(A_ALLOC_EPH, idx) = P.alloc_eph[g];
+            ((double *)S.a64)[A_INV_MCPU * L + idx] = ac > 0 ? 1.0 / (double)ac : 0.0;
+            ((double *)S.a64)[A_INV_MEM * L + idx] = am > 0 ? 1.0 / (double)am : 0.0;
+            A32(B_ALLOC_PODS, idx) = P.alloc_pods[g];
+            A32(B_NODE_CLASS, idx) = P.node_class[g];
+            A64(A_REQ_MCPU, idx) = SC.req_mcpu[g]; A64(A_REQ_MEM, idx) = SC.req_mem[g]; A64(A_REQ_EPH, idx) = SC.req_eph[g];
+            A64(A_NZ_MCPU, idx) = SC.nz_mcpu[g]; A64(A_NZ_MEM, idx) = SC.nz_mem[g]; A32(B_NUM_PODS, idx) = SC.num_pods[g];
+            #pragma unroll 1
+            for (uint32_t t = 0; t < T; t++) DOM(t, idx) = P.topo_dom[(uint64_t)t * N + g];
         }
-        S.node_g[idx] = g;
-        S.nflags[idx] = nf;
-        S.st_code[idx] = 0;
-        S.regbits[idx] = 0;
+        A32(B_NODE_G, idx) = g;
+        A8(C_NFLAGS, idx) = nf;
+        A8(C_ST_CODE, idx) = 0;
+        A8(C_REGBITS, idx) = 0;
     }
     __syncthreads();
 
     int32_t cur_class = -1;
     uint32_t n_fail = 0, n_sched = 0;
-    // per-class uniform state (identical in every thread)
-    uint32_t E = 0, n_ports = 0, n_hard = 0, n_soft = 0, n_aff = 0, n_isc = 0;
-    uint32_t e_hard = 0, e_soft = 0, e_aff = 0, e_anti = 0, e_exist = 0, e_isc = 0;
-    int64_t aff_total = 0;
-    uint32_t cflags = 0;
-    bool any_table = false;
+    ClassState C;
+    C.sum_valid = false;
+    C.have_pred = false;
+    C.snorm_valid = false;
+    C.n_soft = 0;
+    const int64_t *cw = S.blob;
+
+    // NodeResourcesFit verdict + LeastAllocated + BalancedAllocation of one node for the current class
+    auto own_eval = [&](uint32_t idx) {
+        uint8_t nf = A8(C_NFLAGS, idx);
+        bool fit = !(A32(B_NUM_PODS, idx) + 1 > A32(B_ALLOC_PODS, idx));
+        const int64_t capc = A64(A_ALLOC_MCPU, idx), capm = A64(A_ALLOC_MEM, idx);
+        if (fit && (C.cflags & SIMON_CLS_HAS_REQUEST)) {
+            if (capc < cw[SCW_REQ_MCPU] + A64(A_REQ_MCPU, idx)) fit = false;
+            if (capm < cw[SCW_REQ_MEM] + A64(A_REQ_MEM, idx)) fit = false;
+            if (A64(A_ALLOC_EPH, idx) < cw[SCW_REQ_EPH] + A64(A_REQ_EPH, idx)) fit = false;
+            if (K) {
+                uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+                const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
+                #pragma unroll 1
+                for (uint32_t k = 0; k < K; k++)
+                    if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * N + g] < sc_req[k] + SC.req_scalar[(uint64_t)k * N + g]) fit = false;
+            }
+        }
+        A8(C_NFLAGS, idx) = (nf & ~NF_FIT_OK) | (fit ? NF_FIT_OK : 0);
+        const int64_t rqc = A64(A_NZ_MCPU, idx) + cw[SCW_SCORE_MCPU], rqm = A64(A_NZ_MEM, idx) + cw[SCW_SCORE_MEM];
+        const double ic = ((const double *)S.a64)[A_INV_MCPU * L + idx], im = ((const double *)S.a64)[A_INV_MEM * L + idx];
+        int64_t s1 = (capc == 0 || rqc > capc) ? 0 : div_by((capc - rqc) * 100, capc, ic);
+        int64_t s2 = (capm == 0 || rqm > capm) ? 0 : div_by((capm - rqm) * 100, capm, im);
+        int64_t la = (s1 + s2) / 2;
+        // BalancedAllocation: int64((1 - |cpuFraction - memFraction|) * 100), fractions are correctly rounded quotients
+        // (balanced_allocation.go:82-119).  fraction >= 1  <=>  requested >= capacity for these magnitudes.
+        int64_t ba = 0;
+        if (capc != 0 && capm != 0 && rqc < capc && rqm < capm) {
+            double cf = (double)rqc * ic, mf = (double)rqm * im;        // within 4e-16 of the rounded quotients
+            double x = (1.0 - fabs(cf - mf)) * 100.0;
+            double fl = floor(x);
+            if (x - fl < 1e-7 || fl + 1.0 - x < 1e-7) {                  // too close to an integer: exact path
+                cf = (double)rqc / (double)capc;
+                mf = (double)rqm / (double)capm;
+                x = (1.0 - fabs(cf - mf)) * 100.0;
+                fl = floor(x);
+            }
+            ba = (int64_t)fl;
+        }
+        A32(B_OWN, idx) = (int32_t)(la + ba);
+    };
+
+    // filters on cached state; returns the reason bitmask (0 = feasible). hard_min: global minima of hard constraints.
+    auto filter_node = [&](uint32_t idx, uint8_t nf, const int32_t *hard_min, bool want_reasons) -> uint32_t {
+        if (nf & NF_STATIC_FAIL) return 1u << SFC_STATIC;
+        #pragma unroll 1
+        for (uint32_t e = 0; e < C.n_ports; e++)
+            if (VAL(e, idx) > 0) return 1u << SFC_PORTS;
+        if (!(nf & NF_FIT_OK)) {
+            if (!want_reasons) return 1u << SFC_CPU;
+            uint32_t reasons = 0;
+            if (A32(B_NUM_PODS, idx) + 1 > A32(B_ALLOC_PODS, idx)) reasons |= 1u << SFC_TOO_MANY_PODS;
+            if (C.cflags & SIMON_CLS_HAS_REQUEST) {
+                if (A64(A_ALLOC_MCPU, idx) < cw[SCW_REQ_MCPU] + A64(A_REQ_MCPU, idx)) reasons |= 1u << SFC_CPU;
+                if (A64(A_ALLOC_MEM, idx) < cw[SCW_REQ_MEM] + A64(A_REQ_MEM, idx)) reasons |= 1u << SFC_MEM;
+                if (A64(A_ALLOC_EPH, idx) < cw[SCW_REQ_EPH] + A64(A_REQ_EPH, idx)) reasons |= 1u << SFC_EPH;
+                if (K) {
+                    uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+                    const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
+                    #pragma unroll 1
+                    for (uint32_t k = 0; k < K; k++)
+                        if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * N + g] < sc_req[k] + SC.req_scalar[(uint64_t)k * N + g])
+                            reasons |= 1u << (SFC_SCALAR0 + k);
+                }
+            }
+            return reasons;
+        }
+        #pragma unroll 1
+        for (uint32_t jh = 0; jh < C.n_hard; jh++) {
+            uint32_t e = C.e_hard + jh;
+            int32_t d = DOM(ENT(ER_T, e), idx);
+            if (d < 0) return 1u << SFC_PTS_MISSING;
+            int64_t match = (A8(C_REGBITS, idx) >> jh) & 1 ? VAL(e, idx) : 0;
+            int64_t skew = match + ENT(ER_B, e) - (int64_t)hard_min[jh];
+            if (skew > ENT(ER_A, e)) return 1u << SFC_PTS_SKEW;
+        }
+        if (C.n_aff) {
+            bool pods_exist = true, missing = false;
+            #pragma unroll 1
+            for (uint32_t e = C.e_aff; e < C.e_anti; e++) {
+                if (DOM(ENT(ER_T, e), idx) < 0) { missing = true; break; }
+                if (VAL(e, idx) <= 0) pods_exist = false;
+            }
+            bool ok = true;
+            if (missing) ok = false;
+            else if (!pods_exist) ok = (C.aff_total == 0 && (C.cflags & SIMON_CLS_IPA_SELF_MATCH));
+            if (!ok) return 1u << SFC_IPA_AFF;
+        }
+        #pragma unroll 1
+        for (uint32_t e = C.e_anti; e < C.e_exist; e++)
+            if (DOM(ENT(ER_T, e), idx) >= 0 && VAL(e, idx) > 0) return 1u << SFC_IPA_ANTI;
+        #pragma unroll 1
+        for (uint32_t e = C.e_exist; e < C.e_isc; e++)
+            if (DOM(ENT(ER_T, e), idx) >= 0 && VAL(e, idx) > 0) return 1u << SFC_IPA_EXIST;
+        if (C.has_gpu) {
+            uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+            int slots[64];
+            int64_t total = P.gpu_total_mem ? P.gpu_total_mem[g] : 0;
+            if (total < cw[SCW_GPU_MEM] || gpu_allocate(P, SC, cw[SCW_GPU_MEM], cw[SCW_GPU_COUNT], g, slots) == 0) return 1u << SFC_GPU;
+        }
+        return 0;
+    };
+
+    // PodTopologySpread raw scores with the current weights (scoring.go:175-208); returns local (min, max) encoded
+    auto pts_pass = [&](unsigned long long &lo, unsigned long long &hi) {
+        lo = sk_enc(INT64_MAX);
+        hi = sk_enc(0);
+        if (C.n_soft == 0) return;
+        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+        for (uint32_t s = 0; s < NPT; s++) {
+            uint32_t idx = s * TPB + tid;
+            uint8_t nf = A8(C_NFLAGS, idx);
+            if ((nf & (NF_FEASIBLE | NF_IGNORED)) != NF_FEASIBLE) continue;
+            double score = 0.0;
+            #pragma unroll 1
+            for (uint32_t js = 0; js < C.n_soft; js++) {
+                uint32_t e = C.e_soft + js;
+                double sfc = (double)VAL(e, idx) * S.soft_w[js] + (double)(ENT(ER_A, e) - 1);
+                score = score + sfc;
+            }
+            int64_t raw = f2i(score);
+            A32(B_RAW_PTS, idx) = (int32_t)raw;
+            unsigned long long er = sk_enc(raw);
+            lo = er < lo ? er : lo;
+            hi = er > hi ? er : hi;
+        }
+    };
+
+    int32_t psz[SK_MAX_SOFT];      // topology sizes the current weights were computed from (registers: static indexing only)
+#pragma unroll
+    for (int q = 0; q < SK_MAX_SOFT; q++) psz[q] = 0;
+    auto set_weights = [&]() {
+#pragma unroll
+        for (int js = 0; js < SK_MAX_SOFT; js++)
+            if ((uint32_t)js < C.n_soft) S.soft_w[js] = __ldg(&P.log_table[psz[js] + 2]);
+    };
 
     const uint32_t end = P.first + P.count;
     uint32_t i = P.first;
@@ -163,6 +360,7 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
         if (guard == -2) exists = false;
         else if (guard >= 0) exists = SC.rank_of ? (SC.rank_of[guard] >= 0) : true;
 
+        TICK(0);
         if (!exists || fixed != -1) {
             // ---- batch of pods that bypass scheduling (spec.nodeName preset) or do not exist in this scenario ----
             uint32_t j = i;
@@ -173,9 +371,9 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
                 if (ex2 && f2 == -1) break;
                 j++;
             }
+            #pragma unroll 1
             for (uint32_t q = i; q < j; q++) {
-                int32_t c2 = P.pod_class[q], f2 = P.pod_fixed[q];
-                const int64_t *cw2 = P.class_blob + P.class_off[c2];
+                int32_t f2 = P.pod_fixed[q];
                 int64_t g2 = P.pod_guard[q];
                 bool ex2 = g2 == -2 ? false : (g2 >= 0 ? (SC.rank_of ? SC.rank_of[g2] >= 0 : true) : true);
                 int32_t res;
@@ -187,15 +385,18 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
                     else {
                         res = f2;
                         if ((uint32_t)r % CT == gtid) {       // I own that node: account the pod
+                            const int64_t *cw2 = P.class_blob + P.class_off[P.pod_class[q]];
                             uint32_t idx = ((uint32_t)r / CT) * TPB + tid;
-                            S.req_mcpu[idx] += cw2[SCW_REQ_MCPU]; S.req_mem[idx] += cw2[SCW_REQ_MEM]; S.req_eph[idx] += cw2[SCW_REQ_EPH];
-                            S.nz_mcpu[idx] += cw2[SCW_NZ_MCPU]; S.nz_mem[idx] += cw2[SCW_NZ_MEM]; S.num_pods[idx] += 1;
+                            A64(A_REQ_MCPU, idx) += cw2[SCW_REQ_MCPU]; A64(A_REQ_MEM, idx) += cw2[SCW_REQ_MEM]; A64(A_REQ_EPH, idx) += cw2[SCW_REQ_EPH];
+                            A64(A_NZ_MCPU, idx) += cw2[SCW_NZ_MCPU]; A64(A_NZ_MEM, idx) += cw2[SCW_NZ_MEM]; A32(B_NUM_PODS, idx) += 1;
                             const int64_t *sc = cw2 + cw2[SCW_OFF_SCALARS];
+                            #pragma unroll 1
                             for (uint32_t k = 0; k < K; k++) SC.req_scalar[(uint64_t)k * N + f2] += sc[k];
                             const int64_t *inc = cw2 + cw2[SCW_OFF_INC];
+                            #pragma unroll 1
                             for (int64_t u = 0; u < cw2[SCW_N_INC]; u++) {
                                 int64_t k = inc[3 * u], t = inc[3 * u + 1], sig = inc[3 * u + 2];
-                                int32_t d = S.dom[t * L + idx];
+                                int32_t d = DOM(t, idx);
                                 if (d < 0) continue;
                                 if (sig >= 0 && !elig_eval(P, sig, RC, (uint32_t)f2)) continue;
                                 atomicAdd(&SC.cnt[P.cnt_off[k] + d], 1);
@@ -207,290 +408,387 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
                 if (leader) { SC.out_node[q] = res; if (SC.out_score) SC.out_score[q] = 0; }
             }
             cur_class = -1;
+            TICK(1);
             i = j;
             if (i < end) { nx_cls = P.pod_class[i]; nx_fixed = P.pod_fixed[i]; nx_guard = P.pod_guard[i]; }
             continue;
         }
 
         // =================================================================================================
-        // class change: stage the class record, evaluate everything that is static per (class, node), and
-        // (re)load the cached counter values of this class's constraint/term entries
+        // class change
         // =================================================================================================
         if (cls != cur_class) {
-            // the previous commit's counter updates (global atomics by the owner thread) must be visible
-            __threadfence();
+            st_class++;
+            // remember the summary of the class we leave: it is the prediction for its next visit
+            if (leader && cur_class >= 0 && C.sum_valid && SC.csum) {
+                long long *rec = SC.csum + (uint64_t)cur_class * SK_CSUM_W;
+#pragma unroll
+                for (int js = 0; js < SK_MAX_SOFT; js++) rec[1 + js] = (uint32_t)js < C.n_soft ? psz[js] : 0;
+                rec[0] = 1;
+            }
+            TICK(10);
+            __threadfence();          // the previous commit's counter updates (owner-thread atomics) must be visible
             cluster.sync();
+            TICK(11);
             const int64_t *gw = P.class_blob + P.class_off[cls];
             const uint32_t words = (uint32_t)(P.class_off[cls + 1] - P.class_off[cls]);
+            #pragma unroll 1
             for (uint32_t w = tid; w < words; w += TPB) S.blob[w] = gw[w];
+            // prediction of the topology sizes from the previous visit of this class (any value is safe: verified)
+            long long pred[1 + SK_MAX_SOFT];
+#pragma unroll
+            for (int q = 0; q < 1 + SK_MAX_SOFT; q++) pred[q] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + q) : 0;
             __syncthreads();
-            const int64_t *cw = S.blob;
-            cflags = (uint32_t)cw[SCW_FLAGS];
-            n_ports = (uint32_t)cw[SCW_N_PORTS]; n_hard = (uint32_t)cw[SCW_N_PTS_HARD]; n_soft = (uint32_t)cw[SCW_N_PTS_SOFT];
-            n_aff = (uint32_t)cw[SCW_N_IPA_AFF]; n_isc = (uint32_t)cw[SCW_N_IPA_SCORE];
+            TICK(12);
+            C.cflags = (uint32_t)cw[SCW_FLAGS];
+            C.n_ports = (uint32_t)cw[SCW_N_PORTS]; C.n_hard = (uint32_t)cw[SCW_N_PTS_HARD]; C.n_soft = (uint32_t)cw[SCW_N_PTS_SOFT];
+            C.n_aff = (uint32_t)cw[SCW_N_IPA_AFF]; C.n_isc = (uint32_t)cw[SCW_N_IPA_SCORE];
             const uint32_t n_anti = (uint32_t)cw[SCW_N_IPA_ANTI], n_exist = (uint32_t)cw[SCW_N_IPA_EXIST];
-            e_hard = n_ports; e_soft = e_hard + n_hard; e_aff = e_soft + n_soft; e_anti = e_aff + n_aff;
-            e_exist = e_anti + n_anti; e_isc = e_exist + n_exist; E = e_isc + n_isc;
-            // bitmask word budget for the "number of distinct domains among feasible nodes" of soft constraints
-            any_table = false;
-            {
-                uint32_t woff = 0;
-                const int64_t *q = cw + cw[SCW_OFF_PTS_SOFT];
-                for (uint32_t js = 0; js < n_soft; js++) {
-                    if (q[5 * js + 3]) continue;
-                    uint32_t nw = (P.topo_ndom[q[5 * js + 1]] + 63) / 64;
-                    if (woff + nw <= SK_MAXW) woff += nw; else any_table = true;
-                }
+            C.e_hard = C.n_ports; C.e_soft = C.e_hard + C.n_hard; C.e_aff = C.e_soft + C.n_soft; C.e_anti = C.e_aff + C.n_aff;
+            C.e_exist = C.e_anti + n_anti; C.e_isc = C.e_exist + n_exist; C.E = C.e_isc + C.n_isc;
+            C.has_gpu = cw[SCW_GPU_MEM] > 0;
+            C.sum_valid = false;
+            C.snorm_valid = false;
+            C.any_table = cw[SCW_ANY_TABLE] != 0;
+            C.have_pred = pred[0] == 1;
+#pragma unroll
+            for (int js = 0; js < SK_MAX_SOFT; js++) {
+                long long v = pred[1 + js];
+                psz[js] = (C.have_pred && v >= 0 && v + 2 < (long long)P.n_log) ? (int32_t)v : 0;
             }
-            if (tid < E) {
-                uint32_t e = tid;
-                int32_t kind, k, t, a = 0, b = 0, woff = -1;
-                if (e < e_hard) { kind = EK_PORT; k = (int32_t)cw[cw[SCW_OFF_PORTS] + e]; t = 0; }
-                else if (e < e_soft) { const int64_t *q = cw + cw[SCW_OFF_PTS_HARD] + 4 * (e - e_hard); kind = EK_HARD; k = (int32_t)q[0]; t = (int32_t)q[1]; a = (int32_t)q[2]; b = (int32_t)q[3]; }
-                else if (e < e_aff) {
-                    const int64_t *q0 = cw + cw[SCW_OFF_PTS_SOFT];
-                    const int64_t *q = q0 + 5 * (e - e_soft);
-                    kind = EK_SOFT; t = (int32_t)q[1]; a = (int32_t)q[2]; b = (int32_t)q[3];
-                    k = b ? (int32_t)q[0] : (int32_t)q[4];
-                    if (!b) {
-                        uint32_t wo = 0;
-                        for (uint32_t js = 0; js < e - e_soft; js++)
-                            if (!q0[5 * js + 3]) { uint32_t nw = (P.topo_ndom[q0[5 * js + 1]] + 63) / 64; if (wo + nw <= SK_MAXW) wo += nw; }
-                        uint32_t nw = (P.topo_ndom[t] + 63) / 64;
-                        woff = (wo + nw <= SK_MAXW) ? (int32_t)wo : -1;
-                    }
-                }
-                else if (e < e_anti) { const int64_t *q = cw + cw[SCW_OFF_IPA_AFF] + 2 * (e - e_aff); kind = EK_AFF; k = (int32_t)q[0]; t = (int32_t)q[1]; }
-                else if (e < e_exist) { const int64_t *q = cw + cw[SCW_OFF_IPA_ANTI] + 2 * (e - e_anti); kind = EK_ANTI; k = (int32_t)q[0]; t = (int32_t)q[1]; }
-                else if (e < e_isc) { const int64_t *q = cw + cw[SCW_OFF_IPA_EXIST] + 2 * (e - e_exist); kind = EK_EXIST; k = (int32_t)q[0]; t = (int32_t)q[1]; }
-                else { const int64_t *q = cw + cw[SCW_OFF_IPA_SCORE] + 3 * (e - e_isc); kind = EK_SCORE; k = (int32_t)q[0]; t = (int32_t)q[1]; a = (int32_t)q[2]; }
-                int32_t inc = 0;
-                int32_t tk = (kind == EK_SOFT && b) ? 0 : t;     // hostname constraints count on the node-level counter
-                const int64_t *il = cw + cw[SCW_OFF_INC];
-                for (int64_t u = 0; u < cw[SCW_N_INC]; u++)
-                    if (il[3 * u] == k && il[3 * u + 1] == tk) inc = 1;
-                ENT(ER_KIND, e) = kind; ENT(ER_K, e) = k; ENT(ER_T, e) = t; ENT(ER_A, e) = a; ENT(ER_B, e) = b;
-                ENT(ER_INC, e) = inc; ENT(ER_WOFF, e) = woff;
+            {
+                // the entry table was laid out by the snapshot compiler (SCW_OFF_ENT): 8 words per entry -> 8 rows in smem
+                const int64_t *et = cw + cw[SCW_OFF_ENT];
+#pragma unroll 1
+                for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
             }
             __syncthreads();
-            // node-static evaluation + cached counter values
+            TICK(13);
+            // ---- node-static verdicts: from the per-(static signature, node) cache, or computed and cached ----
+            // All long-latency loads of up to 4 nodes (cache record, Simon row, first 4 counter values each) are issued
+            // back to back before any of them is consumed: the class switch costs ~one memory round trip.
+            const int64_t sig = cw[SCW_STATIC_SIG];
             const int64_t *tol = cw + cw[SCW_OFF_TOL];
             const int64_t *simon_row = P.simon_raw + (uint64_t)cw[SCW_STATIC_ROW] * P.NC;
             const int32_t *extra = cw[SCW_EXTRA_ROW] >= 0 ? P.extra_score + (uint64_t)cw[SCW_EXTRA_ROW] * N : nullptr;
-            for (uint32_t s = 0; s < NPT; s++) {
-                uint32_t idx = s * TPB + tid;
-                uint8_t nf = S.nflags[idx] & NF_VALID;
-                if (!nf) continue;
-                uint32_t g = (uint32_t)S.node_g[idx];
-                bool ok = selection_ok(cw, RC, g);
-                if (ok) nf |= NF_SEL_OK;
-                uint8_t code = 0;
-                if ((P.node_flags[g] & SIMON_NODE_UNSCHEDULABLE) && !(cflags & SIMON_CLS_TOL_UNSCHED)) code = 1;
-                if (!code && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)g) code = 2;
-                if (!code)
-                    for (uint32_t w = 0; w < WT; w++)
-                        if (P.taint_hard[(uint64_t)w * N + g] & ~(uint64_t)tol[w]) code = 3;
-                if (!code && !ok) code = 4;
-                S.st_code[idx] = code;
-                const int64_t *p = cw + cw[SCW_OFF_PREF];
-                int64_t na = 0;
-                for (int64_t q = 0; q < cw[SCW_N_PREF]; q++) { int64_t w = *p++; if (term_eval(p, RC, g)) na += w; }
-                S.raw_na[idx] = (int32_t)na;
-                int tt = 0;
-                for (uint32_t w = 0; w < WT; w++) tt += __popcll(P.taint_soft[(uint64_t)w * N + g] & ~(uint64_t)tol[WT + w]);
-                S.raw_tt[idx] = tt;
-                S.raw_simon[idx] = simon_row[P.node_class[g]];
-                S.extra[idx] = extra ? extra[g] : 1000000;
-                bool hk = true, ign = false;
-                for (uint32_t jh = 0; jh < n_hard; jh++) if (S.dom[ENT(ER_T, e_hard + jh) * L + idx] < 0) hk = false;
-                for (uint32_t js = 0; js < n_soft; js++) if (S.dom[ENT(ER_T, e_soft + js) * L + idx] < 0) ign = true;
-                if (hk) nf |= NF_HARDKEYS;
-                if (ign) nf |= NF_IGNORED;
-                S.nflags[idx] = nf;
-                for (uint32_t e = 0; e < E; e++) {
-                    int32_t kind = ENT(ER_KIND, e), k = ENT(ER_K, e), t = ENT(ER_T, e);
-                    int32_t d = (kind == EK_SOFT && ENT(ER_B, e)) ? (int32_t)g : S.dom[t * L + idx];
-                    S.val[e * L + idx] = d >= 0 ? ldcg32(&SC.cnt[P.cnt_off[k] + d]) : 0;
+            #pragma unroll 1
+            for (uint32_t s0 = 0; s0 < NPT; s0 += 4) {
+                unsigned long long rec4[4];
+                long long sim4[4];
+                int32_t v4[4][4], ex4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t s = s0 + u;
+                    uint32_t idx = s * TPB + tid;
+                    bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
+                    rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) v4[u][e] = 0;
+                    if (valid) {
+                        uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+                        if (P.use_scache) rec4[u] = __ldcg(&P.scache[(uint64_t)sig * N + g]);
+                        sim4[u] = __ldg(&simon_row[A32(B_NODE_CLASS, idx)]);
+                        if (extra) ex4[u] = __ldg(&extra[g]);
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if ((uint32_t)e < C.E) {
+                                int32_t d = (ENT(ER_KIND, e) == EK_SOFT && ENT(ER_B, e)) ? (int32_t)g : DOM(ENT(ER_T, e), idx);
+                                if (d >= 0) v4[u][e] = ldcg32(&SC.cnt[(uint32_t)ENT(ER_BASE, e) + (uint32_t)d]);
+                            }
+                    }
                 }
-                S.regbits[idx] = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t s = s0 + u;
+                    if (s >= NPT) continue;
+                    uint32_t idx = s * TPB + tid;
+                    uint8_t nf = A8(C_NFLAGS, idx) & NF_VALID;
+                    if (!nf) continue;
+                    uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+                    uint8_t code, fl;
+                    int32_t na, tt;
+                    // record = {code:8, flags:8, tt:8, valid:1 (bit 24), na:32 (bits 32..63)}; 8-byte loads/stores are atomic, so a
+                    // record is either absent (computed here and published) or complete, also across concurrent scenarios
+                    unsigned long long rec = rec4[u];
+                    if (rec & (1ull << 24)) {
+                        code = (uint8_t)rec; fl = (uint8_t)(rec >> 8); tt = (int32_t)((rec >> 16) & 0xff); na = (int32_t)(rec >> 32);
+                    } else {
+                        st_slow++;
+                        bool ok = selection_ok(cw, RC, g);
+                        fl = ok ? NF_SEL_OK : 0;
+                        code = 0;
+                        if ((P.node_flags[g] & SIMON_NODE_UNSCHEDULABLE) && !(C.cflags & SIMON_CLS_TOL_UNSCHED)) code = 1;
+                        if (!code && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)g) code = 2;
+                        if (!code)
+                            #pragma unroll 1
+                            for (uint32_t w = 0; w < WT; w++)
+                                if (P.taint_hard[(uint64_t)w * N + g] & ~(uint64_t)tol[w]) code = 3;
+                        if (!code && !ok) code = 4;
+                        const int64_t *p = cw + cw[SCW_OFF_PREF];
+                        int64_t na64 = 0;
+                        #pragma unroll 1
+                        for (int64_t q = 0; q < cw[SCW_N_PREF]; q++) { int64_t w = *p++; if (term_eval(p, RC, g)) na64 += w; }
+                        na = (int32_t)na64;
+                        tt = 0;
+                        #pragma unroll 1
+                        for (uint32_t w = 0; w < WT; w++) tt += __popcll(P.taint_soft[(uint64_t)w * N + g] & ~(uint64_t)tol[WT + w]);
+                        bool hk = true, ign = false;
+                        #pragma unroll 1
+                        for (uint32_t jh = 0; jh < C.n_hard; jh++) if (DOM(ENT(ER_T, C.e_hard + jh), idx) < 0) hk = false;
+                        #pragma unroll 1
+                        for (uint32_t js = 0; js < C.n_soft; js++) if (DOM(ENT(ER_T, C.e_soft + js), idx) < 0) ign = true;
+                        if (hk) fl |= NF_HARDKEYS;
+                        if (ign) fl |= NF_IGNORED;
+                        if (P.use_scache && tt < 256)
+                            P.scache[(uint64_t)sig * N + g] = (unsigned long long)code | ((unsigned long long)fl << 8) |
+                                                             ((unsigned long long)(uint32_t)tt << 16) | (1ull << 24) |
+                                                             ((unsigned long long)(uint32_t)na << 32);
+                    }
+                    nf |= fl | (code ? NF_STATIC_FAIL : 0);
+                    A8(C_ST_CODE, idx) = code;
+                    A32(B_RAW_NA, idx) = na;
+                    A32(B_RAW_TT, idx) = tt;
+                    A64(A_SIMON, idx) = sim4[u];
+                    A32(B_EXTRA, idx) = ex4[u];
+                    A8(C_NFLAGS, idx) = nf;
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if ((uint32_t)e < C.E) VAL(e, idx) = v4[u][e];
+                    #pragma unroll 1
+                    for (uint32_t e = 4; e < C.E; e++) {
+                        int32_t d = (ENT(ER_KIND, e) == EK_SOFT && ENT(ER_B, e)) ? (int32_t)g : DOM(ENT(ER_T, e), idx);
+                        VAL(e, idx) = d >= 0 ? ldcg32(&SC.cnt[(uint32_t)ENT(ER_BASE, e) + (uint32_t)d]) : 0;
+                    }
+                    A8(C_REGBITS, idx) = 0;
+                    own_eval(idx);
+                }
             }
-            if (n_hard > 0 || any_table) {
+            TICK(14);
+            if (C.n_hard > 0 || C.any_table) {
                 // rare: DoNotSchedule constraints need the set of registered domains (filtering.go:221-243);
                 // soft constraints over very large topologies fall back to per-domain tables
-                for (uint32_t jh = 0; jh < n_hard; jh++) {
-                    uint32_t nd = P.topo_ndom[ENT(ER_T, e_hard + jh)];
+                #pragma unroll 1
+                for (uint32_t jh = 0; jh < C.n_hard; jh++) {
+                    uint32_t nd = S.tnd[ENT(ER_T, C.e_hard + jh)];
+                    #pragma unroll 1
                     for (uint32_t d = gtid; d < nd; d += CT) SC.hard_reg[(uint64_t)jh * P.max_dom + d] = 0;
                 }
-                for (uint32_t js = 0; js < n_soft; js++) {
-                    if (ENT(ER_B, e_soft + js) || ENT(ER_WOFF, e_soft + js) >= 0) continue;
-                    uint32_t nd = P.topo_ndom[ENT(ER_T, e_soft + js)];
+                #pragma unroll 1
+                for (uint32_t js = 0; js < C.n_soft; js++) {
+                    if (ENT(ER_B, C.e_soft + js) || ENT(ER_WOFF, C.e_soft + js) >= 0) continue;
+                    uint32_t nd = S.tnd[ENT(ER_T, C.e_soft + js)];
+                    #pragma unroll 1
                     for (uint32_t d = gtid; d < nd; d += CT) SC.fcount[(uint64_t)js * P.max_dom + d] = 0;
                     if (gtid == 0) SC.size[js] = 0;
                 }
                 __threadfence();
                 cluster.sync();
+                #pragma unroll 1
                 for (uint32_t s = 0; s < NPT; s++) {
                     uint32_t idx = s * TPB + tid;
-                    uint8_t nf = S.nflags[idx];
+                    uint8_t nf = A8(C_NFLAGS, idx);
                     if ((nf & (NF_VALID | NF_SEL_OK | NF_HARDKEYS)) != (NF_VALID | NF_SEL_OK | NF_HARDKEYS)) continue;
-                    for (uint32_t jh = 0; jh < n_hard; jh++)
-                        SC.hard_reg[(uint64_t)jh * P.max_dom + S.dom[ENT(ER_T, e_hard + jh) * L + idx]] = 1;
+                    #pragma unroll 1
+                    for (uint32_t jh = 0; jh < C.n_hard; jh++)
+                        SC.hard_reg[(uint64_t)jh * P.max_dom + DOM(ENT(ER_T, C.e_hard + jh), idx)] = 1;
                 }
                 __threadfence();
                 cluster.sync();
+                #pragma unroll 1
                 for (uint32_t s = 0; s < NPT; s++) {
                     uint32_t idx = s * TPB + tid;
-                    if (!(S.nflags[idx] & NF_VALID)) continue;
+                    if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
                     uint8_t rb = 0;
-                    for (uint32_t jh = 0; jh < n_hard; jh++) {
-                        int32_t d = S.dom[ENT(ER_T, e_hard + jh) * L + idx];
+                    #pragma unroll 1
+                    for (uint32_t jh = 0; jh < C.n_hard; jh++) {
+                        int32_t d = DOM(ENT(ER_T, C.e_hard + jh), idx);
                         if (d >= 0 && __ldcg(&SC.hard_reg[(uint64_t)jh * P.max_dom + d])) rb |= (uint8_t)(1u << jh);
                     }
-                    S.regbits[idx] = rb;
+                    A8(C_REGBITS, idx) = rb;
                 }
             }
-            aff_total = 0;
-            for (uint32_t e = e_aff; e < e_anti; e++) aff_total += ldcg32(&SC.cnt_total[ENT(ER_K, e)]);
+            C.aff_total = 0;
+            #pragma unroll 1
+            for (uint32_t e = C.e_aff; e < C.e_anti; e++) C.aff_total += ldcg32(&SC.cnt_total[ENT(ER_K, e)]);
+            if (C.have_pred) set_weights();
             cur_class = cls;
+            TICK(2);
         }
-        const int64_t *cw = S.blob;
 
         // =================================================================================================
         // one placement decision
         // =================================================================================================
-        long long pl[SK_PAYLOAD];
-        // ---- R1: global minimum of every hard spread constraint over its registered domains ----
+        // ---- R1 (rare): global minimum of every hard spread constraint over its registered domains ----
         int32_t hard_min[SK_MAX_HARD];
-        if (n_hard > 0) {
-            long long hv[SK_MAX_HARD];
-            const int hop[SK_MAX_HARD] = {1, 1, 1, 1, 1, 1, 1, 1};
+        if (C.n_hard > 0) {
+            unsigned long long hv[SK_MAX_HARD];
+            const int hop[SK_MAX_HARD] = {OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU};
 #pragma unroll
-            for (int q = 0; q < SK_MAX_HARD; q++) hv[q] = INT32_MAX;
+            for (int q = 0; q < SK_MAX_HARD; q++) hv[q] = (unsigned long long)INT32_MAX;
+            #pragma unroll 1
             for (uint32_t s = 0; s < NPT; s++) {
                 uint32_t idx = s * TPB + tid;
-                uint8_t nf = S.nflags[idx];
+                uint8_t nf = A8(C_NFLAGS, idx);
                 if ((nf & (NF_VALID | NF_SEL_OK | NF_HARDKEYS)) != (NF_VALID | NF_SEL_OK | NF_HARDKEYS)) continue;
 #pragma unroll
                 for (int q = 0; q < SK_MAX_HARD; q++)
-                    if ((uint32_t)q < n_hard) { long long v = S.val[(e_hard + q) * L + idx]; hv[q] = v < hv[q] ? v : hv[q]; }
+                    if ((uint32_t)q < C.n_hard) { unsigned long long v = (unsigned long long)(uint32_t)VAL(C.e_hard + q, idx); hv[q] = v < hv[q] ? v : hv[q]; }
             }
-            sk_allreduce<SK_MAX_HARD, false>(R, hv, hop, pl);
+            sk_allreduce<SK_MAX_HARD>(R, hv, hop);
 #pragma unroll
             for (int q = 0; q < SK_MAX_HARD; q++) hard_min[q] = (int32_t)hv[q];
         }
 
-        // ---- P1: filters on cached state; raw scores that do not depend on other nodes ----
-        const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
-        auto filter_node = [&](uint32_t idx) -> uint32_t {
-            uint32_t reasons = 0;
-            if (S.st_code[idx]) return 1u << SFC_STATIC;
-            for (uint32_t e = 0; e < n_ports; e++)
-                if (S.val[e * L + idx] > 0) return 1u << SFC_PORTS;
-            if (S.num_pods[idx] + 1 > S.alloc_pods[idx]) reasons |= 1u << SFC_TOO_MANY_PODS;
-            if (cflags & SIMON_CLS_HAS_REQUEST) {
-                if (S.alloc_mcpu[idx] < cw[SCW_REQ_MCPU] + S.req_mcpu[idx]) reasons |= 1u << SFC_CPU;
-                if (S.alloc_mem[idx] < cw[SCW_REQ_MEM] + S.req_mem[idx]) reasons |= 1u << SFC_MEM;
-                if (S.alloc_eph[idx] < cw[SCW_REQ_EPH] + S.req_eph[idx]) reasons |= 1u << SFC_EPH;
-                if (K) {
-                    uint32_t g = (uint32_t)S.node_g[idx];
-                    for (uint32_t k = 0; k < K; k++)
-                        if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * N + g] < sc_req[k] + SC.req_scalar[(uint64_t)k * N + g])
-                            reasons |= 1u << (SFC_SCALAR0 + k);
-                }
-            }
-            if (reasons) return reasons;
-            for (uint32_t jh = 0; jh < n_hard; jh++) {
-                uint32_t e = e_hard + jh;
-                int32_t d = S.dom[ENT(ER_T, e) * L + idx];
-                if (d < 0) return 1u << SFC_PTS_MISSING;
-                int64_t match = (S.regbits[idx] >> jh) & 1 ? S.val[e * L + idx] : 0;
-                int64_t skew = match + ENT(ER_B, e) - (int64_t)hard_min[jh];
-                if (skew > ENT(ER_A, e)) return 1u << SFC_PTS_SKEW;
-            }
-            if (n_aff) {
-                bool pods_exist = true, missing = false;
-                for (uint32_t e = e_aff; e < e_anti; e++) {
-                    int32_t d = S.dom[ENT(ER_T, e) * L + idx];
-                    if (d < 0) { missing = true; break; }
-                    if (S.val[e * L + idx] <= 0) pods_exist = false;
-                }
-                bool ok = true;
-                if (missing) ok = false;
-                else if (!pods_exist) ok = (aff_total == 0 && (cflags & SIMON_CLS_IPA_SELF_MATCH));
-                if (!ok) return 1u << SFC_IPA_AFF;
-            }
-            for (uint32_t e = e_anti; e < e_exist; e++)
-                if (S.dom[ENT(ER_T, e) * L + idx] >= 0 && S.val[e * L + idx] > 0) return 1u << SFC_IPA_ANTI;
-            for (uint32_t e = e_exist; e < e_isc; e++)
-                if (S.dom[ENT(ER_T, e) * L + idx] >= 0 && S.val[e * L + idx] > 0) return 1u << SFC_IPA_EXIST;
-            if (cw[SCW_GPU_MEM] > 0) {
-                uint32_t g = (uint32_t)S.node_g[idx];
-                int slots[64];
-                int64_t total = P.gpu_total_mem ? P.gpu_total_mem[g] : 0;
-                if (total < cw[SCW_GPU_MEM] || gpu_allocate(P, SC, cw[SCW_GPU_MEM], cw[SCW_GPU_COUNT], g, slots) == 0) return 1u << SFC_GPU;
-            }
-            return 0;
-        };
-
-        long long rv[SK_NV];
-        // F, n_ignored (sum); na, tt, simon, ipa (max); simon, ipa (min); 8 domain-bitmask words (or)
-        const int rop[SK_NV] = {0, 0, 2, 2, 2, 2, 1, 1, 3, 3, 3, 3, 3, 3, 3, 3};
-        rv[0] = 0; rv[1] = 0; rv[2] = 0; rv[3] = 0; rv[4] = -INT64_MAX; rv[5] = 0; rv[6] = INT64_MAX; rv[7] = 0;
-#pragma unroll
-        for (int q = 8; q < SK_NV; q++) rv[q] = 0;
+        TICK(3);
+        // ---- P1: filters on cached state ----
+        bool my_flip = false;
+        int64_t ipa_lo = 0, ipa_hi = 0;     // min/max of raw InterPodAffinity scores (initialised to 0: scoring.go:255)
+        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
         for (uint32_t s = 0; s < NPT; s++) {
             uint32_t idx = s * TPB + tid;
-            uint8_t nf = S.nflags[idx];
+            uint8_t nf = A8(C_NFLAGS, idx);
             if (!(nf & NF_VALID)) continue;
-            bool feas = filter_node(idx) == 0;
+            bool feas = filter_node(idx, nf, hard_min, false) == 0;
+            if (feas != ((nf & NF_FEASIBLE) != 0)) my_flip = true;
             bool counted = feas && !(nf & NF_IGNORED);
-            if (counted)
-                for (uint32_t js = 0; js < n_soft; js++) {
-                    uint32_t e = e_soft + js;
-                    int32_t wo = ENT(ER_WOFF, e);
-                    if (wo < 0) continue;
-                    int32_t d = S.dom[ENT(ER_T, e) * L + idx];
-                    uint32_t w = (uint32_t)wo + ((uint32_t)d >> 6);
-#pragma unroll
-                    for (int q = 0; q < SK_MAXW; q++)
-                        if ((uint32_t)q == w) rv[8 + q] |= (long long)(1ull << (d & 63));
-                }
-            if (any_table && counted != ((nf & NF_COUNTED) != 0)) {
-                for (uint32_t js = 0; js < n_soft; js++) {
-                    uint32_t e = e_soft + js;
+            if (C.any_table && counted != ((nf & NF_COUNTED) != 0)) {
+                #pragma unroll 1
+                for (uint32_t js = 0; js < C.n_soft; js++) {
+                    uint32_t e = C.e_soft + js;
                     if (ENT(ER_B, e) || ENT(ER_WOFF, e) >= 0) continue;
-                    int32_t d = S.dom[ENT(ER_T, e) * L + idx];
+                    int32_t d = DOM(ENT(ER_T, e), idx);
                     if (counted) { if (atomicAdd(&SC.fcount[(uint64_t)js * P.max_dom + d], 1) == 0) atomicAdd(&SC.size[js], 1); }
                     else { if (atomicAdd(&SC.fcount[(uint64_t)js * P.max_dom + d], -1) == 1) atomicAdd(&SC.size[js], -1); }
                 }
             }
-            nf = (nf & ~(NF_COUNTED | NF_FEASIBLE)) | (counted ? NF_COUNTED : 0) | (feas ? NF_FEASIBLE : 0);
-            S.nflags[idx] = nf;
-            if (feas) {
+            A8(C_NFLAGS, idx) = (nf & ~(NF_COUNTED | NF_FEASIBLE)) | (counted ? NF_COUNTED : 0) | (feas ? NF_FEASIBLE : 0);
+            if (feas && C.n_isc) {
                 int64_t ip = 0;
-                for (uint32_t e = e_isc; e < E; e++)
-                    if (S.dom[ENT(ER_T, e) * L + idx] >= 0) ip += (int64_t)ENT(ER_A, e) * S.val[e * L + idx];
-                S.raw_ipa[idx] = (int32_t)ip;
-                rv[0] += 1;
-                if (nf & NF_IGNORED) rv[1] += 1;
-                long long na = S.raw_na[idx], tt = S.raw_tt[idx], sm = S.raw_simon[idx];
-                rv[2] = na > rv[2] ? na : rv[2]; rv[3] = tt > rv[3] ? tt : rv[3];
-                rv[4] = sm > rv[4] ? sm : rv[4]; rv[6] = sm < rv[6] ? sm : rv[6];
-                rv[5] = ip > rv[5] ? ip : rv[5]; rv[7] = ip < rv[7] ? ip : rv[7];
+                #pragma unroll 1
+                for (uint32_t e = C.e_isc; e < C.E; e++)
+                    if (DOM(ENT(ER_T, e), idx) >= 0) ip += (int64_t)ENT(ER_A, e) * VAL(e, idx);
+                A32(B_RAW_IPA, idx) = (int32_t)ip;
+                ipa_hi = ip > ipa_hi ? ip : ipa_hi;
+                ipa_lo = ip < ipa_lo ? ip : ipa_lo;
             }
         }
-        if (any_table) __threadfence();
-        sk_allreduce<SK_NV, false>(R, rv, rop, pl);
-        const int64_t F = rv[0], n_ign = rv[1], na_max = rv[2], tt_max = rv[3], simon_max = rv[4], ipa_max = rv[5],
-                      simon_min = rv[6], ipa_min = rv[7];
+        if (C.any_table) __threadfence();
+        TICK(4);
 
-        if (F == 0) {
-            // ---- unschedulable: histogram of per-node failure reasons (FitError, generic_scheduler.go:72-90) ----
-            if (n_fail < P.max_fail && SC.fail_counts) {
+        // ---- P2 + all-reduce: spread raw scores under the predicted summary, verified by the same reduction ----
+        int64_t pts_min = 0, pts_max = 0, ipa_min = 0, ipa_max = 0;
+        unsigned long long plo, phi;
+        if (C.sum_valid) {
+            // steady state: the summary is exact unless some node flipped feasibility since it was taken
+            pts_pass(plo, phi);
+            unsigned long long pv[5] = {plo, phi, sk_enc(ipa_lo), sk_enc(ipa_hi), my_flip ? 1ull : 0ull};
+            const int pop[5] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR};
+            sk_allreduce<5>(R, pv, pop);
+            pts_min = sk_dec(pv[0]); pts_max = sk_dec(pv[1]); ipa_min = sk_dec(pv[2]); ipa_max = sk_dec(pv[3]);
+            if (pv[4] != 0) { C.sum_valid = false; st_redo++; }
+        }
+        TICK(5);
+        if (!C.sum_valid) {
+            // full summary (F, ignored count, normaliser inputs, domain bitmasks) + spread min/max under the prediction
+            st_sum++;
+            const bool spec = C.have_pred;
+            if (spec) pts_pass(plo, phi); else { plo = sk_enc(INT64_MAX); phi = sk_enc(0); }
+            unsigned long long rv[SK_NV];
+            const int rop[SK_NV] = {OP_SUM32, OP_SUM32, OP_MAXU, OP_MAXU, OP_MAXU, OP_MINU, OP_MINU, OP_MAXU, OP_MINU, OP_MAXU,
+                                    OP_OR, OP_OR, OP_OR, OP_OR, OP_OR, OP_OR};
+            rv[0] = 0; rv[1] = 0; rv[2] = 0; rv[3] = 0; rv[4] = sk_enc(-INT64_MAX); rv[5] = sk_enc(INT64_MAX);
+            rv[6] = plo; rv[7] = phi; rv[8] = sk_enc(ipa_lo); rv[9] = sk_enc(ipa_hi);
+#pragma unroll
+            for (int q = 10; q < SK_NV; q++) rv[q] = 0;
+            #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+            for (uint32_t s = 0; s < NPT; s++) {
+                uint32_t idx = s * TPB + tid;
+                uint8_t nf = A8(C_NFLAGS, idx);
+                if (!(nf & NF_FEASIBLE)) continue;
+                rv[0] += 1;
+                if (nf & NF_IGNORED) rv[1] += 1;
+                unsigned long long na = (unsigned long long)(uint32_t)A32(B_RAW_NA, idx), tt = (unsigned long long)(uint32_t)A32(B_RAW_TT, idx);
+                unsigned long long sm = sk_enc(A64(A_SIMON, idx));
+                rv[2] = na > rv[2] ? na : rv[2]; rv[3] = tt > rv[3] ? tt : rv[3];
+                rv[4] = sm > rv[4] ? sm : rv[4]; rv[5] = sm < rv[5] ? sm : rv[5];
+                if (!(nf & NF_IGNORED))
+                    #pragma unroll 1
+                    for (uint32_t js = 0; js < C.n_soft; js++) {
+                        uint32_t e = C.e_soft + js;
+                        int32_t wo = ENT(ER_WOFF, e);
+                        if (wo < 0) continue;
+                        int32_t d = DOM(ENT(ER_T, e), idx);
+                        uint32_t w = (uint32_t)wo + ((uint32_t)d >> 6);
+#pragma unroll
+                        for (int q = 0; q < SK_MAXW; q++)
+                            if ((uint32_t)q == w) rv[10 + q] |= 1ull << (d & 63);
+                    }
+            }
+            sk_allreduce<SK_NV>(R, rv, rop);
+            C.F = (int64_t)rv[0]; C.n_ign = (int64_t)rv[1]; C.na_max = (int64_t)rv[2]; C.tt_max = (int64_t)rv[3];
+            C.simon_max = sk_dec(rv[4]); C.simon_min = sk_dec(rv[5]);
+            pts_min = sk_dec(rv[6]); pts_max = sk_dec(rv[7]); ipa_min = sk_dec(rv[8]); ipa_max = sk_dec(rv[9]);
+            bool sizes_ok = spec;
+#pragma unroll
+            for (int js = 0; js < SK_MAX_SOFT; js++) {
+                if ((uint32_t)js >= C.n_soft) continue;
+                uint32_t e = C.e_soft + js;
+                int64_t size;
+                if (ENT(ER_B, e)) size = C.F - C.n_ign;
+                else if (ENT(ER_WOFF, e) >= 0) {
+                    uint32_t nw = (S.tnd[ENT(ER_T, e)] + 63) / 64;
+                    size = 0;
+                    const uint32_t w0 = (uint32_t)ENT(ER_WOFF, e);
+#pragma unroll
+                    for (int q = 0; q < SK_MAXW; q++)
+                        if ((uint32_t)q >= w0 && (uint32_t)q < w0 + nw) size += __popcll(rv[10 + q]);
+                } else size = (int64_t)ldcg32(&SC.size[js]);
+                if (size != (int64_t)psz[js]) sizes_ok = false;
+                psz[js] = (int32_t)size;
+            }
+            C.sum_valid = true;
+            C.have_pred = true;
+            if (!sizes_ok && C.F > 1 && C.n_soft > 0) {
+                // the predicted topology sizes were wrong (or there was no prediction): redo the spread pass
+                set_weights();
+                pts_pass(plo, phi);
+                unsigned long long pv[2] = {plo, phi};
+                const int pop[2] = {OP_MINU, OP_MAXU};
+                sk_allreduce<2>(R, pv, pop);
+                pts_min = sk_dec(pv[0]); pts_max = sk_dec(pv[1]);
+            } else if (!sizes_ok) set_weights();
+            if (!(C.snorm_valid && C.nm_na_max == C.na_max && C.nm_tt_max == C.tt_max && C.nm_simon_min == C.simon_min &&
+                  C.nm_simon_max == C.simon_max)) {
+                // static-normalised part of the total: NodeAffinity + TaintToleration + 2 x Simon + extra
+                const int64_t range = C.simon_max - C.simon_min;
+                const bool small = range > 0 && range < (1ll << 24) && C.simon_max < (1ll << 24) && C.simon_min >= 0;
+                #pragma unroll 1
                 for (uint32_t s = 0; s < NPT; s++) {
                     uint32_t idx = s * TPB + tid;
-                    if (!(S.nflags[idx] & NF_VALID)) continue;
-                    uint32_t rs = filter_node(idx);
+                    if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
+                    int64_t na = C.na_max == 0 ? A32(B_RAW_NA, idx) : (int64_t)((uint32_t)(100 * A32(B_RAW_NA, idx)) / (uint32_t)C.na_max);
+                    int64_t tt = C.tt_max == 0 ? 100 : 100 - (int64_t)((uint32_t)(100 * A32(B_RAW_TT, idx)) / (uint32_t)C.tt_max);
+                    int64_t sm;
+                    if (range == 0) sm = 0;
+                    else if (small) sm = (int64_t)((uint32_t)((uint32_t)(A64(A_SIMON, idx) - C.simon_min) * 100u) / (uint32_t)range);
+                    else sm = ((A64(A_SIMON, idx) - C.simon_min) * 100) / range;
+                    A32(B_SNORM, idx) = (int32_t)(na + tt + 2 * sm + (int64_t)A32(B_EXTRA, idx));
+                }
+                C.nm_na_max = C.na_max; C.nm_tt_max = C.tt_max; C.nm_simon_min = C.simon_min; C.nm_simon_max = C.simon_max;
+                C.snorm_valid = true;
+            }
+        }
+
+        TICK(6);
+        if (C.F == 0) {
+            // ---- unschedulable: histogram of per-node failure reasons (FitError, generic_scheduler.go:72-90) ----
+            if (n_fail < P.max_fail && SC.fail_counts) {
+                #pragma unroll 1
+                for (uint32_t s = 0; s < NPT; s++) {
+                    uint32_t idx = s * TPB + tid;
+                    uint8_t nf = A8(C_NFLAGS, idx);
+                    if (!(nf & NF_VALID)) continue;
+                    uint32_t rs = filter_node(idx, nf, hard_min, true);
                     while (rs) { int b = __ffs(rs) - 1; rs &= rs - 1; atomicAdd(&SC.fail_counts[(uint64_t)n_fail * SIMON_N_FAIL_CODES + b], 1u); }
                 }
                 if (leader) SC.fail_pod[n_fail] = i;
@@ -501,112 +799,53 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
             continue;
         }
 
-        // ---- P2: PodTopologySpread raw scores (scoring.go:175-208) ----
-        long long pv[2];
-        const int pop[2] = {1, 2};
-        pv[0] = INT64_MAX; pv[1] = 0;
-        if (n_soft > 0 && F > 1) {
-            double soft_w[SK_MAX_SOFT];
-#pragma unroll
-            for (int js = 0; js < SK_MAX_SOFT; js++) {
-                soft_w[js] = 0.0;
-                if ((uint32_t)js < n_soft) {
-                    uint32_t e = e_soft + js;
-                    int64_t size;
-                    if (ENT(ER_B, e)) size = F - n_ign;
-                    else if (ENT(ER_WOFF, e) >= 0) {
-                        uint32_t nw = (P.topo_ndom[ENT(ER_T, e)] + 63) / 64;
-                        size = 0;
-#pragma unroll
-                        for (int q = 0; q < SK_MAXW; q++)
-                            if (q >= ENT(ER_WOFF, e) && (uint32_t)q < (uint32_t)ENT(ER_WOFF, e) + nw) size += __popcll((unsigned long long)rv[8 + q]);
-                    } else size = (int64_t)ldcg32(&SC.size[js]);
-                    soft_w[js] = P.log_table[size + 2];
-                }
-            }
-            for (uint32_t s = 0; s < NPT; s++) {
-                uint32_t idx = s * TPB + tid;
-                uint8_t nf = S.nflags[idx];
-                if (!(nf & NF_FEASIBLE)) continue;
-                int64_t raw = 0;
-                if (!(nf & NF_IGNORED)) {
-                    double score = 0.0;
-#pragma unroll
-                    for (int js = 0; js < SK_MAX_SOFT; js++)
-                        if ((uint32_t)js < n_soft) {
-                            uint32_t e = e_soft + js;
-                            double sfc = (double)S.val[e * L + idx] * soft_w[js] + (double)(ENT(ER_A, e) - 1);
-                            score = score + sfc;
-                        }
-                    raw = f2i(score);
-                    pv[0] = raw < pv[0] ? raw : pv[0];
-                    pv[1] = raw > pv[1] ? raw : pv[1];
-                }
-                S.raw_pts[idx] = (int32_t)raw;
-            }
-            sk_allreduce<2, false>(R, pv, pop, pl);
-        }
-        const int64_t pts_min = pv[0], pts_max = pv[1];
-
         // ---- P3: totals and arg-max (first node in scenario order wins ties) ----
-        long long best[1];
-        const int bop[1] = {2};
-        best[0] = -1;
-#pragma unroll
-        for (int q = 0; q < SK_PAYLOAD; q++) pl[q] = 0;
-        const int64_t simon_range = simon_max - simon_min, ipa_diff = ipa_max - ipa_min;
+        unsigned long long best = 0;
+        const int64_t ipa_diff = ipa_max - ipa_min;
+        const bool pts32 = pts_max > 0 && pts_max < (1 << 23) && pts_min >= 0;
+        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
         for (uint32_t s = 0; s < NPT; s++) {
             uint32_t idx = s * TPB + tid;
-            uint8_t nf = S.nflags[idx];
+            uint8_t nf = A8(C_NFLAGS, idx);
             if (!(nf & NF_FEASIBLE)) continue;
             int64_t total = 0;
-            if (F > 1) {
-                int64_t capc = S.alloc_mcpu[idx], rqc = S.nz_mcpu[idx] + cw[SCW_SCORE_MCPU];
-                int64_t capm = S.alloc_mem[idx], rqm = S.nz_mem[idx] + cw[SCW_SCORE_MEM];
-                int64_t s1 = (capc == 0 || rqc > capc) ? 0 : ((capc - rqc) * 100) / capc;
-                int64_t s2 = (capm == 0 || rqm > capm) ? 0 : ((capm - rqm) * 100) / capm;
-                int64_t la = (s1 + s2) / 2;
-                double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
-                double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
-                int64_t ba = 0;
-                if (!(cf >= 1.0 || mf >= 1.0)) ba = f2i((1.0 - fabs(cf - mf)) * 100.0);
-                int64_t na = na_max == 0 ? S.raw_na[idx] : (100 * (int64_t)S.raw_na[idx]) / na_max;
-                int64_t tt = tt_max == 0 ? 100 : 100 - (100 * (int64_t)S.raw_tt[idx]) / tt_max;
-                int64_t sm = simon_range == 0 ? 0 : ((S.raw_simon[idx] - simon_min) * 100) / simon_range;
-                int64_t ip = 0;
-                if (ipa_diff > 0) ip = f2i(100.0 * ((double)((int64_t)S.raw_ipa[idx] - ipa_min) / (double)ipa_diff));
+            if (C.F > 1) {
                 int64_t pts;
-                if (n_soft == 0) pts = 100;
+                if (C.n_soft == 0) pts = 100;
                 else if (nf & NF_IGNORED) pts = 0;
                 else if (pts_max == 0) pts = 100;
-                else pts = (100 * (pts_max + pts_min - (int64_t)S.raw_pts[idx])) / pts_max;
-                total = ba + la + ip + na + 2 * pts + tt + 2 * sm + (int64_t)S.extra[idx];
+                else if (pts32) pts = (int64_t)((uint32_t)(100 * (uint32_t)(pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / (uint32_t)pts_max);
+                else pts = (100 * (pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / pts_max;
+                int64_t ip = 0;
+                if (C.n_isc && ipa_diff > 0) ip = f2i(100.0 * ((double)((int64_t)A32(B_RAW_IPA, idx) - ipa_min) / (double)ipa_diff));
+                total = (int64_t)A32(B_OWN, idx) + (int64_t)A32(B_SNORM, idx) + ip + 2 * pts;
             }
             uint32_t r = s * CT + gtid;
-            long long key = (long long)(((unsigned long long)total << 24) | (unsigned long long)(0xFFFFFFu - r));
-            if (key > best[0]) {
-                best[0] = key;
-#pragma unroll
-                for (int t = 0; t < SIMON_MAX_TOPOS; t++) pl[t] = (uint32_t)t < T ? S.dom[t * L + idx] : -1;
-                pl[8] = nf;
-            }
+            unsigned long long key = ((unsigned long long)(total + 1) << 24) | (unsigned long long)(0xFFFFFFu - r);
+            best = key > best ? key : best;
         }
-        sk_allreduce<1, true>(R, best, bop, pl);
-        const uint32_t win_r = 0xFFFFFFu - (uint32_t)((unsigned long long)best[0] & 0xFFFFFFu);
-        const int64_t win_total = (int64_t)((unsigned long long)best[0] >> 24);
-        const bool win_ignored = ((uint32_t)pl[8] & NF_IGNORED) != 0;
+        TICK(7);
+        int32_t pay[10];
+        best = sk_argmax(R, best, CT, TPB, pay);
+        TICK(8);
+        const uint32_t win_r = 0xFFFFFFu - (uint32_t)(best & 0xFFFFFFu);
+        const int64_t win_total = (int64_t)(best >> 24) - 1;
+        const bool win_ignored = ((uint32_t)pay[8] & NF_IGNORED) != 0;
 
         // ---- commit (AssumePod / NodeInfo.AddPod) ----
         if (win_r % CT == gtid) {
             uint32_t idx = (win_r / CT) * TPB + tid;
-            uint32_t g = (uint32_t)S.node_g[idx];
-            S.req_mcpu[idx] += cw[SCW_REQ_MCPU]; S.req_mem[idx] += cw[SCW_REQ_MEM]; S.req_eph[idx] += cw[SCW_REQ_EPH];
-            S.nz_mcpu[idx] += cw[SCW_NZ_MCPU]; S.nz_mem[idx] += cw[SCW_NZ_MEM]; S.num_pods[idx] += 1;
+            uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+            A64(A_REQ_MCPU, idx) += cw[SCW_REQ_MCPU]; A64(A_REQ_MEM, idx) += cw[SCW_REQ_MEM]; A64(A_REQ_EPH, idx) += cw[SCW_REQ_EPH];
+            A64(A_NZ_MCPU, idx) += cw[SCW_NZ_MCPU]; A64(A_NZ_MEM, idx) += cw[SCW_NZ_MEM]; A32(B_NUM_PODS, idx) += 1;
+            const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
+            #pragma unroll 1
             for (uint32_t k = 0; k < K; k++) SC.req_scalar[(uint64_t)k * N + g] += sc_req[k];
             const int64_t *inc = cw + cw[SCW_OFF_INC];
+            #pragma unroll 1
             for (int64_t u = 0; u < cw[SCW_N_INC]; u++) {
                 int64_t k = inc[3 * u], t = inc[3 * u + 1], sig = inc[3 * u + 2];
-                int32_t d = S.dom[t * L + idx];
+                int32_t d = DOM(t, idx);
                 if (d < 0) continue;
                 if (sig >= 0) {
                     bool el = (sig == (int64_t)cls) ? !win_ignored : elig_eval(P, sig, RC, g);   // the winner passed NodeAffinity
@@ -615,45 +854,67 @@ extern "C" __global__ void __launch_bounds__(1024, 1) simon_place_kernel(const S
                 atomicAdd(&SC.cnt[P.cnt_off[k] + d], 1);
                 atomicAdd(&SC.cnt_total[k], 1);
             }
-            if (cw[SCW_GPU_MEM] > 0) {
+            if (C.has_gpu) {
                 int slots[64];
                 int ns = gpu_allocate(P, SC, cw[SCW_GPU_MEM], cw[SCW_GPU_COUNT], g, slots);
+                #pragma unroll 1
                 for (int q = 0; q < ns && q < 64; q++) SC.gpu_used[(uint64_t)slots[q] * N + g] += cw[SCW_GPU_MEM];
             }
             SC.out_node[i] = (int32_t)g;
-            if (SC.out_score) SC.out_score[i] = F > 1 ? win_total : 0;
+            if (SC.out_score) SC.out_score[i] = C.F > 1 ? win_total : 0;
+            own_eval(idx);      // Fit verdict + LeastAllocated/BalancedAllocation of the node that changed
         }
         // every thread folds the winner into its cached counter values
-        for (uint32_t e = 0; e < E; e++) {
+        #pragma unroll 1
+        for (uint32_t e = 0; e < C.E; e++) {
             if (!ENT(ER_INC, e)) continue;
             int32_t kind = ENT(ER_KIND, e), t = ENT(ER_T, e);
             bool host = kind == EK_SOFT && ENT(ER_B, e);
-            int32_t wd = host ? (int32_t)pl[0] : (int32_t)pl[t];
+            int32_t wd = ((const int32_t *)&S.fin[SK_NV])[host ? 0 : t];
             if (kind == EK_SOFT && !host && win_ignored) continue;
             if (wd < 0) continue;
-            const int32_t *dcol = S.dom + (host ? 0 : t) * L;
+            const uint32_t trow = host ? 0 : (uint32_t)t;
+            #pragma unroll (NPT_T > 0 ? NPT_T : 1)
             for (uint32_t s = 0; s < NPT; s++) {
                 uint32_t idx = s * TPB + tid;
-                if ((S.nflags[idx] & NF_VALID) && dcol[idx] == wd) S.val[e * L + idx] += 1;
+                if ((A8(C_NFLAGS, idx) & NF_VALID) && DOM(trow, idx) == wd) VAL(e, idx) += 1;
             }
-            if (kind == EK_AFF) aff_total += 1;
+            if (kind == EK_AFF) C.aff_total += 1;
         }
         n_sched++;
         i++;
+        TICK(9);
     }
 
     // ---- write the dynamic state back -------------------------------------------------------------------
+    #pragma unroll 1
     for (uint32_t s = 0; s < NPT; s++) {
         uint32_t idx = s * TPB + tid;
-        if (!(S.nflags[idx] & NF_VALID)) continue;
-        uint32_t g = (uint32_t)S.node_g[idx];
-        SC.req_mcpu[g] = S.req_mcpu[idx]; SC.req_mem[g] = S.req_mem[idx]; SC.req_eph[g] = S.req_eph[idx];
-        SC.nz_mcpu[g] = S.nz_mcpu[idx]; SC.nz_mem[g] = S.nz_mem[idx]; SC.num_pods[g] = S.num_pods[idx];
+        if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
+        uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+        SC.req_mcpu[g] = A64(A_REQ_MCPU, idx); SC.req_mem[g] = A64(A_REQ_MEM, idx); SC.req_eph[g] = A64(A_REQ_EPH, idx);
+        SC.nz_mcpu[g] = A64(A_NZ_MCPU, idx); SC.nz_mem[g] = A64(A_NZ_MEM, idx); SC.num_pods[g] = A32(B_NUM_PODS, idx);
     }
     if (leader) {
         if (SC.n_fail) *SC.n_fail = n_fail;
         if (SC.n_sched) *SC.n_sched = n_sched;
         if (SC.clk) SC.clk[1] = sk_globaltimer();
+        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; for (int q = 0; q < 20; q++) P.stats[8 + q] = (unsigned long long)tk[q]; }
     }
     cluster.sync();   // no CTA may exit while peers can still address its shared memory
 }
+
+#define SIMON_KERNEL(MAXT, NPTT)                                                                         \
+    extern "C" __global__ void __launch_bounds__(MAXT, 1) simon_place_kernel_##MAXT##_##NPTT(const __grid_constant__ SkParams P) { \
+        simon_place_body<MAXT, NPTT>(P);                                                                 \
+    }
+SIMON_KERNEL(256, 0)
+SIMON_KERNEL(256, 1)
+SIMON_KERNEL(256, 2)
+SIMON_KERNEL(256, 3)
+SIMON_KERNEL(256, 4)
+SIMON_KERNEL(512, 0)
+SIMON_KERNEL(512, 1)
+SIMON_KERNEL(512, 2)
+SIMON_KERNEL(1024, 0)
+SIMON_KERNEL(1024, 1)

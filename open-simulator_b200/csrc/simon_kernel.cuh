@@ -1,13 +1,13 @@
-// simon_kernel.cuh — persistent thread-block-cluster placement kernel (sm_100a).
+// simon_kernel.cuh — persistent thread-block-cluster placement kernel (sm_100a): shared declarations.
 //
 // One scenario = one thread-block cluster (up to 16 CTAs, DSMEM).  Every node of the scenario is owned by
-// one thread slot for the whole kernel; its static columns, its dynamic NodeInfo aggregates and the
-// per-class cached values live in that CTA's shared memory, so a placement decision touches no global
-// memory on its critical path: filter -> score -> cluster-wide reductions over DSMEM -> argmax -> commit.
+// one thread slot for the whole kernel; its static columns, its dynamic NodeInfo aggregates and the values
+// cached for the current pod class live in that CTA's shared memory, so a placement decision touches no
+// global memory on its critical path: filter -> score -> cluster-wide reductions over DSMEM -> argmax -> commit.
 //
 // Semantics follow oracle/simon_oracle.c line by line (which cites the reference file:line of every
-// plugin); the data layout is include/simon_gpu.h.  Integer work is exact; the five float64 plugin
-// formulas use IEEE double with contraction disabled (-fmad=false) and truncation by cast.
+// plugin); the data layout is include/simon_gpu.h.  Integer work is exact; the float64 plugin formulas use
+// IEEE double with contraction disabled (-fmad=false) and truncation by cast.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -21,11 +21,31 @@ namespace cg = cooperative_groups;
 #define SK_MAX_HARD 8
 #define SK_MAX_SOFT 8
 #define SK_MAX_CS 16
-#define SK_NV 16            // values per cluster all-reduce (8 scalars + 8 domain-bitmask words)
-#define SK_MAXW 8            // domain-bitmask words available per decision
-#define SK_PAYLOAD 10       // winner payload words: T domains + flags
+#define SK_MAXW 6           // domain-bitmask words available per decision
+#define SK_NV 16            // max values per all-reduce
+#define SK_PLW 5            // payload: 10 int32 packed in 5 u64 (T domains + flags)
+#define SK_MSGW (SK_NV + SK_PLW)
+#define SK_CSUM_W 16
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
+enum { ER_KIND = 0, ER_K, ER_T, ER_A, ER_B, ER_INC, ER_WOFF, ER_BASE, ER_ROWS };   // ER_BASE: offset of the counter in cnt[]
+
+// 64-bit per-node arrays
+enum { A_ALLOC_MCPU = 0, A_ALLOC_MEM, A_ALLOC_EPH, A_REQ_MCPU, A_REQ_MEM, A_REQ_EPH, A_NZ_MCPU, A_NZ_MEM, A_SIMON,
+       A_INV_MCPU, A_INV_MEM, A_N64 };
+// 32-bit per-node arrays (followed by T domain rows and emax cached counter rows)
+enum { B_ALLOC_PODS = 0, B_NUM_PODS, B_NODE_G, B_NODE_CLASS, B_RAW_NA, B_RAW_TT, B_EXTRA, B_RAW_PTS, B_RAW_IPA, B_OWN, B_SNORM, B_N32 };
+// 8-bit per-node arrays
+enum { C_ST_CODE = 0, C_NFLAGS, C_REGBITS, C_N8 };
+
+#define NF_SEL_OK 1
+#define NF_IGNORED 2
+#define NF_HARDKEYS 4
+#define NF_COUNTED 8
+#define NF_FEASIBLE 16
+#define NF_VALID 32
+#define NF_FIT_OK 64
+#define NF_STATIC_FAIL 128
 
 struct SkScenario {
     const uint32_t *order;     // [n_active] scenario order -> node index (nullptr: identity)
@@ -39,6 +59,7 @@ struct SkScenario {
     int32_t *cnt_total;        // [n_counters]
     // scratch tables [SK_MAX_SOFT or SK_MAX_HARD][max_dom]
     int32_t *tp, *fcount, *size;   // size: [SK_MAX_SOFT]
+    long long *csum;           // [n_classes][SK_CSUM_W] last feasible-set summary per class (prediction only)
     uint8_t *hard_reg;
     // outputs
     int32_t *out_node;         // [P]
@@ -72,166 +93,188 @@ struct SkParams {
     // launch
     uint32_t first, count, max_fail, npt, emax, record_scores;
     const SkScenario *scen;    // [gridDim.x / cluster size]
+    unsigned long long *stats; // optional [8]: decisions, class changes, summary rebuilds, redone decisions
+    // static cache: per (static signature, node) verdicts, filled on first use
+    uint32_t n_sigs, use_scache;
+    unsigned long long *scache;    // [n_sigs][N] packed {st_code, flags, tt, 0, na:int32}
+    uint32_t *scache_ready;        // [n_sigs]
 };
-
-// ---------------------------------------------------------------------------------------------------------
-// shared memory carve-up (per CTA).  L = npt * blockDim.x node slots.
-struct SkSmem {
-    int64_t *alloc_mcpu, *alloc_mem, *alloc_eph, *req_mcpu, *req_mem, *req_eph, *nz_mcpu, *nz_mem, *raw_simon;
-    int32_t *alloc_pods, *num_pods, *node_g, *raw_na, *raw_tt, *extra, *raw_pts, *raw_ipa;
-    int32_t *dom;        // [T][L]
-    int32_t *val;        // [emax][L]
-    uint8_t *st_code, *nflags, *regbits;
-    int64_t *blob;       // [max_blob_words]
-    long long *inbox;    // [2][SK_MAX_CS][SK_NV + SK_PAYLOAD]
-    long long *wpart;    // [32][SK_NV + SK_PAYLOAD]
-    int32_t *ent;        // [7][SK_MAX_ENT]: kind, k, t, a, b, inc, bitmask word offset (-1: table method)
-};
-
-#define NF_SEL_OK 1
-#define NF_IGNORED 2
-#define NF_HARDKEYS 4
-#define NF_COUNTED 8
-#define NF_FEASIBLE 16
-#define NF_VALID 32
 
 __host__ __device__ inline size_t sk_align(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// shared memory carve-up (per CTA).  L = npt * blockDim.x node slots.
+struct SkSmem {
+    int64_t *a64;        // [A_N64][L]
+    int32_t *a32;        // [B_N32 + T + emax][L]
+    uint8_t *a8;         // [C_N8][L]
+    int64_t *blob;       // [max_blob_words]
+    unsigned long long *inbox;   // [2][SK_MAX_CS][SK_MSGW]
+    unsigned long long *wpart;   // [32][SK_MSGW]
+    unsigned long long *fin;     // [SK_MSGW]
+    int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
+    uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
+    double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
+    int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
+    SkScenario *scen;    // this cluster's scenario descriptor
+    uint32_t L, T;
+};
+
 __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words) {
     size_t b = 0;
-    b += 9 * sk_align(8ull * L);
-    b += 8 * sk_align(4ull * L);
-    b += sk_align(4ull * T * L);
-    b += sk_align(4ull * (emax ? emax : 1) * L);
-    b += 3 * sk_align(L);
+    b += sk_align(8ull * A_N64 * L);
+    b += sk_align(4ull * (B_N32 + T + emax) * L);
+    b += sk_align(1ull * C_N8 * L);
     b += sk_align(8ull * blob_words);
-    b += sk_align(8ull * 2 * SK_MAX_CS * (SK_NV + SK_PAYLOAD));
-    b += sk_align(8ull * 32 * (SK_NV + SK_PAYLOAD));
-    b += sk_align(4ull * 7 * SK_MAX_ENT);
+    b += sk_align(8ull * 2 * SK_MAX_CS * SK_MSGW);
+    b += sk_align(8ull * 32 * SK_MSGW);
+    b += sk_align(8ull * SK_MSGW);
+    b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
+    b += sk_align(4ull * SIMON_MAX_TOPOS);
+    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     return b + 64;
 }
 
 __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words) {
     unsigned char *p = base;
-    auto take = [&](size_t bytes) { unsigned char *q = p; p += sk_align(bytes); return q; };
-    S.alloc_mcpu = (int64_t *)take(8ull * L); S.alloc_mem = (int64_t *)take(8ull * L); S.alloc_eph = (int64_t *)take(8ull * L);
-    S.req_mcpu = (int64_t *)take(8ull * L); S.req_mem = (int64_t *)take(8ull * L); S.req_eph = (int64_t *)take(8ull * L);
-    S.nz_mcpu = (int64_t *)take(8ull * L); S.nz_mem = (int64_t *)take(8ull * L); S.raw_simon = (int64_t *)take(8ull * L);
-    S.alloc_pods = (int32_t *)take(4ull * L); S.num_pods = (int32_t *)take(4ull * L); S.node_g = (int32_t *)take(4ull * L);
-    S.raw_na = (int32_t *)take(4ull * L); S.raw_tt = (int32_t *)take(4ull * L); S.extra = (int32_t *)take(4ull * L);
-    S.raw_pts = (int32_t *)take(4ull * L); S.raw_ipa = (int32_t *)take(4ull * L);
-    S.dom = (int32_t *)take(4ull * T * L);
-    S.val = (int32_t *)take(4ull * (emax ? emax : 1) * L);
-    S.st_code = (uint8_t *)take(L); S.nflags = (uint8_t *)take(L); S.regbits = (uint8_t *)take(L);
-    S.blob = (int64_t *)take(8ull * blob_words);
-    S.inbox = (long long *)take(8ull * 2 * SK_MAX_CS * (SK_NV + SK_PAYLOAD));
-    S.wpart = (long long *)take(8ull * 32 * (SK_NV + SK_PAYLOAD));
-    S.ent = (int32_t *)take(4ull * 7 * SK_MAX_ENT);
+    S.a64 = (int64_t *)p; p += sk_align(8ull * A_N64 * L);
+    S.a32 = (int32_t *)p; p += sk_align(4ull * (B_N32 + T + emax) * L);
+    S.a8 = (uint8_t *)p; p += sk_align(1ull * C_N8 * L);
+    S.blob = (int64_t *)p; p += sk_align(8ull * blob_words);
+    S.inbox = (unsigned long long *)p; p += sk_align(8ull * 2 * SK_MAX_CS * SK_MSGW);
+    S.wpart = (unsigned long long *)p; p += sk_align(8ull * 32 * SK_MSGW);
+    S.fin = (unsigned long long *)p; p += sk_align(8ull * SK_MSGW);
+    S.ent = (int32_t *)p; p += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
+    S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
+    S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
+    S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
+    S.scen = (SkScenario *)p;
+    S.L = L; S.T = T;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cluster-wide all-reduce of NVAL int64 values (+ optional payload that follows value 0 when value 0 is a max)
-// ops: 0 sum, 1 min, 2 max, 3 bitwise or.
+// warp / cluster reductions on unsigned 64-bit values built from 32-bit redux.sync (one instruction per step)
+enum { OP_SUM32 = 0, OP_MINU = 1, OP_MAXU = 2, OP_OR = 3 };
+
+__device__ __forceinline__ unsigned long long sk_enc(long long x) { return (unsigned long long)x ^ 0x8000000000000000ull; }
+__device__ __forceinline__ long long sk_dec(unsigned long long x) { return (long long)(x ^ 0x8000000000000000ull); }
+
+__device__ __forceinline__ unsigned long long warp_maxu64(unsigned long long x) {
+    unsigned hi = (unsigned)(x >> 32), lo = (unsigned)x;
+    unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_minu64(unsigned long long x) {
+    unsigned hi = (unsigned)(x >> 32), lo = (unsigned)x;
+    unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_oru64(unsigned long long x) {
+    unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32));
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)x);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long warp_op(unsigned long long x, int op) {
+    if (op == OP_SUM32) return (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)x);
+    if (op == OP_MINU) return warp_minu64(x);
+    if (op == OP_MAXU) return warp_maxu64(x);
+    return warp_oru64(x);
+}
+__device__ __forceinline__ unsigned long long sk_ident(int op) { return op == OP_MINU ? ~0ull : 0ull; }
+
 struct SkRed {
     SkSmem *S;
     cg::cluster_group *cluster;
     uint32_t crank, CS, phase;
 };
 
-__device__ inline long long sk_identity(int op) { return (op == 0 || op == 3) ? 0 : (op == 1 ? INT64_MAX : INT64_MIN); }
-
-__device__ inline long long sk_combine(long long a, long long b, int op) {
-    return op == 0 ? a + b : (op == 1 ? (a < b ? a : b) : (op == 2 ? (a > b ? a : b) : (a | b)));
-}
-
-template <int NVAL, bool PAYLOAD>
-__device__ inline void sk_allreduce(SkRed &R, long long (&v)[NVAL], const int (&op)[NVAL], long long (&pl)[SK_PAYLOAD]) {
+// All-reduce NVAL values over the cluster; every thread returns with the reduced values in v[].
+template <int NVAL>
+__device__ inline void sk_allreduce(SkRed &R, unsigned long long (&v)[NVAL], const int (&op)[NVAL]) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    constexpr int W = SK_NV + SK_PAYLOAD;
-    // 1) warp level
+    SkSmem &S = *R.S;
 #pragma unroll
-    for (int i = 0; i < NVAL; i++) {
-        long long x = v[i];
-        if (PAYLOAD && i == 0) {
-            // arg-max: find the winning lane, broadcast its payload
-            long long m = x;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { long long y = __shfl_xor_sync(0xffffffffu, m, o); m = y > m ? y : m; }
-            unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
-#pragma unroll
-            for (int j = 0; j < SK_PAYLOAD; j++) pl[j] = __shfl_sync(0xffffffffu, pl[j], who);
-            v[i] = m;
-        } else {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = sk_combine(x, __shfl_xor_sync(0xffffffffu, x, o), op[i]);
-            v[i] = x;
-        }
-    }
+    for (int i = 0; i < NVAL; i++) v[i] = warp_op(v[i], op[i]);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < NVAL; i++) R.S->wpart[warp * W + i] = v[i];
-        if (PAYLOAD) {
-#pragma unroll
-            for (int j = 0; j < SK_PAYLOAD; j++) R.S->wpart[warp * W + SK_NV + j] = pl[j];
-        }
+        for (int i = 0; i < NVAL; i++) S.wpart[warp * SK_MSGW + i] = v[i];
     }
     __syncthreads();
-    // 2) CTA level by warp 0, then publish to every CTA of the cluster through DSMEM
     const uint32_t buf = R.phase & 1;
     if (warp == 0) {
-        long long cv[NVAL];
-        long long cpl[SK_PAYLOAD];
+        unsigned long long cv[NVAL];
 #pragma unroll
-        for (int i = 0; i < NVAL; i++) {
-            long long x = lane < nwarp ? R.S->wpart[lane * W + i] : sk_identity(op[i]);
-            if (PAYLOAD && i == 0) {
-                long long m = x;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { long long y = __shfl_xor_sync(0xffffffffu, m, o); m = y > m ? y : m; }
-                unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
-#pragma unroll
-                for (int j = 0; j < SK_PAYLOAD; j++) {
-                    long long p = lane < nwarp ? R.S->wpart[lane * W + SK_NV + j] : 0;
-                    cpl[j] = __shfl_sync(0xffffffffu, p, who);
-                }
-                cv[i] = m;
-            } else {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x = sk_combine(x, __shfl_xor_sync(0xffffffffu, x, o), op[i]);
-                cv[i] = x;
-            }
-        }
+        for (int i = 0; i < NVAL; i++) cv[i] = warp_op(lane < nwarp ? S.wpart[lane * SK_MSGW + i] : sk_ident(op[i]), op[i]);
         if (lane < R.CS) {
-            long long *dst = R.cluster->map_shared_rank(R.S->inbox, lane) + (buf * SK_MAX_CS + R.crank) * W;
+            unsigned long long *dst = R.cluster->map_shared_rank(S.inbox, lane) + (buf * SK_MAX_CS + R.crank) * SK_MSGW;
 #pragma unroll
             for (int i = 0; i < NVAL; i++) dst[i] = cv[i];
-            if (PAYLOAD) {
-#pragma unroll
-                for (int j = 0; j < SK_PAYLOAD; j++) dst[SK_NV + j] = cpl[j];
-            }
         }
     }
     R.cluster->sync();
-    // 3) every warp folds the CS partials (lane = source CTA)
+    if (warp == 0) {
 #pragma unroll
-    for (int i = 0; i < NVAL; i++) {
-        long long x = lane < R.CS ? R.S->inbox[(buf * SK_MAX_CS + lane) * W + i] : sk_identity(op[i]);
-        if (PAYLOAD && i == 0) {
-            long long m = x;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { long long y = __shfl_xor_sync(0xffffffffu, m, o); m = y > m ? y : m; }
-            unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
-#pragma unroll
-            for (int j = 0; j < SK_PAYLOAD; j++) {
-                long long p = lane < R.CS ? R.S->inbox[(buf * SK_MAX_CS + lane) * W + SK_NV + j] : 0;
-                pl[j] = __shfl_sync(0xffffffffu, p, who);
-            }
-            v[i] = m;
-        } else {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = sk_combine(x, __shfl_xor_sync(0xffffffffu, x, o), op[i]);
-            v[i] = x;
+        for (int i = 0; i < NVAL; i++) {
+            unsigned long long x = warp_op(lane < R.CS ? S.inbox[(buf * SK_MAX_CS + lane) * SK_MSGW + i] : sk_ident(op[i]), op[i]);
+            if (lane == 0) S.fin[i] = x;
         }
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) v[i] = S.fin[i];
     R.phase++;
+}
+
+// Arg-max over the cluster of a unique u64 key (0 = no candidate); the payload of the winner (its topology
+// domains + node flags, read from the owning CTA's shared memory) travels with the key.
+// Every thread returns the winning key; pay[0..9] holds the payload.
+__device__ inline unsigned long long sk_argmax(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, int32_t (&pay)[10]) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    SkSmem &S = *R.S;
+    key = warp_maxu64(key);
+    if (lane == 0) S.wpart[warp * SK_MSGW] = key;
+    __syncthreads();
+    const uint32_t buf = R.phase & 1;
+    if (warp == 0) {
+        unsigned long long k = warp_maxu64(lane < nwarp ? S.wpart[lane * SK_MSGW] : 0ull);
+        // payload of the CTA-local winner: lane t reads domain t, lane 8 reads the node flags
+        int32_t pw = -1;
+        if (k != 0) {
+            uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
+            uint32_t idx = (r / CT) * TPB + (r % CT) % TPB;
+            if (lane < S.T) pw = S.a32[(B_N32 + lane) * S.L + idx];
+            else if (lane == 8) pw = S.a8[C_NFLAGS * S.L + idx];
+        }
+        unsigned long long w[SK_PLW];
+#pragma unroll
+        for (int j = 0; j < SK_PLW; j++) {
+            unsigned lo = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j), hi = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j + 1);
+            w[j] = ((unsigned long long)hi << 32) | lo;
+        }
+        if (lane < R.CS) {
+            unsigned long long *dst = R.cluster->map_shared_rank(S.inbox, lane) + (buf * SK_MAX_CS + R.crank) * SK_MSGW;
+            dst[0] = k;
+#pragma unroll
+            for (int j = 0; j < SK_PLW; j++) dst[SK_NV + j] = w[j];
+        }
+    }
+    R.cluster->sync();
+    if (warp == 0) {
+        unsigned long long x = lane < R.CS ? S.inbox[(buf * SK_MAX_CS + lane) * SK_MSGW] : 0ull;
+        unsigned long long m = warp_maxu64(x);
+        unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
+        if (lane == 0) S.fin[0] = m;
+        if (lane < SK_PLW) S.fin[SK_NV + lane] = S.inbox[(buf * SK_MAX_CS + who) * SK_MSGW + SK_NV + lane];
+    }
+    __syncthreads();
+    unsigned long long m = S.fin[0];
+#pragma unroll
+    for (int j = 0; j < SK_PLW; j++) {
+        unsigned long long w = S.fin[SK_NV + j];
+        pay[2 * j] = (int32_t)(unsigned)w;
+        pay[2 * j + 1] = (int32_t)(unsigned)(w >> 32);
+    }
+    R.phase++;
+    return m;
 }

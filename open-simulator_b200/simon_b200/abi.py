@@ -25,7 +25,7 @@ class SimonSnapshot(C.Structure):
 class SimonPodset(C.Structure):
     _fields_ = [
         ("n_classes", C.c_uint32), ("n_pods", C.c_uint32), ("n_counters", C.c_uint32),
-        ("n_static_rows", C.c_uint32), ("n_extra_rows", C.c_uint32), ("reserved", C.c_uint32),
+        ("n_static_rows", C.c_uint32), ("n_extra_rows", C.c_uint32), ("n_static_sigs", C.c_uint32),
         ("class_off", C.c_void_p), ("class_blob", C.c_void_p), ("pod_class", C.c_void_p),
         ("pod_fixed_node", C.c_void_p), ("counter_topo", C.c_void_p), ("simon_raw", C.c_void_p),
         ("extra_score", C.c_void_p),

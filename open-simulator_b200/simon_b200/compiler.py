@@ -45,15 +45,18 @@ N_FAIL_CODES = 24
 NODE_UNSCHEDULABLE = 1
 NODE_HAS_LABELS = 2
 (SCW_REQ_MCPU, SCW_REQ_MEM, SCW_REQ_EPH, SCW_NZ_MCPU, SCW_NZ_MEM, SCW_SCORE_MCPU, SCW_SCORE_MEM, SCW_GPU_MEM,
- SCW_GPU_COUNT, SCW_FLAGS, SCW_NODE_NAME, SCW_STATIC_ROW, SCW_EXTRA_ROW, SCW_GUARD_NODE, SCW_OFF_SCALARS, SCW_OFF_TOL, SCW_OFF_SEL,
+ SCW_GPU_COUNT, SCW_FLAGS, SCW_NODE_NAME, SCW_STATIC_ROW, SCW_EXTRA_ROW, SCW_GUARD_NODE, SCW_STATIC_SIG, SCW_OFF_SCALARS, SCW_OFF_TOL, SCW_OFF_SEL,
  SCW_OFF_PREF, SCW_N_PREF, SCW_OFF_PORTS, SCW_N_PORTS, SCW_OFF_PTS_HARD, SCW_N_PTS_HARD, SCW_OFF_PTS_SOFT,
  SCW_N_PTS_SOFT, SCW_OFF_IPA_AFF, SCW_N_IPA_AFF, SCW_OFF_IPA_ANTI, SCW_N_IPA_ANTI, SCW_OFF_IPA_EXIST,
- SCW_N_IPA_EXIST, SCW_OFF_IPA_SCORE, SCW_N_IPA_SCORE, SCW_OFF_INC, SCW_N_INC, SCW_HDR_WORDS) = range(36)
+ SCW_N_IPA_EXIST, SCW_OFF_IPA_SCORE, SCW_N_IPA_SCORE, SCW_OFF_INC, SCW_N_INC, SCW_OFF_ENT, SCW_N_ENT, SCW_ANY_TABLE,
+ SCW_HDR_WORDS) = range(40)
 CLS_HAS_REQUEST = 1
 CLS_TOL_UNSCHED = 2
 CLS_IPA_SELF_MATCH = 4
 CLS_SIMON_NOREQ = 8
 REQ_ANY, REQ_NONE, REQ_NODE_IS, REQ_NODE_ISNOT = 1, 2, 3, 4
+EK_PORT, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE = range(7)
+SK_MAXW = 6      # domain-bitmask words the engine reduces per decision (csrc/simon_kernel.cuh)
 
 DEFAULT_MILLI_CPU_REQUEST = 100
 DEFAULT_MEMORY_REQUEST = 200 * 1024 * 1024
@@ -819,8 +822,14 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
     extra_score = np.stack(extra_rows) if extra_rows else np.zeros((1, max(N, 1)), np.int32)
 
     # ---- class blobs ----
+    cnt_base = np.zeros(max(1, n_counters), np.int64)
+    acc = 0
+    for kid, (_S, t, _sig) in enumerate(counters.items):
+        cnt_base[kid] = acc
+        acc += int(topo_ndom[t])
     blob: List[int] = []
     class_off = [0]
+    static_sigs = _Interner()
     for c in classes:
         L = per_class[c.cid]
         w = [0] * SCW_HDR_WORDS
@@ -903,6 +912,47 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
         w[SCW_N_INC] = len(inc_lists[c.cid])
         for e in inc_lists[c.cid]:
             body.extend(e)
+        # engine entry table: one 8-word row per list entry (kind, counter, topo, a, b, inc, bitmask word offset, counter base)
+        put(SCW_OFF_ENT)
+        ent_rows = []
+        inc_set = {(kid, t) for (kid, t, _sig) in inc_lists[c.cid]}
+        for kid in L["ports"]:
+            ent_rows.append([EK_PORT, kid, 0, 0, 0])
+        for (kid, t, skew, selfm) in L["hard"]:
+            ent_rows.append([EK_HARD, kid, t, skew, selfm])
+        for (nodek, t, skew, host, domk) in L["soft"]:
+            ent_rows.append([EK_SOFT, nodek if host else domk, t, skew, host])
+        for (kid, t) in L["aff"]:
+            ent_rows.append([EK_AFF, kid, t, 0, 0])
+        for (kid, t) in L["anti"]:
+            ent_rows.append([EK_ANTI, kid, t, 0, 0])
+        for (kid, t) in ex:
+            ent_rows.append([EK_EXIST, kid, t, 0, 0])
+        for (kid, t), wt in sc:
+            ent_rows.append([EK_SCORE, kid, t, wt, 0])
+        woff = 0
+        any_table = 0
+        for r in ent_rows:
+            kind, kid, t, a, b = r
+            tk = 0 if (kind == EK_SOFT and b) else t
+            inc = 1 if (kid, tk) in inc_set else 0
+            wo = -1
+            if kind == EK_SOFT and not b:
+                nw = (int(topo_ndom[t]) + 63) // 64
+                if woff + nw <= SK_MAXW:
+                    wo = woff
+                    woff += nw
+                else:
+                    any_table = 1
+            r.extend([inc, wo, int(cnt_base[kid])])
+        w[SCW_N_ENT] = len(ent_rows)
+        w[SCW_ANY_TABLE] = any_table
+        for r in ent_rows:
+            body.extend(r)
+        # static signature: everything the per-(class, node) static evaluation depends on
+        skey = (tuple(body[w[SCW_OFF_TOL] - SCW_HDR_WORDS:w[SCW_OFF_PORTS] - SCW_HDR_WORDS]), w[SCW_NODE_NAME],
+                flags & CLS_TOL_UNSCHED, tuple(e[1] for e in L["hard"]), tuple(e[1] for e in L["soft"]))
+        w[SCW_STATIC_SIG] = static_sigs.get(skey)
         blob.extend(w)
         blob.extend(body)
         class_off.append(len(blob))
@@ -923,7 +973,7 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
         "pod_class": pod_class, "pod_fixed_node": pod_fixed, "counter_topo": counter_topo,
         "simon_raw": np.ascontiguousarray(simon_raw), "extra_score": np.ascontiguousarray(extra_score.astype(np.int32)),
     }
-    pods_dims = {"n_classes": C, "n_pods": len(pods), "n_counters": n_counters,
+    pods_dims = {"n_classes": C, "n_pods": len(pods), "n_counters": n_counters, "n_static_sigs": max(1, len(static_sigs.items)),
                  "n_static_rows": simon_raw.shape[0], "n_extra_rows": len(extra_rows)}
     return Compiled(N, node_names, order, snodes, snap, snap_dims, podset, pods_dims, classes, scalar_names,
                     list(taint_ids.items), list(topo.items), list(counters.items), list(pods))

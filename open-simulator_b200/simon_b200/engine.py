@@ -19,7 +19,7 @@ _LIB = None
 
 EXPORTS = ["simon_gpu_version", "simon_ctx_create", "simon_ctx_destroy", "simon_last_error", "simon_snapshot_upload",
            "simon_pods_upload", "simon_state_reset", "simon_schedule", "simon_results_download", "simon_last_kernel_ms",
-           "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay"]
+           "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay", "simon_stats"]
 
 
 class EngineUnavailable(RuntimeError):
@@ -52,6 +52,8 @@ def lib():
     L.simon_results_download.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     L.simon_replay.restype = C.c_int
     L.simon_replay.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    L.simon_stats.restype = C.c_int
+    L.simon_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.simon_last_kernel_ms.restype = C.c_float
     L.simon_last_kernel_ms.argtypes = [C.c_void_p]
     L.simon_launch_count.restype = C.c_uint64
@@ -138,6 +140,14 @@ class Engine:
         ms = C.c_float(0)
         self._check(lib().simon_replay(self.h, steps, C.byref(ms)))
         return float(ms.value)
+
+    def stats(self):
+        a = np.zeros(32, np.uint64)
+        self._check(lib().simon_stats(self.h, a.ctypes.data))
+        return dict(decisions=int(a[0]), class_switches=int(a[1]), summary_rebuilds=int(a[2]), redone=int(a[3]), static_evals=int(a[4]),
+                    cycles=dict(zip(['loop', 'fixed', 'class_change_tail', 'r1', 'p1', 'reduce_steady', 'reduce_summary', 'p3', 'argmax', 'commit',
+                                     'cc_pre', 'cc_sync', 'cc_blob', 'cc_entry', 'cc_static'],
+                                    [int(x) for x in a[8:23]])))
 
     def last_kernel_ms(self) -> float:
         return float(lib().simon_last_kernel_ms(self.h))

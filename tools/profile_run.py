@@ -31,3 +31,4 @@ with Engine(c, device=0, cluster_ctas=a.cluster_ctas, threads_per_cta=a.threads)
     for _ in range(a.reps):
         eng.schedule(first, a.pods, download=False)
         print(f"placed {a.pods} pods in {eng.last_kernel_ms():.3f} ms -> {a.pods / eng.last_kernel_ms() * 1e3:.0f} decisions/s")
+    print("stats", eng.stats())
