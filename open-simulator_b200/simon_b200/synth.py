@@ -208,3 +208,37 @@ def make_c3(n_nodes: int = 10000, n_workloads: int = 1000, replicas: int = 100, 
         apps[w % n_apps].Resource.Deployments.append(_deployment(name, ns, replicas, labels, cpu, mem, extra))
         cluster.Services.append(_service(name, ns, {"app": name}))
     return cluster, apps
+
+
+def make_c4(n_nodes: int = 2000, n_workloads: int = 50, replicas: int = 100, fill_pct: int = 85, seed_no: int = 4):
+    """C4: base cluster ~fill_pct % full + pending pods that do not all fit; 8 candidate node specs.
+    Returns (cluster, apps, specs)."""
+    rng = SplitMix64(SEED_BASE + seed_no)
+    cluster = ResourceTypes()
+    for i in range(n_nodes):
+        cores = rng.pick(CPU_SHAPES)
+        eph = rng.pick([100, 200, 500, 1000, 2048])
+        cluster.Nodes.append(_node(f"node-{i:05d}", cores, f"zone-{i % 16:02d}", "", eph))
+        # one running "filler" pod per node occupying ~fill_pct % of cpu and memory
+        cpu_m = cores * 10 * fill_pct
+        mem_mi = cores * 4 * 1024 * fill_pct // 100
+        cluster.Pods.append({"apiVersion": "v1", "kind": "Pod",
+                             "metadata": {"name": f"filler-{i:05d}", "namespace": "kube-system", "labels": {"app": "filler"}},
+                             "spec": {"nodeName": f"node-{i:05d}",
+                                      "containers": [{"name": "c", "image": "registry.local/filler:v1",
+                                                      "resources": {"requests": {"cpu": f"{cpu_m}m", "memory": f"{mem_mi}Mi"}}}]}})
+    app = AppResource("pending", ResourceTypes())
+    for w in range(n_workloads):
+        name = f"pend-{w:03d}"
+        cpu = _log_uniform(rng, 500, 8000, 50)
+        mem = _log_uniform(rng, 512, 32768, 64)
+        extra = {}
+        if rng.chance(20):
+            extra["affinity"] = {"podAntiAffinity": {"requiredDuringSchedulingIgnoredDuringExecution": [
+                {"labelSelector": {"matchLabels": {"app": name}}, "topologyKey": "kubernetes.io/hostname"}]}}
+        app.Resource.Deployments.append(_deployment(name, "default", replicas, {"app": name}, cpu, mem, extra))
+        cluster.Services.append(_service(name, "default", {"app": name}))
+    specs = []
+    for si, cores in enumerate(CPU_SHAPES):
+        specs.append(_node(f"spec-{si}", cores, f"zone-{si % 16:02d}", "", 500))
+    return cluster, [app], specs

@@ -57,3 +57,37 @@ def test_incremental_calls_match_single_call():
         a, _, _, _ = eng.schedule(0, P // 3)
         b, _, _, _ = eng.schedule(P // 3, P - P // 3)
     np.testing.assert_array_equal(np.concatenate([a, b]), ref)
+
+
+def test_full_size_c3_properties():
+    """BASELINE.json's 10k-node x 100k-pod configuration: size-independent properties + an oracle-checked prefix."""
+    from oracle.binding import Oracle
+    p, c = make_case("c3", n_nodes=10000, n_workloads=1000, replicas=100, n_apps=10, seed_no=3)
+    with _engine(c) as eng:
+        out, score, fc, fp = eng.schedule()
+        st = eng.state()
+        eng.reset()
+        out2, _, fc2, fp2 = eng.schedule()
+    # idempotence: a second pass from the empty state reproduces every placement and every failure histogram
+    np.testing.assert_array_equal(out, out2)
+    np.testing.assert_array_equal(fc, fc2)
+    # accounting: NodeInfo aggregates equal the sum over placed pods, and no node is over-committed
+    cls = c.pods["pod_class"]
+    blob, off = c.pods["class_blob"], c.pods["class_off"]
+    req = np.array([[blob[int(off[k]) + w] for w in (0, 1, 2)] for k in range(c.pods_dims["n_classes"])], dtype=np.int64)
+    placed = out >= 0
+    for col, name in enumerate(["req_mcpu", "req_mem", "req_eph"]):
+        agg = np.zeros(c.n_nodes, np.int64)
+        np.add.at(agg, out[placed], req[cls[placed], col])
+        np.testing.assert_array_equal(agg, st[name], err_msg=name)
+    assert (st["req_mcpu"] <= c.snap["alloc_mcpu"]).all() and (st["req_mem"] <= c.snap["alloc_mem"]).all()
+    assert (st["num_pods"] <= c.snap["alloc_pods"]).all()
+    assert int(st["num_pods"].sum()) == int(placed.sum())
+    # every unschedulable pod has a complete reason histogram (one or more reasons per node)
+    assert len(fp) == int((out == -1).sum())
+    assert (fc.sum(axis=1) >= c.n_nodes).all()
+    # oracle-checked prefix: pre-bound pods + the first 3000 scheduled pods
+    first = int(np.argmax(c.pods["pod_fixed_node"] == -1))
+    o = Oracle(c)
+    ref, _, _, _ = o.schedule(0, first + 3000)
+    np.testing.assert_array_equal(out[: first + 3000], ref)
