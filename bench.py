@@ -177,6 +177,7 @@ def main():
     from simon_b200.engine import Engine
     p, c, host_s = build_workload(args, 3 + rank)          # replicas: distinct seeds per rank
     P = int(c.pods_dims["n_pods"])
+    D = int((c.pods["pod_fixed_node"] == -1).sum())        # decisions = pods that go through filter+score (pre-bound pods excluded)
     eng = Engine(c, device=local, cluster_ctas=args.cluster_ctas, threads_per_cta=args.threads)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
@@ -205,7 +206,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * P * args.steps / (ms_max * 1e-3)
+    value = world * D * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: host buffers -> C ABI -> host results ----
     from simon_b200 import abi
@@ -229,16 +230,22 @@ def main():
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * P * len(e2e_times) / float(te.item())
+    e2e_value = world * D * len(e2e_times) / float(te.item())
     placed = int((out_node >= 0).sum())
 
     if rank == 0:
         peak, peak_src = peaks()
-        per_gpu_dps = P * args.steps / (ms_total * 1e-3)
+        per_gpu_dps = D * args.steps / (ms_total * 1e-3)
         achieved = per_gpu_dps * ALGO_BYTES_PER_NODE_DECISION * args.nodes / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
+            traffic = prof["dram_bytes_per_launch"]      # dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "note": f"algorithmic bytes = {ALGO_BYTES_PER_NODE_DECISION} B/node-decision x {args.nodes} nodes x {P} decisions per launch; "
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NODE_DECISION * args.nodes * D,
+                "note": f"algorithmic bytes = {ALGO_BYTES_PER_NODE_DECISION} B/node-decision x {args.nodes} nodes x {D} decisions per launch; "
                         "the snapshot is cluster-resident in shared memory, so DRAM traffic << algorithmic bytes"}
         cb = None
         if not args.no_cpu_baseline:
@@ -260,7 +267,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cb,
                 "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * P + 8),
                         "path": "simon_snapshot_upload + simon_pods_upload + simon_schedule(host out_node), wall clock"},
-                "gpu_launches": int(launches), "clocks": clocks, "placed": placed, "unschedulable": int((out_node == -1).sum()),
+                "gpu_launches": int(launches), "clocks": clocks, "decisions_per_step": D, "prebound_pods_per_step": P - D, "placed": placed, "unschedulable": int((out_node == -1).sum()),
                 "wall_s_timed_region": wall, "host_compile_s": host_s}
         print(json.dumps(line), flush=True)
     eng.close()
