@@ -200,7 +200,7 @@ static_assert(sizeof(SkScenario) % 8 == 0, "SkScenario is copied in 8-byte words
 
 int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t TPB, size_t smem, bool record = true) {
     sk_kernel_fn fn;
-    const uint32_t npt = P.npt;
+    const uint32_t npt = getenv("SIMON_NO_UNROLL") ? 0u : P.npt;
     if (TPB <= 256) fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
     else if (TPB <= 512) fn = npt == 1 ? simon_place_kernel_512_1 : npt == 2 ? simon_place_kernel_512_2 : simon_place_kernel_512_0;
     else fn = npt == 1 ? simon_place_kernel_1024_1 : simon_place_kernel_1024_0;

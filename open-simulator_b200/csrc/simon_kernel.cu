@@ -165,7 +165,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     __syncthreads();
     const SkScenario &SC = *S.scen;
     const uint32_t NA = SC.n_active;
-    SkRed R{&S, &cluster, crank, CS, 0};
+    SkRed R{&S, &cluster, crank, CS, 0, 0};
+    sk_red_init(R);
     const ReqCtx RC{P.label_bits, N};
     const bool leader = (gtid == 0);
     unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0;
@@ -826,7 +827,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         }
         TICK(7);
         int32_t pay[10];
-        best = sk_argmax(R, best, CT, TPB, pay);
+        const int32_t *wpay;
+        best = sk_argmax2(R, best, CT, TPB, pay, wpay);
         TICK(8);
         const uint32_t win_r = 0xFFFFFFu - (uint32_t)(best & 0xFFFFFFu);
         const int64_t win_total = (int64_t)(best >> 24) - 1;
@@ -870,7 +872,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             if (!ENT(ER_INC, e)) continue;
             int32_t kind = ENT(ER_KIND, e), t = ENT(ER_T, e);
             bool host = kind == EK_SOFT && ENT(ER_B, e);
-            int32_t wd = ((const int32_t *)&S.fin[SK_NV])[host ? 0 : t];
+            int32_t wd = wpay[host ? 0 : t];
             if (kind == EK_SOFT && !host && win_ignored) continue;
             if (wd < 0) continue;
             const uint32_t trow = host ? 0 : (uint32_t)t;

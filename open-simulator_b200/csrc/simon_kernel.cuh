@@ -116,6 +116,9 @@ struct SkSmem {
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
     int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
     SkScenario *scen;    // this cluster's scenario descriptor
+    unsigned long long *acc;     // [3][SK_MSGW] CTA-level accumulators of the mbarrier all-reduce
+    unsigned long long *mbar;    // [2] mbarriers guarding the two abox buffers
+    unsigned long long *abox;    // [2][SK_MAX_CS][SK_MSGW] inbox of the mbarrier-based reductions
     uint32_t L, T;
 };
 
@@ -131,6 +134,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     b += sk_align(4ull * SIMON_MAX_TOPOS);
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
+    b += sk_align(8ull * 3 * SK_MSGW) + sk_align(8ull * 2) + sk_align(8ull * 2 * SK_MAX_CS * SK_MSGW);
     return b + 64;
 }
 
@@ -147,7 +151,10 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
-    S.scen = (SkScenario *)p;
+    S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
+    S.acc = (unsigned long long *)p; p += sk_align(8ull * 3 * SK_MSGW);
+    S.mbar = (unsigned long long *)p; p += sk_align(8ull * 2);
+    S.abox = (unsigned long long *)p;
     S.L = L; S.T = T;
 }
 
@@ -187,6 +194,7 @@ struct SkRed {
     SkSmem *S;
     cg::cluster_group *cluster;
     uint32_t crank, CS, phase;
+    uint32_t mph;      // phase counter of the mbarrier-based reductions (own inbox + mbarrier pair)
 };
 
 // All-reduce NVAL values over the cluster; every thread returns with the reduced values in v[].
@@ -276,5 +284,139 @@ __device__ inline unsigned long long sk_argmax(SkRed &R, unsigned long long key,
         pay[2 * j + 1] = (int32_t)(unsigned)(w >> 32);
     }
     R.phase++;
+    return m;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Low-latency cluster all-reduce: warp redux -> shared-memory atomics -> ONE __syncthreads -> every CTA's warp 0
+// pushes its CTA's partials into every CTA's inbox with st.async (DSMEM store that completes a transaction on the
+// destination's mbarrier) -> all threads wait on their LOCAL mbarrier -> every warp folds the CS partials itself.
+// No barrier.cluster, no second __syncthreads.
+__device__ __forceinline__ uint32_t sk_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void sk_mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_expect(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sk_saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t a = sk_saddr(bar), ok = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint32_t sk_mapa(uint32_t laddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void sk_st_async(uint32_t raddr, unsigned long long v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(v), "r"(rbar) : "memory");
+}
+
+// must be called once by every thread of the cluster before the first sk_allreduce2 / sk_argmax2
+__device__ inline void sk_red_init(SkRed &R) {
+    SkSmem &S = *R.S;
+    if (threadIdx.x == 0) {
+        sk_mbar_init(&S.mbar[0], 1);
+        sk_mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = threadIdx.x; i < 3 * SK_MSGW; i += blockDim.x) S.acc[i] = 0;
+    __syncthreads();
+    R.cluster->sync();
+}
+
+// All accumulators use identity 0: a MIN is carried as the MAX of the complemented value.
+__device__ __forceinline__ unsigned long long sk_fwd(unsigned long long x, int op) { return op == OP_MINU ? ~x : x; }
+__device__ __forceinline__ int sk_rop(int op) { return op == OP_MINU ? OP_MAXU : op; }
+__device__ __forceinline__ void sk_acc_atomic(unsigned long long *a, unsigned long long v, int op) {
+    if (op == OP_SUM32) atomicAdd(a, v);
+    else if (op == OP_OR) atomicOr(a, v);
+    else atomicMax(a, v);
+}
+
+template <int NVAL>
+__device__ inline void sk_allreduce2(SkRed &R, unsigned long long (&v)[NVAL], const int (&op)[NVAL]) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SkSmem &S = *R.S;
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1;
+    unsigned long long *acc = S.acc + (ph % 3) * SK_MSGW;
+    // clear the accumulators of the NEXT phase (last read two phases ago); arm this phase's mbarrier
+    if (threadIdx.x < SK_MSGW) S.acc[((ph + 1) % 3) * SK_MSGW + threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], R.CS * NVAL * 8u);
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) {
+        unsigned long long x = warp_op(sk_fwd(v[i], op[i]), sk_rop(op[i]));
+        if (lane == 0) sk_acc_atomic(&acc[i], x, op[i]);
+    }
+    __syncthreads();
+    if (warp == 0 && lane < R.CS) {
+        const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
+        const uint32_t rbox = sk_mapa(sk_saddr(S.abox + (buf * SK_MAX_CS + R.crank) * SK_MSGW), lane);
+#pragma unroll
+        for (int i = 0; i < NVAL; i++) sk_st_async(rbox + 8u * i, acc[i], rbar);
+    }
+    sk_mbar_wait(&S.mbar[buf], parity);
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) {
+        unsigned long long x = warp_op(lane < R.CS ? S.abox[(buf * SK_MAX_CS + lane) * SK_MSGW + i] : 0ull, sk_rop(op[i]));
+        v[i] = sk_fwd(x, op[i]);
+    }
+    R.mph++;
+}
+
+// arg-max variant: value 0 is the key (0 = no candidate); the winner's payload (domains + flags) is read from the owning
+// CTA's shared memory by that CTA's warp 0 and travels in the same message.
+__device__ inline unsigned long long sk_argmax2(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, int32_t (&pay)[10],
+                                                 const int32_t *&wpay) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SkSmem &S = *R.S;
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1;
+    unsigned long long *acc = S.acc + (ph % 3) * SK_MSGW;
+    if (threadIdx.x < SK_MSGW) S.acc[((ph + 1) % 3) * SK_MSGW + threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], R.CS * (1 + SK_PLW) * 8u);
+    key = warp_maxu64(key);
+    if (lane == 0) atomicMax(&acc[0], key);
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long k = acc[0];
+        int32_t pw = -1;
+        if (k != 0) {
+            uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
+            uint32_t idx = (r / CT) * TPB + (r % CT) % TPB;
+            if (lane < S.T) pw = S.a32[(B_N32 + lane) * S.L + idx];
+            else if (lane == 8) pw = S.a8[C_NFLAGS * S.L + idx];
+        }
+        unsigned long long w[SK_PLW];
+#pragma unroll
+        for (int j = 0; j < SK_PLW; j++) {
+            unsigned lo = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j), hi = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j + 1);
+            w[j] = ((unsigned long long)hi << 32) | lo;
+        }
+        if (lane < R.CS) {
+            const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
+            const uint32_t rbox = sk_mapa(sk_saddr(S.abox + (buf * SK_MAX_CS + R.crank) * SK_MSGW), lane);
+            sk_st_async(rbox, k, rbar);
+#pragma unroll
+            for (int j = 0; j < SK_PLW; j++) sk_st_async(rbox + 8u * (SK_NV + j), w[j], rbar);
+        }
+    }
+    sk_mbar_wait(&S.mbar[buf], parity);
+    unsigned long long x = lane < R.CS ? S.abox[(buf * SK_MAX_CS + lane) * SK_MSGW] : 0ull;
+    unsigned long long m = warp_maxu64(x);
+    unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
+    const unsigned long long *pl = S.abox + (buf * SK_MAX_CS + who) * SK_MSGW + SK_NV;
+    wpay = (const int32_t *)pl;     // stays valid until the next-but-one mbarrier reduction
+#pragma unroll
+    for (int j = 0; j < SK_PLW; j++) {
+        unsigned long long w = pl[j];
+        pay[2 * j] = (int32_t)(unsigned)w;
+        pay[2 * j + 1] = (int32_t)(unsigned)(w >> 32);
+    }
+    R.mph++;
     return m;
 }

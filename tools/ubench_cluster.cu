@@ -7,27 +7,29 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
     cg::cluster_group cluster = cg::this_cluster();
     SkSmem S;
     sk_carve(S, smem_raw, blockDim.x, 2, 4, 64);
-    SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0};
-    __syncthreads();
-    cluster.sync();
+    SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0, 0};
+    sk_red_init(R);
     long long t0 = clock64();
     unsigned long long acc = threadIdx.x;
     for (int i = 0; i < iters; i++) {
         if (mode == 0) cluster.sync();
         else if (mode == 1) { unsigned long long v[5] = {acc, acc + 1, acc + 2, acc + 3, acc & 1}; const int op[5] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR}; sk_allreduce<5>(R, v, op); acc += v[1]; }
         else if (mode == 2) { unsigned long long v[16]; int op[16]; for (int q = 0; q < 16; q++) { v[q] = acc + q; } const int opc[16] = {0,0,2,2,2,1,1,2,1,2,3,3,3,3,3,3}; sk_allreduce<16>(R, v, opc); acc += v[2]; }
-        else if (mode == 3) { int32_t pay[10]; unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, pay); acc += k + pay[0]; }
+        else if (mode == 3) { int32_t pay[10]; unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, pay, wp); acc += k + pay[0]; }
         else if (mode == 4) __syncthreads();
         else if (mode == 5) { __threadfence(); cluster.sync(); }
+        else if (mode == 6) { unsigned long long v[5] = {acc, acc + 1, acc + 2, acc + 3, acc & 1}; const int op[5] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR}; sk_allreduce2<5>(R, v, op); if (i == iters - 1 && threadIdx.x == 0 && blockIdx.x == 0) { out[2] = (long long)v[0]; out[3] = (long long)v[1]; } acc += v[1]; }
+        else if (mode == 7) { unsigned long long v[16]; for (int q = 0; q < 16; q++) { v[q] = acc + q; } const int opc[16] = {0,0,2,2,2,1,1,2,1,2,3,3,3,3,3,3}; sk_allreduce2<16>(R, v, opc); acc += v[2]; }
+        else if (mode == 8) { int32_t pay[10]; const int32_t *wp; unsigned long long k = sk_argmax2(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, pay, wp); acc += k + pay[0]; }
     }
     long long t1 = clock64();
     if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (t1 - t0) / iters; out[1] = (long long)acc; }
 }
 
 int main() {
-    long long *d; cudaMalloc(&d, 16);
-    const char *names[6] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync"};
-    for (int cs : {1, 2, 4, 8, 16}) for (int tpb : {256, 640}) for (int mode = 0; mode < 6; mode++) {
+    long long *d; cudaMalloc(&d, 64);
+    const char *names[9] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "allreduce2<5> (mbarrier)", "allreduce2<16> (mbarrier)", "argmax2 (mbarrier)"};
+    for (int cs : {1, 4, 16}) for (int tpb : {256, 640}) for (int mode = 0; mode < 9; mode++) {
         size_t smem = sk_smem_bytes(tpb, 2, 4, 64);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -37,9 +39,9 @@ int main() {
         cfg.attrs = at; cfg.numAttrs = 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, k_sync, d, 2000, mode);
         cudaError_t e2 = cudaDeviceSynchronize();
-        long long h[2] = {0, 0};
-        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("cs=%2d tpb=%4d %-26s %6lld cycles  (%s %s)\n", cs, tpb, names[mode], h[0], cudaGetErrorString(e), cudaGetErrorString(e2));
+        long long h[4] = {0, 0, 0, 0};
+        cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+        printf("cs=%2d tpb=%4d %-28s %6lld cycles  acc=%lld (%s %s)\n", cs, tpb, names[mode], h[0], h[1], cudaGetErrorString(e), cudaGetErrorString(e2));
     }
     return 0;
 }
