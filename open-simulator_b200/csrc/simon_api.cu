@@ -187,7 +187,8 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
                 if (t < 64) t = 64;
                 if (t > 256) continue;            // the 256-thread variants keep >= 200 registers/thread (no spills)
             }
-            size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words);
+            if (t > 256) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= 256 (got %u)", t);
+            size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs);
             if (b <= (size_t)max_smem) { CS = cs; TPB = t; NPT = npt; smem = b; return SIMON_OK; }
             if (want_t) break;
         }
@@ -200,10 +201,9 @@ static_assert(sizeof(SkScenario) % 8 == 0, "SkScenario is copied in 8-byte words
 
 int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t TPB, size_t smem, bool record = true) {
     sk_kernel_fn fn;
-    const uint32_t npt = getenv("SIMON_NO_UNROLL") ? 0u : P.npt;
-    if (TPB <= 256) fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
-    else if (TPB <= 512) fn = npt == 1 ? simon_place_kernel_512_1 : npt == 2 ? simon_place_kernel_512_2 : simon_place_kernel_512_0;
-    else fn = npt == 1 ? simon_place_kernel_1024_1 : simon_place_kernel_1024_0;
+    const uint32_t npt = P.npt;
+    if (TPB > 256) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= 256");
+    fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg;

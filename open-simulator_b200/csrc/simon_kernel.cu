@@ -159,13 +159,13 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     const uint32_t N = P.N, T = P.T, K = P.K, WT = P.WT;
 
     SkSmem S;
-    sk_carve(S, smem_raw, L, T, P.emax, P.max_blob_words);
+    sk_carve(S, smem_raw, L, T, P.emax, P.max_blob_words, CS);
     // the scenario descriptor lives in shared memory (kernel-lifetime constant, read after every barrier)
     if (tid < sizeof(SkScenario) / 8) ((unsigned long long *)S.scen)[tid] = ((const unsigned long long *)(P.scen + scen_id))[tid];
     __syncthreads();
     const SkScenario &SC = *S.scen;
     const uint32_t NA = SC.n_active;
-    SkRed R{&S, &cluster, crank, CS, 0, 0};
+    SkRed R{&S, &cluster, crank, CS, 0};
     sk_red_init(R);
     const ReqCtx RC{P.label_bits, N};
     const bool leader = (gtid == 0);
@@ -725,6 +725,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                             if ((uint32_t)q == w) rv[10 + q] |= 1ull << (d & 63);
                     }
             }
+            if (C.any_table) { __threadfence(); cluster.sync(); }     // SC.size / SC.fcount were updated with global atomics in P1
             sk_allreduce<SK_NV>(R, rv, rop);
             C.F = (int64_t)rv[0]; C.n_ign = (int64_t)rv[1]; C.na_max = (int64_t)rv[2]; C.tt_max = (int64_t)rv[3];
             C.simon_max = sk_dec(rv[4]); C.simon_min = sk_dec(rv[5]);
@@ -826,13 +827,12 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             best = key > best ? key : best;
         }
         TICK(7);
-        int32_t pay[10];
-        const int32_t *wpay;
-        best = sk_argmax2(R, best, CT, TPB, pay, wpay);
+        uint32_t who;
+        best = sk_argmax(R, best, CT, TPB, who);
         TICK(8);
         const uint32_t win_r = 0xFFFFFFu - (uint32_t)(best & 0xFFFFFFu);
         const int64_t win_total = (int64_t)(best >> 24) - 1;
-        const bool win_ignored = ((uint32_t)pay[8] & NF_IGNORED) != 0;
+        const bool win_ignored = ((uint32_t)sk_wpay(S, who, 8) & NF_IGNORED) != 0;
 
         // ---- commit (AssumePod / NodeInfo.AddPod) ----
         if (win_r % CT == gtid) {
@@ -872,7 +872,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             if (!ENT(ER_INC, e)) continue;
             int32_t kind = ENT(ER_KIND, e), t = ENT(ER_T, e);
             bool host = kind == EK_SOFT && ENT(ER_B, e);
-            int32_t wd = wpay[host ? 0 : t];
+            int32_t wd = sk_wpay(S, who, host ? 0 : (uint32_t)t);
             if (kind == EK_SOFT && !host && win_ignored) continue;
             if (wd < 0) continue;
             const uint32_t trow = host ? 0 : (uint32_t)t;
@@ -915,8 +915,3 @@ SIMON_KERNEL(256, 1)
 SIMON_KERNEL(256, 2)
 SIMON_KERNEL(256, 3)
 SIMON_KERNEL(256, 4)
-SIMON_KERNEL(512, 0)
-SIMON_KERNEL(512, 1)
-SIMON_KERNEL(512, 2)
-SIMON_KERNEL(1024, 0)
-SIMON_KERNEL(1024, 1)

@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 #define SK_MAXW 6           // domain-bitmask words available per decision
 #define SK_NV 16            // max values per all-reduce
 #define SK_PLW 5            // payload: 10 int32 packed in 5 u64 (T domains + flags)
-#define SK_MSGW (SK_NV + SK_PLW)
+#define SK_MAX_WARPS 8      // threads per CTA <= 256
 #define SK_CSUM_W 16
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
@@ -108,54 +108,46 @@ struct SkSmem {
     int32_t *a32;        // [B_N32 + T + emax][L]
     uint8_t *a8;         // [C_N8][L]
     int64_t *blob;       // [max_blob_words]
-    unsigned long long *inbox;   // [2][SK_MAX_CS][SK_MSGW]
-    unsigned long long *wpart;   // [32][SK_MSGW]
-    unsigned long long *fin;     // [SK_MSGW]
+    unsigned long long *box;     // [2][SK_NV][nslots] reduction inbox: one slot per CTA of the cluster, double buffered
+    unsigned long long *wpart;   // [SK_NV][SK_MAX_WARPS] per-warp partials of the CTA-level fold
     int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
     uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
     int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
     SkScenario *scen;    // this cluster's scenario descriptor
-    unsigned long long *acc;     // [3][SK_MSGW] CTA-level accumulators of the mbarrier all-reduce
-    unsigned long long *mbar;    // [2] mbarriers guarding the two abox buffers
-    unsigned long long *abox;    // [2][SK_MAX_CS][SK_MSGW] inbox of the mbarrier-based reductions
-    uint32_t L, T;
+    unsigned long long *mbar;    // [2] mbarriers guarding the two inbox buffers
+    uint32_t L, T, nslots;
 };
 
-__host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words) {
+__host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words, uint32_t nslots) {
     size_t b = 0;
     b += sk_align(8ull * A_N64 * L);
     b += sk_align(4ull * (B_N32 + T + emax) * L);
     b += sk_align(1ull * C_N8 * L);
     b += sk_align(8ull * blob_words);
-    b += sk_align(8ull * 2 * SK_MAX_CS * SK_MSGW);
-    b += sk_align(8ull * 32 * SK_MSGW);
-    b += sk_align(8ull * SK_MSGW);
+    b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     b += sk_align(4ull * SIMON_MAX_TOPOS);
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
-    b += sk_align(8ull * 3 * SK_MSGW) + sk_align(8ull * 2) + sk_align(8ull * 2 * SK_MAX_CS * SK_MSGW);
+    b += sk_align(8ull * 2);
     return b + 64;
 }
 
-__device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words) {
+__device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words, uint32_t nslots) {
     unsigned char *p = base;
     S.a64 = (int64_t *)p; p += sk_align(8ull * A_N64 * L);
     S.a32 = (int32_t *)p; p += sk_align(4ull * (B_N32 + T + emax) * L);
     S.a8 = (uint8_t *)p; p += sk_align(1ull * C_N8 * L);
     S.blob = (int64_t *)p; p += sk_align(8ull * blob_words);
-    S.inbox = (unsigned long long *)p; p += sk_align(8ull * 2 * SK_MAX_CS * SK_MSGW);
-    S.wpart = (unsigned long long *)p; p += sk_align(8ull * 32 * SK_MSGW);
-    S.fin = (unsigned long long *)p; p += sk_align(8ull * SK_MSGW);
+    S.box = (unsigned long long *)p; p += sk_align(8ull * 2 * SK_NV * nslots);
+    S.wpart = (unsigned long long *)p; p += sk_align(8ull * SK_NV * SK_MAX_WARPS);
     S.ent = (int32_t *)p; p += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
-    S.acc = (unsigned long long *)p; p += sk_align(8ull * 3 * SK_MSGW);
-    S.mbar = (unsigned long long *)p; p += sk_align(8ull * 2);
-    S.abox = (unsigned long long *)p;
-    S.L = L; S.T = T;
+    S.mbar = (unsigned long long *)p;
+    S.L = L; S.T = T; S.nslots = nslots;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -193,106 +185,21 @@ __device__ __forceinline__ unsigned long long sk_ident(int op) { return op == OP
 struct SkRed {
     SkSmem *S;
     cg::cluster_group *cluster;
-    uint32_t crank, CS, phase;
-    uint32_t mph;      // phase counter of the mbarrier-based reductions (own inbox + mbarrier pair)
+    uint32_t crank, CS;
+    uint32_t mph;      // reduction phase counter (selects inbox buffer, mbarrier and parity)
 };
 
-// All-reduce NVAL values over the cluster; every thread returns with the reduced values in v[].
-template <int NVAL>
-__device__ inline void sk_allreduce(SkRed &R, unsigned long long (&v)[NVAL], const int (&op)[NVAL]) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    SkSmem &S = *R.S;
-#pragma unroll
-    for (int i = 0; i < NVAL; i++) v[i] = warp_op(v[i], op[i]);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NVAL; i++) S.wpart[warp * SK_MSGW + i] = v[i];
-    }
-    __syncthreads();
-    const uint32_t buf = R.phase & 1;
-    if (warp == 0) {
-        unsigned long long cv[NVAL];
-#pragma unroll
-        for (int i = 0; i < NVAL; i++) cv[i] = warp_op(lane < nwarp ? S.wpart[lane * SK_MSGW + i] : sk_ident(op[i]), op[i]);
-        if (lane < R.CS) {
-            unsigned long long *dst = R.cluster->map_shared_rank(S.inbox, lane) + (buf * SK_MAX_CS + R.crank) * SK_MSGW;
-#pragma unroll
-            for (int i = 0; i < NVAL; i++) dst[i] = cv[i];
-        }
-    }
-    R.cluster->sync();
-    if (warp == 0) {
-#pragma unroll
-        for (int i = 0; i < NVAL; i++) {
-            unsigned long long x = warp_op(lane < R.CS ? S.inbox[(buf * SK_MAX_CS + lane) * SK_MSGW + i] : sk_ident(op[i]), op[i]);
-            if (lane == 0) S.fin[i] = x;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NVAL; i++) v[i] = S.fin[i];
-    R.phase++;
-}
-
-// Arg-max over the cluster of a unique u64 key (0 = no candidate); the payload of the winner (its topology
-// domains + node flags, read from the owning CTA's shared memory) travels with the key.
-// Every thread returns the winning key; pay[0..9] holds the payload.
-__device__ inline unsigned long long sk_argmax(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, int32_t (&pay)[10]) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    SkSmem &S = *R.S;
-    key = warp_maxu64(key);
-    if (lane == 0) S.wpart[warp * SK_MSGW] = key;
-    __syncthreads();
-    const uint32_t buf = R.phase & 1;
-    if (warp == 0) {
-        unsigned long long k = warp_maxu64(lane < nwarp ? S.wpart[lane * SK_MSGW] : 0ull);
-        // payload of the CTA-local winner: lane t reads domain t, lane 8 reads the node flags
-        int32_t pw = -1;
-        if (k != 0) {
-            uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
-            uint32_t idx = (r / CT) * TPB + (r % CT) % TPB;
-            if (lane < S.T) pw = S.a32[(B_N32 + lane) * S.L + idx];
-            else if (lane == 8) pw = S.a8[C_NFLAGS * S.L + idx];
-        }
-        unsigned long long w[SK_PLW];
-#pragma unroll
-        for (int j = 0; j < SK_PLW; j++) {
-            unsigned lo = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j), hi = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j + 1);
-            w[j] = ((unsigned long long)hi << 32) | lo;
-        }
-        if (lane < R.CS) {
-            unsigned long long *dst = R.cluster->map_shared_rank(S.inbox, lane) + (buf * SK_MAX_CS + R.crank) * SK_MSGW;
-            dst[0] = k;
-#pragma unroll
-            for (int j = 0; j < SK_PLW; j++) dst[SK_NV + j] = w[j];
-        }
-    }
-    R.cluster->sync();
-    if (warp == 0) {
-        unsigned long long x = lane < R.CS ? S.inbox[(buf * SK_MAX_CS + lane) * SK_MSGW] : 0ull;
-        unsigned long long m = warp_maxu64(x);
-        unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
-        if (lane == 0) S.fin[0] = m;
-        if (lane < SK_PLW) S.fin[SK_NV + lane] = S.inbox[(buf * SK_MAX_CS + who) * SK_MSGW + SK_NV + lane];
-    }
-    __syncthreads();
-    unsigned long long m = S.fin[0];
-#pragma unroll
-    for (int j = 0; j < SK_PLW; j++) {
-        unsigned long long w = S.fin[SK_NV + j];
-        pay[2 * j] = (int32_t)(unsigned)w;
-        pay[2 * j + 1] = (int32_t)(unsigned)(w >> 32);
-    }
-    R.phase++;
-    return m;
-}
-
-
 // ---------------------------------------------------------------------------------------------------------
-// Low-latency cluster all-reduce: warp redux -> shared-memory atomics -> ONE __syncthreads -> every CTA's warp 0
-// pushes its CTA's partials into every CTA's inbox with st.async (DSMEM store that completes a transaction on the
-// destination's mbarrier) -> all threads wait on their LOCAL mbarrier -> every warp folds the CS partials itself.
-// No barrier.cluster, no second __syncthreads.
+// Cluster reductions without barrier.cluster and without __syncthreads.
+//   warp redux.sync -> per-warp partials in shared memory -> ONE __syncthreads -> warp 0 folds them and its lanes
+//   0..CS-1 push the CTA's partials into EVERY CTA's inbox with st.async (a DSMEM store that completes a transaction
+//   on the destination's mbarrier) -> all threads wait on the LOCAL mbarrier (armed by thread 0 with the byte count
+//   of all CS messages) -> every warp folds the CS partials itself.
+//   (Measured on B200: sending per-warp partials directly, 128 x 16 messages, is slower than this two-level form.)
+// A reduction is still an execution barrier for the cluster (nobody returns before every warp has sent), but it does
+// NOT order global memory: code that exchanges data through global memory fences and uses cluster.sync() explicitly.
+// Inbox buffer, mbarrier and parity alternate with the phase counter; a warp can be at most one phase ahead of any
+// other warp of the cluster, so two buffers suffice.
 __device__ __forceinline__ uint32_t sk_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void sk_mbar_init(unsigned long long *bar, uint32_t count) {
@@ -316,8 +223,14 @@ __device__ __forceinline__ uint32_t sk_mapa(uint32_t laddr, uint32_t rank) {
 __device__ __forceinline__ void sk_st_async(uint32_t raddr, unsigned long long v, uint32_t rbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(v), "r"(rbar) : "memory");
 }
+__device__ __forceinline__ unsigned long long sk_comb(unsigned long long a, unsigned long long b, int op) {
+    if (op == OP_SUM32) return a + b;
+    if (op == OP_MINU) return a < b ? a : b;
+    if (op == OP_MAXU) return a > b ? a : b;
+    return a | b;
+}
 
-// must be called once by every thread of the cluster before the first sk_allreduce2 / sk_argmax2
+// must be called once by every thread of the cluster before the first reduction
 __device__ inline void sk_red_init(SkRed &R) {
     SkSmem &S = *R.S;
     if (threadIdx.x == 0) {
@@ -325,65 +238,57 @@ __device__ inline void sk_red_init(SkRed &R) {
         sk_mbar_init(&S.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t i = threadIdx.x; i < 3 * SK_MSGW; i += blockDim.x) S.acc[i] = 0;
     __syncthreads();
     R.cluster->sync();
 }
 
-// All accumulators use identity 0: a MIN is carried as the MAX of the complemented value.
-__device__ __forceinline__ unsigned long long sk_fwd(unsigned long long x, int op) { return op == OP_MINU ? ~x : x; }
-__device__ __forceinline__ int sk_rop(int op) { return op == OP_MINU ? OP_MAXU : op; }
-__device__ __forceinline__ void sk_acc_atomic(unsigned long long *a, unsigned long long v, int op) {
-    if (op == OP_SUM32) atomicAdd(a, v);
-    else if (op == OP_OR) atomicOr(a, v);
-    else atomicMax(a, v);
-}
-
+// All-reduce NVAL values over the cluster; every thread returns with the reduced values in v[].
+// Two levels: warps -> CTA partial through shared memory (one __syncthreads, folded by warp 0), CTA partials ->
+// every CTA's inbox with st.async; all threads wait on the local mbarrier and fold the CS partials themselves.
 template <int NVAL>
-__device__ inline void sk_allreduce2(SkRed &R, unsigned long long (&v)[NVAL], const int (&op)[NVAL]) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void sk_allreduce(SkRed &R, unsigned long long (&v)[NVAL], const int (&op)[NVAL]) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     SkSmem &S = *R.S;
-    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1;
-    unsigned long long *acc = S.acc + (ph % 3) * SK_MSGW;
-    // clear the accumulators of the NEXT phase (last read two phases ago); arm this phase's mbarrier
-    if (threadIdx.x < SK_MSGW) S.acc[((ph + 1) % 3) * SK_MSGW + threadIdx.x] = 0ull;
-    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], R.CS * NVAL * 8u);
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, ns = S.nslots;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * NVAL * 8u);
 #pragma unroll
-    for (int i = 0; i < NVAL; i++) {
-        unsigned long long x = warp_op(sk_fwd(v[i], op[i]), sk_rop(op[i]));
-        if (lane == 0) sk_acc_atomic(&acc[i], x, op[i]);
+    for (int i = 0; i < NVAL; i++) v[i] = warp_op(v[i], op[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NVAL; i++) S.wpart[i * SK_MAX_WARPS + warp] = v[i];
     }
     __syncthreads();
-    if (warp == 0 && lane < R.CS) {
-        const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
-        const uint32_t rbox = sk_mapa(sk_saddr(S.abox + (buf * SK_MAX_CS + R.crank) * SK_MSGW), lane);
+    if (warp == 0) {
+        unsigned long long c[NVAL];
 #pragma unroll
-        for (int i = 0; i < NVAL; i++) sk_st_async(rbox + 8u * i, acc[i], rbar);
+        for (int i = 0; i < NVAL; i++) c[i] = warp_op(lane < nwarp ? S.wpart[i * SK_MAX_WARPS + lane] : sk_ident(op[i]), op[i]);
+        if (lane < R.CS) {
+            const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
+            const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), lane);
+#pragma unroll
+            for (int i = 0; i < NVAL; i++) sk_st_async(rbox + 8u * i * ns, c[i], rbar);
+        }
     }
     sk_mbar_wait(&S.mbar[buf], parity);
+    const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
 #pragma unroll
-    for (int i = 0; i < NVAL; i++) {
-        unsigned long long x = warp_op(lane < R.CS ? S.abox[(buf * SK_MAX_CS + lane) * SK_MSGW + i] : 0ull, sk_rop(op[i]));
-        v[i] = sk_fwd(x, op[i]);
-    }
+    for (int i = 0; i < NVAL; i++) v[i] = warp_op(lane < ns ? bx[i * ns + lane] : sk_ident(op[i]), op[i]);
     R.mph++;
 }
 
-// arg-max variant: value 0 is the key (0 = no candidate); the winner's payload (domains + flags) is read from the owning
-// CTA's shared memory by that CTA's warp 0 and travels in the same message.
-__device__ inline unsigned long long sk_argmax2(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, int32_t (&pay)[10],
-                                                 const int32_t *&wpay) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Arg-max: value 0 of the message is the key (0 = no candidate); values 1..SK_PLW carry the payload of the CTA-local
+// winner (its topology domains + node flags, read from this CTA's shared memory by warp 0).
+// Returns the winning key; `who` addresses the winner's message for sk_wpay().
+__device__ __forceinline__ unsigned long long sk_argmax(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, uint32_t &who) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     SkSmem &S = *R.S;
-    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1;
-    unsigned long long *acc = S.acc + (ph % 3) * SK_MSGW;
-    if (threadIdx.x < SK_MSGW) S.acc[((ph + 1) % 3) * SK_MSGW + threadIdx.x] = 0ull;
-    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], R.CS * (1 + SK_PLW) * 8u);
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, ns = S.nslots;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (1 + SK_PLW) * 8u);
     key = warp_maxu64(key);
-    if (lane == 0) atomicMax(&acc[0], key);
+    if (lane == 0) S.wpart[warp] = key;
     __syncthreads();
     if (warp == 0) {
-        const unsigned long long k = acc[0];
+        const unsigned long long k = warp_maxu64(lane < nwarp ? S.wpart[lane] : 0ull);
         int32_t pw = -1;
         if (k != 0) {
             uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
@@ -399,24 +304,21 @@ __device__ inline unsigned long long sk_argmax2(SkRed &R, unsigned long long key
         }
         if (lane < R.CS) {
             const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
-            const uint32_t rbox = sk_mapa(sk_saddr(S.abox + (buf * SK_MAX_CS + R.crank) * SK_MSGW), lane);
+            const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), lane);
             sk_st_async(rbox, k, rbar);
 #pragma unroll
-            for (int j = 0; j < SK_PLW; j++) sk_st_async(rbox + 8u * (SK_NV + j), w[j], rbar);
+            for (int j = 0; j < SK_PLW; j++) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
         }
     }
     sk_mbar_wait(&S.mbar[buf], parity);
-    unsigned long long x = lane < R.CS ? S.abox[(buf * SK_MAX_CS + lane) * SK_MSGW] : 0ull;
-    unsigned long long m = warp_maxu64(x);
-    unsigned who = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
-    const unsigned long long *pl = S.abox + (buf * SK_MAX_CS + who) * SK_MSGW + SK_NV;
-    wpay = (const int32_t *)pl;     // stays valid until the next-but-one mbarrier reduction
-#pragma unroll
-    for (int j = 0; j < SK_PLW; j++) {
-        unsigned long long w = pl[j];
-        pay[2 * j] = (int32_t)(unsigned)w;
-        pay[2 * j + 1] = (int32_t)(unsigned)(w >> 32);
-    }
+    const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
+    const unsigned long long y = lane < ns ? bx[lane] : 0ull;
+    const unsigned long long m = warp_maxu64(y);
+    who = buf * SK_NV * ns + (__ffs(__ballot_sync(0xffffffffu, y == m)) - 1);
     R.mph++;
     return m;
+}
+// word j (0..9) of the winner's payload: j < T -> domain of topology j, 8 -> node flags
+__device__ __forceinline__ int32_t sk_wpay(const SkSmem &S, uint32_t who, uint32_t j) {
+    return ((const int32_t *)(S.box + who + (size_t)(1 + (j >> 1)) * S.nslots))[j & 1];
 }

@@ -6,8 +6,11 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     SkSmem S;
-    sk_carve(S, smem_raw, blockDim.x, 2, 4, 64);
-    SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0, 0};
+    const uint32_t NW = (blockDim.x + 31) >> 5;
+    sk_carve(S, smem_raw, blockDim.x, 2, 4, 64, cluster.num_blocks());
+    for (uint32_t q = threadIdx.x; q < (B_N32 + 2 + 4) * blockDim.x; q += blockDim.x) S.a32[q] = (int32_t)q;
+    for (uint32_t q = threadIdx.x; q < C_N8 * blockDim.x; q += blockDim.x) S.a8[q] = (uint8_t)q;
+    SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0};
     sk_red_init(R);
     long long t0 = clock64();
     unsigned long long acc = threadIdx.x;
@@ -15,12 +18,9 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
         if (mode == 0) cluster.sync();
         else if (mode == 1) { unsigned long long v[5] = {acc, acc + 1, acc + 2, acc + 3, acc & 1}; const int op[5] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR}; sk_allreduce<5>(R, v, op); acc += v[1]; }
         else if (mode == 2) { unsigned long long v[16]; int op[16]; for (int q = 0; q < 16; q++) { v[q] = acc + q; } const int opc[16] = {0,0,2,2,2,1,1,2,1,2,3,3,3,3,3,3}; sk_allreduce<16>(R, v, opc); acc += v[2]; }
-        else if (mode == 3) { int32_t pay[10]; unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, pay, wp); acc += k + pay[0]; }
+        else if (mode == 3) { uint32_t who; unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, who); acc += k + sk_wpay(S, who, 0) + sk_wpay(S, who, 8); }
         else if (mode == 4) __syncthreads();
         else if (mode == 5) { __threadfence(); cluster.sync(); }
-        else if (mode == 6) { unsigned long long v[5] = {acc, acc + 1, acc + 2, acc + 3, acc & 1}; const int op[5] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR}; sk_allreduce2<5>(R, v, op); if (i == iters - 1 && threadIdx.x == 0 && blockIdx.x == 0) { out[2] = (long long)v[0]; out[3] = (long long)v[1]; } acc += v[1]; }
-        else if (mode == 7) { unsigned long long v[16]; for (int q = 0; q < 16; q++) { v[q] = acc + q; } const int opc[16] = {0,0,2,2,2,1,1,2,1,2,3,3,3,3,3,3}; sk_allreduce2<16>(R, v, opc); acc += v[2]; }
-        else if (mode == 8) { int32_t pay[10]; const int32_t *wp; unsigned long long k = sk_argmax2(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, pay, wp); acc += k + pay[0]; }
     }
     long long t1 = clock64();
     if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (t1 - t0) / iters; out[1] = (long long)acc; }
@@ -28,9 +28,9 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
 
 int main() {
     long long *d; cudaMalloc(&d, 64);
-    const char *names[9] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "allreduce2<5> (mbarrier)", "allreduce2<16> (mbarrier)", "argmax2 (mbarrier)"};
-    for (int cs : {1, 4, 16}) for (int tpb : {256, 640}) for (int mode = 0; mode < 9; mode++) {
-        size_t smem = sk_smem_bytes(tpb, 2, 4, 64);
+    const char *names[6] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync"};
+    for (int cs : {1, 4, 16}) for (int tpb : {128, 256}) for (int mode = 0; mode < 6; mode++) {
+        size_t smem = sk_smem_bytes(tpb, 2, 4, 64, cs);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaLaunchConfig_t cfg = {};
