@@ -43,6 +43,7 @@ struct ScenState {
     DevBuf<int64_t> req_mcpu, req_mem, req_eph, nz_mcpu, nz_mem, req_scalar, gpu_used;
     DevBuf<int32_t> num_pods, cnt, cnt_total, tp, fcount, size;
     DevBuf<long long> csum;
+    DevBuf<uint8_t> fbits;
     DevBuf<uint8_t> hard_reg;
     DevBuf<int32_t> out_node;
     DevBuf<int64_t> out_score;
@@ -114,6 +115,7 @@ int alloc_state(simon_ctx *ctx, ScenState &s, uint32_t max_fail, bool scores) {
     CU(s.tp.alloc((size_t)SK_MAX_SOFT * ctx->max_dom)); CU(s.fcount.alloc((size_t)SK_MAX_SOFT * ctx->max_dom));
     CU(s.size.alloc(SK_MAX_SOFT)); CU(s.hard_reg.alloc((size_t)SK_MAX_HARD * ctx->max_dom));
     CU(s.csum.alloc((size_t)ctx->n_classes * SK_CSUM_W));
+    CU(s.fbits.alloc((size_t)ctx->n_classes * N));
     CU(cudaMemsetAsync(s.csum.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * SK_CSUM_W), ctx->stream));
     CU(s.out_node.alloc(ctx->n_pods));
     if (scores) CU(s.out_score.alloc(ctx->n_pods));
@@ -141,7 +143,7 @@ void fill_scen(simon_ctx *ctx, ScenState &s, SkScenario &o, uint32_t n_active, b
     o.pad = 0;
     o.req_mcpu = s.req_mcpu.p; o.req_mem = s.req_mem.p; o.req_eph = s.req_eph.p; o.nz_mcpu = s.nz_mcpu.p; o.nz_mem = s.nz_mem.p;
     o.req_scalar = s.req_scalar.p; o.gpu_used = s.gpu_used.p; o.num_pods = s.num_pods.p; o.cnt = s.cnt.p; o.cnt_total = s.cnt_total.p;
-    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p; o.csum = s.csum.p;
+    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p; o.csum = s.csum.p; o.fbits = s.fbits.p;
     o.out_node = s.out_node.p; o.out_score = s.out_score.p;
     o.fail_counts = s.fail_counts.p; o.fail_pod = s.fail_pod.p; o.n_fail = s.counters.p; o.n_sched = s.counters.p + 1;
     o.clk = s.clk.p;

@@ -353,6 +353,25 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     const uint32_t end = P.first + P.count;
     uint32_t i = P.first;
     int32_t nx_cls = P.pod_class[i], nx_fixed = P.pod_fixed[i], nx_guard = P.pod_guard[i];
+    // static-normalised part of the total (NodeAffinity + TaintToleration + 2 x Simon + extra) under the current normalisers
+    auto snorm_pass = [&]() {
+        const int64_t range = C.simon_max - C.simon_min;
+        const bool small = range > 0 && range < (1ll << 24) && C.simon_max < (1ll << 24) && C.simon_min >= 0;
+        #pragma unroll 1
+        for (uint32_t s = 0; s < NPT; s++) {
+            uint32_t idx = s * TPB + tid;
+            if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
+            int64_t na = C.na_max == 0 ? A32(B_RAW_NA, idx) : (int64_t)((uint32_t)(100 * A32(B_RAW_NA, idx)) / (uint32_t)C.na_max);
+            int64_t tt = C.tt_max == 0 ? 100 : 100 - (int64_t)((uint32_t)(100 * A32(B_RAW_TT, idx)) / (uint32_t)C.tt_max);
+            int64_t sm;
+            if (range == 0) sm = 0;
+            else if (small) sm = (int64_t)((uint32_t)((uint32_t)(A64(A_SIMON, idx) - C.simon_min) * 100u) / (uint32_t)range);
+            else sm = ((A64(A_SIMON, idx) - C.simon_min) * 100) / range;
+            A32(B_SNORM, idx) = (int32_t)(na + tt + 2 * sm + (int64_t)A32(B_EXTRA, idx));
+        }
+        C.nm_na_max = C.na_max; C.nm_tt_max = C.tt_max; C.nm_simon_min = C.simon_min; C.nm_simon_max = C.simon_max;
+        C.snorm_valid = true;
+    };
     while (i < end) {
         const int32_t cls = nx_cls, fixed = nx_fixed;
         const int64_t guard = nx_guard;
@@ -421,11 +440,22 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (cls != cur_class) {
             st_class++;
             // remember the summary of the class we leave: it is the prediction for its next visit
-            if (leader && cur_class >= 0 && C.sum_valid && SC.csum) {
-                long long *rec = SC.csum + (uint64_t)cur_class * SK_CSUM_W;
+            // remember the class we leave: its summary AND the feasibility bits it is exact for.  On the next visit the
+            // bits are restored and P1 detects any change against them, exactly as between two pods of one class.
+            if (cur_class >= 0 && C.sum_valid && SC.csum && SC.fbits && !C.any_table) {
+                if (leader) {
+                    long long *rec = SC.csum + (uint64_t)cur_class * SK_CSUM_W;
 #pragma unroll
-                for (int js = 0; js < SK_MAX_SOFT; js++) rec[1 + js] = (uint32_t)js < C.n_soft ? psz[js] : 0;
-                rec[0] = 1;
+                    for (int js = 0; js < SK_MAX_SOFT; js++) rec[1 + js] = (uint32_t)js < C.n_soft ? psz[js] : 0;
+                    rec[9] = C.F; rec[10] = C.n_ign; rec[11] = C.na_max; rec[12] = C.tt_max; rec[13] = C.simon_max; rec[14] = C.simon_min;
+                    rec[0] = 1;
+                }
+                #pragma unroll 1
+                for (uint32_t s = 0; s < NPT; s++) {
+                    uint32_t idx = s * TPB + tid;
+                    uint8_t nf = A8(C_NFLAGS, idx);
+                    if (nf & NF_VALID) SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = nf & (NF_FEASIBLE | NF_COUNTED);
+                }
             }
             TICK(10);
             __threadfence();          // the previous commit's counter updates (owner-thread atomics) must be visible
@@ -436,9 +466,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             #pragma unroll 1
             for (uint32_t w = tid; w < words; w += TPB) S.blob[w] = gw[w];
             // prediction of the topology sizes from the previous visit of this class (any value is safe: verified)
-            long long pred[1 + SK_MAX_SOFT];
+            long long pred[SK_CSUM_W];
 #pragma unroll
-            for (int q = 0; q < 1 + SK_MAX_SOFT; q++) pred[q] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + q) : 0;
+            for (int q = 0; q < SK_CSUM_W; q++) pred[q] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + q) : 0;
             __syncthreads();
             TICK(12);
             C.cflags = (uint32_t)cw[SCW_FLAGS];
@@ -452,6 +482,11 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             C.snorm_valid = false;
             C.any_table = cw[SCW_ANY_TABLE] != 0;
             C.have_pred = pred[0] == 1;
+            const bool restore = C.have_pred && !C.any_table && SC.fbits;
+            if (restore) {
+                C.F = pred[9]; C.n_ign = pred[10]; C.na_max = pred[11]; C.tt_max = pred[12]; C.simon_max = pred[13]; C.simon_min = pred[14];
+                C.sum_valid = true;
+            }
 #pragma unroll
             for (int js = 0; js < SK_MAX_SOFT; js++) {
                 long long v = pred[1 + js];
@@ -477,12 +512,13 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 unsigned long long rec4[4];
                 long long sim4[4];
                 int32_t v4[4][4], ex4[4];
+                uint8_t fb4[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     uint32_t s = s0 + u;
                     uint32_t idx = s * TPB + tid;
                     bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
-                    rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000;
+                    rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000; fb4[u] = 0;
 #pragma unroll
                     for (int e = 0; e < 4; e++) v4[u][e] = 0;
                     if (valid) {
@@ -490,6 +526,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         if (P.use_scache) rec4[u] = __ldcg(&P.scache[(uint64_t)sig * N + g]);
                         sim4[u] = __ldg(&simon_row[A32(B_NODE_CLASS, idx)]);
                         if (extra) ex4[u] = __ldg(&extra[g]);
+                        if (restore) fb4[u] = __ldcg(&SC.fbits[(uint64_t)cls * N + g]);
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                             if ((uint32_t)e < C.E) {
@@ -545,7 +582,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                                                              ((unsigned long long)(uint32_t)tt << 16) | (1ull << 24) |
                                                              ((unsigned long long)(uint32_t)na << 32);
                     }
-                    nf |= fl | (code ? NF_STATIC_FAIL : 0);
+                    nf |= fl | (code ? NF_STATIC_FAIL : 0) | fb4[u];
                     A8(C_ST_CODE, idx) = code;
                     A32(B_RAW_NA, idx) = na;
                     A32(B_RAW_TT, idx) = tt;
@@ -564,6 +601,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     own_eval(idx);
                 }
             }
+            if (restore) snorm_pass();
             TICK(14);
             if (C.n_hard > 0 || C.any_table) {
                 // rare: DoNotSchedule constraints need the set of registered domains (filtering.go:221-243);
@@ -761,23 +799,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             } else if (!sizes_ok) set_weights();
             if (!(C.snorm_valid && C.nm_na_max == C.na_max && C.nm_tt_max == C.tt_max && C.nm_simon_min == C.simon_min &&
                   C.nm_simon_max == C.simon_max)) {
-                // static-normalised part of the total: NodeAffinity + TaintToleration + 2 x Simon + extra
-                const int64_t range = C.simon_max - C.simon_min;
-                const bool small = range > 0 && range < (1ll << 24) && C.simon_max < (1ll << 24) && C.simon_min >= 0;
-                #pragma unroll 1
-                for (uint32_t s = 0; s < NPT; s++) {
-                    uint32_t idx = s * TPB + tid;
-                    if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
-                    int64_t na = C.na_max == 0 ? A32(B_RAW_NA, idx) : (int64_t)((uint32_t)(100 * A32(B_RAW_NA, idx)) / (uint32_t)C.na_max);
-                    int64_t tt = C.tt_max == 0 ? 100 : 100 - (int64_t)((uint32_t)(100 * A32(B_RAW_TT, idx)) / (uint32_t)C.tt_max);
-                    int64_t sm;
-                    if (range == 0) sm = 0;
-                    else if (small) sm = (int64_t)((uint32_t)((uint32_t)(A64(A_SIMON, idx) - C.simon_min) * 100u) / (uint32_t)range);
-                    else sm = ((A64(A_SIMON, idx) - C.simon_min) * 100) / range;
-                    A32(B_SNORM, idx) = (int32_t)(na + tt + 2 * sm + (int64_t)A32(B_EXTRA, idx));
-                }
-                C.nm_na_max = C.na_max; C.nm_tt_max = C.tt_max; C.nm_simon_min = C.simon_min; C.nm_simon_max = C.simon_max;
-                C.snorm_valid = true;
+                snorm_pass();
             }
         }
 

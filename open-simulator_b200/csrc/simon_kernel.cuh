@@ -59,7 +59,8 @@ struct SkScenario {
     int32_t *cnt_total;        // [n_counters]
     // scratch tables [SK_MAX_SOFT or SK_MAX_HARD][max_dom]
     int32_t *tp, *fcount, *size;   // size: [SK_MAX_SOFT]
-    long long *csum;           // [n_classes][SK_CSUM_W] last feasible-set summary per class (prediction only)
+    long long *csum;           // [n_classes][SK_CSUM_W] feasible-set summary per class as of its last visit
+    uint8_t *fbits;            // [n_classes][N] NF_FEASIBLE|NF_COUNTED per node as of that visit (what csum is exact for)
     uint8_t *hard_reg;
     // outputs
     int32_t *out_node;         // [P]
