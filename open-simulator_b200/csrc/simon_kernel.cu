@@ -458,8 +458,12 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 }
             }
             TICK(10);
-            __threadfence();          // the previous commit's counter updates (owner-thread atomics) must be visible
-            cluster.sync();
+            // the previous commits' counter updates (owner-thread atomics) must be visible before the counters are read:
+            // release here, acquire (barrier_wait) only where the first counter is loaded, so that the class blob, entry
+            // table and summary record loads overlap the barrier latency
+            __threadfence();
+            cluster.barrier_arrive();
+            __syncthreads();          // every thread of this CTA is done with the previous class's blob and entry table
             TICK(11);
             const int64_t *gw = P.class_blob + P.class_off[cls];
             const uint32_t words = (uint32_t)(P.class_off[cls + 1] - P.class_off[cls]);
@@ -499,6 +503,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
             }
             __syncthreads();
+            cluster.barrier_wait();
             TICK(13);
             // ---- node-static verdicts: from the per-(static signature, node) cache, or computed and cached ----
             // All long-latency loads of up to 4 nodes (cache record, Simon row, first 4 counter values each) are issued
@@ -681,6 +686,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         TICK(3);
         // ---- P1: filters on cached state ----
         bool my_flip = false;
+        int32_t my_dc = 0;                  // net change of the counted (feasible, not ignored) set seen by this thread
         int64_t ipa_lo = 0, ipa_hi = 0;     // min/max of raw InterPodAffinity scores (initialised to 0: scoring.go:255)
         #pragma unroll (NPT_T > 0 ? NPT_T : 1)
         for (uint32_t s = 0; s < NPT; s++) {
@@ -690,6 +696,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             bool feas = filter_node(idx, nf, hard_min, false) == 0;
             if (feas != ((nf & NF_FEASIBLE) != 0)) my_flip = true;
             bool counted = feas && !(nf & NF_IGNORED);
+            my_dc += (int32_t)counted - (int32_t)((nf & NF_COUNTED) != 0);
             if (C.any_table && counted != ((nf & NF_COUNTED) != 0)) {
                 #pragma unroll 1
                 for (uint32_t js = 0; js < C.n_soft; js++) {
@@ -720,11 +727,21 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (C.sum_valid) {
             // steady state: the summary is exact unless some node flipped feasibility since it was taken
             pts_pass(plo, phi);
-            unsigned long long pv[5] = {plo, phi, sk_enc(ipa_lo), sk_enc(ipa_hi), my_flip ? 1ull : 0ull};
-            const int pop[5] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR};
-            sk_allreduce<5>(R, pv, pop);
+            unsigned long long pv[6] = {plo, phi, sk_enc(ipa_lo), sk_enc(ipa_hi), my_flip ? 1ull : 0ull, (unsigned long long)(uint32_t)my_dc};
+            const int pop[6] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR, OP_SUM32};
+            sk_allreduce<6>(R, pv, pop);
             pts_min = sk_dec(pv[0]); pts_max = sk_dec(pv[1]); ipa_min = sk_dec(pv[2]); ipa_max = sk_dec(pv[3]);
-            if (pv[4] != 0) { C.sum_valid = false; st_redo++; }
+            if (pv[4] != 0) {
+                // some node flipped: the summary is rebuilt below.  The hostname-topology sizes (= counted nodes) are known
+                // already from the net change, so the rebuild's spread pass runs under exact weights (no second pass)
+                C.sum_valid = false; st_redo++;
+                const int32_t dc = (int32_t)(uint32_t)pv[5];
+                bool ch = false;
+#pragma unroll
+                for (int js = 0; js < SK_MAX_SOFT; js++)
+                    if ((uint32_t)js < C.n_soft && ENT(ER_B, C.e_soft + js) && psz[js] + dc >= 0 && (long long)psz[js] + dc + 2 < (long long)P.n_log) { psz[js] += dc; ch = true; }
+                if (ch && dc != 0) set_weights();
+            }
         }
         TICK(5);
         if (!C.sum_valid) {

@@ -21,6 +21,30 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
         else if (mode == 3) { uint32_t who; unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, who); acc += k + sk_wpay(S, who, 0) + sk_wpay(S, who, 8); }
         else if (mode == 4) __syncthreads();
         else if (mode == 5) { __threadfence(); cluster.sync(); }
+        else if (mode == 6) { unsigned x = (unsigned)acc; for (int q = 0; q < 10; q++) x = __reduce_max_sync(0xffffffffu, x + (threadIdx.x & 31)); acc += x; }
+        else if (mode == 7) { unsigned long long x = acc; for (int q = 0; q < 10; q++) x = warp_maxu64(x + (threadIdx.x & 31)); acc += x; }
+        else if (mode == 8) {   // one st.async round trip to the own CTA + mbarrier wait, all threads waiting
+            const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1;
+            if (threadIdx.x == 0) { sk_mbar_expect(&S.mbar[buf], 8u); sk_st_async(sk_mapa(sk_saddr(S.box + buf * 64), cluster.block_rank()), acc, sk_mapa(sk_saddr(&S.mbar[buf]), cluster.block_rank())); }
+            sk_mbar_wait(&S.mbar[buf], parity); acc += S.box[buf * 64]; R.mph++;
+        }
+        else if (mode == 9) {   // same, to the NEXT CTA of the cluster (ring)
+            const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, nxt = (cluster.block_rank() + 1) % cluster.num_blocks();
+            if (threadIdx.x == 0) { sk_mbar_expect(&S.mbar[buf], 8u); sk_st_async(sk_mapa(sk_saddr(S.box + buf * 64), nxt), acc, sk_mapa(sk_saddr(&S.mbar[buf]), nxt)); }
+            sk_mbar_wait(&S.mbar[buf], parity); acc += S.box[buf * 64]; R.mph++;
+        }
+        else if (mode == 10) {  // CTA-level combine through 32-bit shared atomics + __syncthreads
+            unsigned *a = (unsigned *)S.wpart;
+            unsigned x = __reduce_max_sync(0xffffffffu, (unsigned)acc + threadIdx.x);
+            if ((threadIdx.x & 31) == 0) atomicMax(&a[i & 1], x);
+            __syncthreads(); acc += a[i & 1]; if (threadIdx.x == 0) a[(i + 1) & 1] = 0;
+        }
+        else if (mode == 11) {  // CTA-level combine: per-warp slots + __syncthreads + every warp folds
+            unsigned *a = (unsigned *)S.wpart + (i & 1) * 32;
+            unsigned x = __reduce_max_sync(0xffffffffu, (unsigned)acc + threadIdx.x);
+            if ((threadIdx.x & 31) == 0) a[threadIdx.x >> 5] = x;
+            __syncthreads(); unsigned y = (threadIdx.x & 31) < NW ? a[threadIdx.x & 31] : 0u; acc += __reduce_max_sync(0xffffffffu, y);
+        }
     }
     long long t1 = clock64();
     if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (t1 - t0) / iters; out[1] = (long long)acc; }
@@ -28,8 +52,8 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
 
 int main() {
     long long *d; cudaMalloc(&d, 64);
-    const char *names[6] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync"};
-    for (int cs : {1, 4, 16}) for (int tpb : {128, 256}) for (int mode = 0; mode < 6; mode++) {
+    const char *names[12] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "10x redux.max.u32 (dependent)", "10x warp_maxu64 (dependent)", "st.async self + mbar wait", "st.async next CTA + mbar wait", "redux+smem atomicMax+bar", "redux+slots+bar+fold"};
+    for (int cs : {1, 4, 16}) for (int tpb : {128, 256}) for (int mode = 0; mode < 12; mode++) {
         size_t smem = sk_smem_bytes(tpb, 2, 4, 64, cs);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
