@@ -84,7 +84,7 @@ struct simon_ctx {
     uint32_t max_fail = 0;
     DevBuf<SkScenario> d_scen;
     DevBuf<unsigned long long> d_stats, d_scache;
-    uint32_t n_sigs = 1, use_scache = 0;
+    uint32_t n_sigs = 1, use_scache = 0, simon32 = 0;
     // multi-scenario state
     std::vector<ScenState *> scen_states;
 };
@@ -164,7 +164,7 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.simon_raw = ctx->d_simon_raw.p; P.extra_score = ctx->d_extra.p;
     P.emax = ctx->emax;
     P.stats = ctx->d_stats.p;
-    P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.scache = ctx->d_scache.p; P.scache_ready = nullptr;
+    P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p; P.scache_ready = nullptr;
 }
 
 // choose cluster size / threads / nodes-per-thread for n_active nodes
@@ -342,6 +342,9 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     CU(ctx->d_pod_class.upload(p->pod_class, p->n_pods, st)); CU(ctx->d_pod_fixed.upload(p->pod_fixed_node, p->n_pods, st));
     CU(ctx->d_pod_guard.upload(guard.data(), p->n_pods, st)); CU(ctx->d_cnt_off.upload(cnt_off.data(), cnt_off.size(), st));
     CU(ctx->d_simon_raw.upload(p->simon_raw, (size_t)std::max(1u, p->n_static_rows) * ctx->NC, st));
+    ctx->simon32 = 1;
+    for (size_t q = 0; q < (size_t)p->n_static_rows * ctx->NC; q++)
+        if (p->simon_raw[q] < 0 || p->simon_raw[q] >= (1ll << 31)) { ctx->simon32 = 0; break; }
     CU(ctx->d_extra.upload(p->extra_score, (size_t)std::max(1u, p->n_extra_rows) * std::max(1u, ctx->N), st));
     CU(cudaStreamSynchronize(st));
     ctx->max_fail = std::min<uint32_t>(std::max(1u, p->n_pods), 1u << 16);

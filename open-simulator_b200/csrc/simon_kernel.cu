@@ -317,6 +317,11 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     };
 
     // PodTopologySpread raw scores with the current weights (scoring.go:175-208); returns local (min, max) encoded
+    // order-preserving 32-bit form of an encoded int64 score (raw scores are int32 by storage)
+    auto e32 = [](unsigned long long enc64) -> uint32_t {
+        long long v = sk_dec(enc64);
+        return w_enc(v > (long long)INT32_MAX ? INT32_MAX : (v < (long long)INT32_MIN ? INT32_MIN : (int32_t)v));
+    };
     auto pts_pass = [&](unsigned long long &lo, unsigned long long &hi) {
         lo = sk_enc(INT64_MAX);
         hi = sk_enc(0);
@@ -503,6 +508,19 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
             }
             __syncthreads();
+            if (tid == 0) {
+                // compact list of the entries this class increments on commit: entry | topology row << 8 | flags << 16
+                uint32_t n = 0;
+                #pragma unroll 1
+                for (uint32_t e = 0; e < C.E; e++) {
+                    if (!ENT(ER_INC, e)) continue;
+                    const int32_t kind = ENT(ER_KIND, e);
+                    const bool host = kind == EK_SOFT && ENT(ER_B, e);
+                    S.inc[n++] = e | ((host ? 0u : (uint32_t)ENT(ER_T, e)) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) |
+                                 (kind == EK_AFF ? 1u << 17 : 0u);
+                }
+                S.inc[SK_MAX_ENT] = n;
+            }
             cluster.barrier_wait();
             TICK(13);
             // ---- node-static verdicts: from the per-(static signature, node) cache, or computed and cached ----
@@ -665,10 +683,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // ---- R1 (rare): global minimum of every hard spread constraint over its registered domains ----
         int32_t hard_min[SK_MAX_HARD];
         if (C.n_hard > 0) {
-            unsigned long long hv[SK_MAX_HARD];
-            const int hop[SK_MAX_HARD] = {OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU, OP_MINU};
+            uint32_t hv[SK_MAX_HARD];
+            const int hop[SK_MAX_HARD] = {W_MIN, W_MIN, W_MIN, W_MIN, W_MIN, W_MIN, W_MIN, W_MIN};
 #pragma unroll
-            for (int q = 0; q < SK_MAX_HARD; q++) hv[q] = (unsigned long long)INT32_MAX;
+            for (int q = 0; q < SK_MAX_HARD; q++) hv[q] = (uint32_t)INT32_MAX;
             #pragma unroll 1
             for (uint32_t s = 0; s < NPT; s++) {
                 uint32_t idx = s * TPB + tid;
@@ -676,9 +694,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 if ((nf & (NF_VALID | NF_SEL_OK | NF_HARDKEYS)) != (NF_VALID | NF_SEL_OK | NF_HARDKEYS)) continue;
 #pragma unroll
                 for (int q = 0; q < SK_MAX_HARD; q++)
-                    if ((uint32_t)q < C.n_hard) { unsigned long long v = (unsigned long long)(uint32_t)VAL(C.e_hard + q, idx); hv[q] = v < hv[q] ? v : hv[q]; }
+                    if ((uint32_t)q < C.n_hard) { uint32_t v = (uint32_t)VAL(C.e_hard + q, idx); hv[q] = v < hv[q] ? v : hv[q]; }
             }
-            sk_allreduce<SK_MAX_HARD>(R, hv, hop);
+            sk_allreduce_w<SK_MAX_HARD>(R, hv, hop);
 #pragma unroll
             for (int q = 0; q < SK_MAX_HARD; q++) hard_min[q] = (int32_t)hv[q];
         }
@@ -727,15 +745,15 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (C.sum_valid) {
             // steady state: the summary is exact unless some node flipped feasibility since it was taken
             pts_pass(plo, phi);
-            unsigned long long pv[6] = {plo, phi, sk_enc(ipa_lo), sk_enc(ipa_hi), my_flip ? 1ull : 0ull, (unsigned long long)(uint32_t)my_dc};
-            const int pop[6] = {OP_MINU, OP_MAXU, OP_MINU, OP_MAXU, OP_OR, OP_SUM32};
-            sk_allreduce<6>(R, pv, pop);
-            pts_min = sk_dec(pv[0]); pts_max = sk_dec(pv[1]); ipa_min = sk_dec(pv[2]); ipa_max = sk_dec(pv[3]);
+            uint32_t pv[6] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_flip ? 1u : 0u, (uint32_t)my_dc};
+            const int pop[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
+            sk_allreduce_w<6>(R, pv, pop);
+            pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]); ipa_min = w_dec(pv[2]); ipa_max = w_dec(pv[3]);
             if (pv[4] != 0) {
                 // some node flipped: the summary is rebuilt below.  The hostname-topology sizes (= counted nodes) are known
                 // already from the net change, so the rebuild's spread pass runs under exact weights (no second pass)
                 C.sum_valid = false; st_redo++;
-                const int32_t dc = (int32_t)(uint32_t)pv[5];
+                const int32_t dc = (int32_t)pv[5];
                 bool ch = false;
 #pragma unroll
                 for (int js = 0; js < SK_MAX_SOFT; js++)
@@ -750,8 +768,6 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             const bool spec = C.have_pred;
             if (spec) pts_pass(plo, phi); else { plo = sk_enc(INT64_MAX); phi = sk_enc(0); }
             unsigned long long rv[SK_NV];
-            const int rop[SK_NV] = {OP_SUM32, OP_SUM32, OP_MAXU, OP_MAXU, OP_MAXU, OP_MINU, OP_MINU, OP_MAXU, OP_MINU, OP_MAXU,
-                                    OP_OR, OP_OR, OP_OR, OP_OR, OP_OR, OP_OR};
             rv[0] = 0; rv[1] = 0; rv[2] = 0; rv[3] = 0; rv[4] = sk_enc(-INT64_MAX); rv[5] = sk_enc(INT64_MAX);
             rv[6] = plo; rv[7] = phi; rv[8] = sk_enc(ipa_lo); rv[9] = sk_enc(ipa_hi);
 #pragma unroll
@@ -781,10 +797,33 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     }
             }
             if (C.any_table) { __threadfence(); cluster.sync(); }     // SC.size / SC.fcount were updated with global atomics in P1
-            sk_allreduce<SK_NV>(R, rv, rop);
-            C.F = (int64_t)rv[0]; C.n_ign = (int64_t)rv[1]; C.na_max = (int64_t)rv[2]; C.tt_max = (int64_t)rv[3];
-            C.simon_max = sk_dec(rv[4]); C.simon_min = sk_dec(rv[5]);
-            pts_min = sk_dec(rv[6]); pts_max = sk_dec(rv[7]); ipa_min = sk_dec(rv[8]); ipa_max = sk_dec(rv[9]);
+            {
+                // 22 words: two counts, six extrema, the spread / affinity score ranges and the 6 x 64 domain-presence bits
+                uint32_t sw[22];
+                const int sop[22] = {W_SUM, W_SUM, W_MAX, W_MAX, W_MAX, W_MIN, W_MIN, W_MAX, W_MIN, W_MAX,
+                                     W_OR, W_OR, W_OR, W_OR, W_OR, W_OR, W_OR, W_OR, W_OR, W_OR, W_OR, W_OR};
+                sw[0] = (uint32_t)rv[0]; sw[1] = (uint32_t)rv[1]; sw[2] = (uint32_t)rv[2]; sw[3] = (uint32_t)rv[3];
+                sw[4] = P.simon32 ? (uint32_t)sk_dec(rv[4] == sk_enc(-INT64_MAX) ? sk_enc(0) : rv[4]) : 0u;
+                sw[5] = P.simon32 ? (rv[5] == sk_enc(INT64_MAX) ? 0xffffffffu : (uint32_t)sk_dec(rv[5])) : 0xffffffffu;
+                sw[6] = e32(rv[6]); sw[7] = e32(rv[7]); sw[8] = e32(rv[8]); sw[9] = e32(rv[9]);
+#pragma unroll
+                for (int q = 0; q < SK_MAXW; q++) { sw[10 + 2 * q] = (uint32_t)rv[10 + q]; sw[11 + 2 * q] = (uint32_t)(rv[10 + q] >> 32); }
+                sk_allreduce_w<22>(R, sw, sop);
+                C.F = (int64_t)sw[0]; C.n_ign = (int64_t)sw[1]; C.na_max = (int64_t)sw[2]; C.tt_max = (int64_t)sw[3];
+                pts_min = w_dec(sw[6]); pts_max = w_dec(sw[7]); ipa_min = w_dec(sw[8]); ipa_max = w_dec(sw[9]);
+#pragma unroll
+                for (int q = 0; q < SK_MAXW; q++) rv[10 + q] = ((unsigned long long)sw[11 + 2 * q] << 32) | sw[10 + 2 * q];
+                if (P.simon32) {
+                    // no feasible node: keep the 64-bit conventions of the empty extrema
+                    C.simon_max = C.F > 0 ? (int64_t)sw[4] : -INT64_MAX;
+                    C.simon_min = C.F > 0 ? (int64_t)sw[5] : INT64_MAX;
+                } else {
+                    unsigned long long sv[2] = {rv[4], rv[5]};
+                    const int s2op[2] = {OP_MAXU, OP_MINU};
+                    sk_allreduce<2>(R, sv, s2op);
+                    C.simon_max = sk_dec(sv[0]); C.simon_min = sk_dec(sv[1]);
+                }
+            }
             bool sizes_ok = spec;
 #pragma unroll
             for (int js = 0; js < SK_MAX_SOFT; js++) {
@@ -809,10 +848,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 // the predicted topology sizes were wrong (or there was no prediction): redo the spread pass
                 set_weights();
                 pts_pass(plo, phi);
-                unsigned long long pv[2] = {plo, phi};
-                const int pop[2] = {OP_MINU, OP_MAXU};
-                sk_allreduce<2>(R, pv, pop);
-                pts_min = sk_dec(pv[0]); pts_max = sk_dec(pv[1]);
+                uint32_t pv[2] = {e32(plo), e32(phi)};
+                const int pop[2] = {W_MIN, W_MAX};
+                sk_allreduce_w<2>(R, pv, pop);
+                pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]);
             } else if (!sizes_ok) set_weights();
             if (!(C.snorm_valid && C.nm_na_max == C.na_max && C.nm_tt_max == C.tt_max && C.nm_simon_min == C.simon_min &&
                   C.nm_simon_max == C.simon_max)) {
@@ -905,22 +944,23 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             if (SC.out_score) SC.out_score[i] = C.F > 1 ? win_total : 0;
             own_eval(idx);      // Fit verdict + LeastAllocated/BalancedAllocation of the node that changed
         }
-        // every thread folds the winner into its cached counter values
-        #pragma unroll 1
-        for (uint32_t e = 0; e < C.E; e++) {
-            if (!ENT(ER_INC, e)) continue;
-            int32_t kind = ENT(ER_KIND, e), t = ENT(ER_T, e);
-            bool host = kind == EK_SOFT && ENT(ER_B, e);
-            int32_t wd = sk_wpay(S, who, host ? 0 : (uint32_t)t);
-            if (kind == EK_SOFT && !host && win_ignored) continue;
-            if (wd < 0) continue;
-            const uint32_t trow = host ? 0 : (uint32_t)t;
-            #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-            for (uint32_t s = 0; s < NPT; s++) {
-                uint32_t idx = s * TPB + tid;
-                if ((A8(C_NFLAGS, idx) & NF_VALID) && DOM(trow, idx) == wd) VAL(e, idx) += 1;
+        // every thread folds the winner into its cached counter values (S.inc was built at the class change; the
+        // reductions in between contain __syncthreads)
+        {
+            const uint32_t n_inc = S.inc[SK_MAX_ENT];
+            #pragma unroll 1
+            for (uint32_t k = 0; k < n_inc; k++) {
+                const uint32_t rec = S.inc[k], e = rec & 0xff, trow = (rec >> 8) & 0xff;
+                if ((rec & (1u << 16)) && win_ignored) continue;
+                const int32_t wd = sk_wpay(S, who, trow);
+                if (wd < 0) continue;
+                #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+                for (uint32_t s = 0; s < NPT; s++) {
+                    uint32_t idx = s * TPB + tid;
+                    if ((A8(C_NFLAGS, idx) & NF_VALID) && DOM(trow, idx) == wd) VAL(e, idx) += 1;
+                }
+                if (rec & (1u << 17)) C.aff_total += 1;
             }
-            if (kind == EK_AFF) C.aff_total += 1;
         }
         n_sched++;
         i++;

@@ -97,6 +97,7 @@ struct SkParams {
     unsigned long long *stats; // optional [8]: decisions, class changes, summary rebuilds, redone decisions
     // static cache: per (static signature, node) verdicts, filled on first use
     uint32_t n_sigs, use_scache;
+    uint32_t simon32, pad32;       // simon32: every raw Simon score lies in [0, 2^31) -> reduced as a 32-bit word
     unsigned long long *scache;    // [n_sigs][N] packed {st_code, flags, tt, 0, na:int32}
     uint32_t *scache_ready;        // [n_sigs]
 };
@@ -110,9 +111,10 @@ struct SkSmem {
     uint8_t *a8;         // [C_N8][L]
     int64_t *blob;       // [max_blob_words]
     unsigned long long *box;     // [2][SK_NV][nslots] reduction inbox: one slot per CTA of the cluster, double buffered
-    unsigned long long *wpart;   // [SK_NV][SK_MAX_WARPS] per-warp partials of the CTA-level fold
+    unsigned long long *wpart;   // [SK_NV][SK_MAX_WARPS] per-warp partials of the CTA-level fold (u64, or 2*SK_NV rows of u32)
     int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
     uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
+    uint32_t *inc;       // [SK_MAX_ENT + 1] compact list of the entries the current class increments; [SK_MAX_ENT] = count
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
     int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
     SkScenario *scen;    // this cluster's scenario descriptor
@@ -128,7 +130,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * blob_words);
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
-    b += sk_align(4ull * SIMON_MAX_TOPOS);
+    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1));
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
@@ -144,6 +146,7 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.wpart = (unsigned long long *)p; p += sk_align(8ull * SK_NV * SK_MAX_WARPS);
     S.ent = (int32_t *)p; p += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
+    S.inc = (uint32_t *)p; p += sk_align(4ull * (SK_MAX_ENT + 1));
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
@@ -274,6 +277,61 @@ __device__ __forceinline__ void sk_allreduce(SkRed &R, unsigned long long (&v)[N
     const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
 #pragma unroll
     for (int i = 0; i < NVAL; i++) v[i] = warp_op(lane < ns ? bx[i * ns + lane] : sk_ident(op[i]), op[i]);
+    R.mph++;
+}
+
+// The same all-reduce over 32-bit words (native single-instruction redux.sync per word and stage; two words per
+// st.async message).  This is the form the placement loop uses: scores, counts and domain bitmasks are 32-bit.
+enum { W_SUM = 0, W_MIN = 1, W_MAX = 2, W_OR = 3 };
+__device__ __forceinline__ uint32_t warp_w(uint32_t x, int op) {
+    if (op == W_SUM) return __reduce_add_sync(0xffffffffu, x);
+    if (op == W_MIN) return __reduce_min_sync(0xffffffffu, x);
+    if (op == W_MAX) return __reduce_max_sync(0xffffffffu, x);
+    return __reduce_or_sync(0xffffffffu, x);
+}
+__device__ __forceinline__ uint32_t w_ident(int op) { return op == W_MIN ? 0xffffffffu : 0u; }
+__device__ __forceinline__ uint32_t w_enc(int32_t x) { return (uint32_t)x ^ 0x80000000u; }     // order-preserving int32 -> uint32
+__device__ __forceinline__ int32_t w_dec(uint32_t x) { return (int32_t)(x ^ 0x80000000u); }
+
+template <int NW>
+__device__ __forceinline__ void sk_allreduce_w(SkRed &R, uint32_t (&w)[NW], const int (&op)[NW]) {
+    constexpr int NM = (NW + 1) / 2;
+    static_assert(NM <= SK_NV && NW <= 2 * SK_NV, "message too long for the inbox");
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    SkSmem &S = *R.S;
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, ns = S.nslots;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * NM * 8u);
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = warp_w(w[i], op[i]);
+    uint32_t *wp = (uint32_t *)S.wpart;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) wp[i * SK_MAX_WARPS + warp] = w[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t c[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) c[i] = warp_w(lane < nwarp ? wp[i * SK_MAX_WARPS + lane] : w_ident(op[i]), op[i]);
+        if (lane < R.CS) {
+            const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
+            const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), lane);
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const uint32_t hi = 2 * m + 1 < NW ? c[2 * m + 1 < NW ? 2 * m + 1 : 0] : 0u;
+                sk_st_async(rbox + 8u * m * ns, ((unsigned long long)hi << 32) | c[2 * m], rbar);
+            }
+        }
+    }
+    sk_mbar_wait(&S.mbar[buf], parity);
+    const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
+#pragma unroll
+    for (int m = 0; m < NM; m++) {
+        const bool in = lane < ns;
+        const unsigned long long x = in ? bx[m * ns + lane] : 0ull;
+        w[2 * m] = warp_w(in ? (uint32_t)x : w_ident(op[2 * m]), op[2 * m]);
+        if (2 * m + 1 < NW) w[2 * m + 1 < NW ? 2 * m + 1 : 0] = warp_w(in ? (uint32_t)(x >> 32) : w_ident(op[2 * m + 1 < NW ? 2 * m + 1 : 0]), op[2 * m + 1 < NW ? 2 * m + 1 : 0]);
+    }
     R.mph++;
 }
 
