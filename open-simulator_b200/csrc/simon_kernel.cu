@@ -145,7 +145,7 @@ struct ClassState {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-template <int MAXT, int NPT_T>
+template <int MAXT, int NPT_T, bool PROF>
 __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -171,8 +171,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     const bool leader = (gtid == 0);
     unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0;
     long long tk[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_prev = clock64();
-#define TICK(slot) do { long long t_now = clock64(); tk[slot] += t_now - t_prev; t_prev = t_now; } while (0)
+    long long t_prev = PROF ? clock64() : 0;
+    (void)t_prev;
+#define TICK(slot) do { if constexpr (PROF) { long long t_now = clock64(); tk[slot] += t_now - t_prev; t_prev = t_now; } } while (0)
 
     if (leader && SC.clk) SC.clk[0] = sk_globaltimer();
 
@@ -508,18 +509,21 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
             }
             __syncthreads();
-            if (tid == 0) {
+            if (tid < 32) {
                 // compact list of the entries this class increments on commit: entry | topology row << 8 | flags << 16
-                uint32_t n = 0;
-                #pragma unroll 1
-                for (uint32_t e = 0; e < C.E; e++) {
-                    if (!ENT(ER_INC, e)) continue;
+                // (lane e looks at entry e; SK_MAX_ENT == 32)
+                const uint32_t e = tid;
+                uint32_t rec = 0;
+                bool inc = e < C.E && ENT(ER_INC, e) != 0;
+                if (inc) {
                     const int32_t kind = ENT(ER_KIND, e);
                     const bool host = kind == EK_SOFT && ENT(ER_B, e);
-                    S.inc[n++] = e | ((host ? 0u : (uint32_t)ENT(ER_T, e)) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) |
-                                 (kind == EK_AFF ? 1u << 17 : 0u);
+                    rec = e | ((host ? 0u : (uint32_t)ENT(ER_T, e)) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) |
+                          (kind == EK_AFF ? 1u << 17 : 0u);
                 }
-                S.inc[SK_MAX_ENT] = n;
+                const uint32_t m = __ballot_sync(0xffffffffu, inc);
+                if (inc) S.inc[__popc(m & ((1u << e) - 1u))] = rec;
+                if (e == 0) S.inc[SK_MAX_ENT] = __popc(m);
             }
             cluster.barrier_wait();
             TICK(13);
@@ -987,7 +991,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
 
 #define SIMON_KERNEL(MAXT, NPTT)                                                                         \
     extern "C" __global__ void __launch_bounds__(MAXT, 1) simon_place_kernel_##MAXT##_##NPTT(const __grid_constant__ SkParams P) { \
-        simon_place_body<MAXT, NPTT>(P);                                                                 \
+        simon_place_body<MAXT, NPTT, false>(P);                                                          \
+    }                                                                                                    \
+    extern "C" __global__ void __launch_bounds__(MAXT, 1) simon_prof_kernel_##MAXT##_##NPTT(const __grid_constant__ SkParams P) { \
+        simon_place_body<MAXT, NPTT, true>(P);                                                           \
     }
 SIMON_KERNEL(256, 0)
 SIMON_KERNEL(256, 1)

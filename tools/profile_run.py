@@ -15,7 +15,10 @@ ap.add_argument("--pods", type=int, default=6000, help="scheduled pods placed in
 ap.add_argument("--cluster-ctas", type=int, default=0)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--phase-timers", action="store_true", help="use the kernel variants with per-phase clock64 timers")
 a = ap.parse_args()
+if a.phase_timers:
+    os.environ["SIMON_PROFILE"] = "1"
 
 import numpy as np
 from simon_b200 import simulator, synth
