@@ -167,6 +167,8 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p; P.scache_ready = nullptr;
 }
 
+#define SIMON_MAX_TPB 320u
+
 // choose cluster size / threads / nodes-per-thread for n_active nodes
 int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &TPB, uint32_t &NPT, size_t &smem) {
     int max_smem = 0;
@@ -187,9 +189,9 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
                 uint32_t per_thread_cta = (n_active + cs * npt - 1) / (cs * npt);
                 t = ((per_thread_cta + 31) / 32) * 32;
                 if (t < 64) t = 64;
-                if (t > 256) continue;            // the 256-thread variants keep >= 200 registers/thread (no spills)
+                if (t > SIMON_MAX_TPB) continue;  // 320 threads still leave 200 registers/thread; fewer nodes per thread wins
             }
-            if (t > 256) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= 256 (got %u)", t);
+            if (t > SIMON_MAX_TPB) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= %u (got %u)", SIMON_MAX_TPB, t);
             size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs);
             if (b <= (size_t)max_smem) { CS = cs; TPB = t; NPT = npt; smem = b; return SIMON_OK; }
             if (want_t) break;
@@ -204,11 +206,14 @@ static_assert(sizeof(SkScenario) % 8 == 0, "SkScenario is copied in 8-byte words
 int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t TPB, size_t smem, bool record = true) {
     sk_kernel_fn fn;
     const uint32_t npt = P.npt;
-    if (TPB > 256) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= 256");
+    if (TPB > SIMON_MAX_TPB) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= %u", SIMON_MAX_TPB);
     // SIMON_PROFILE=1 selects the variants with per-phase clock64 timers (simon_stats cycles); the default variants
     // carry no timers
     static const bool prof = getenv("SIMON_PROFILE") != nullptr;
-    if (prof) fn = npt == 1 ? simon_prof_kernel_256_1 : npt == 2 ? simon_prof_kernel_256_2 : npt == 3 ? simon_prof_kernel_256_3 : npt == 4 ? simon_prof_kernel_256_4 : simon_prof_kernel_256_0;
+    if (TPB > 256) {
+        if (prof) fn = npt == 1 ? simon_prof_kernel_320_1 : npt == 2 ? simon_prof_kernel_320_2 : simon_prof_kernel_320_0;
+        else fn = npt == 1 ? simon_place_kernel_320_1 : npt == 2 ? simon_place_kernel_320_2 : simon_place_kernel_320_0;
+    } else if (prof) fn = npt == 1 ? simon_prof_kernel_256_1 : npt == 2 ? simon_prof_kernel_256_2 : npt == 3 ? simon_prof_kernel_256_3 : npt == 4 ? simon_prof_kernel_256_4 : simon_prof_kernel_256_0;
     else fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -1001,3 +1001,6 @@ SIMON_KERNEL(256, 1)
 SIMON_KERNEL(256, 2)
 SIMON_KERNEL(256, 3)
 SIMON_KERNEL(256, 4)
+SIMON_KERNEL(320, 0)
+SIMON_KERNEL(320, 1)
+SIMON_KERNEL(320, 2)

@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 #define SK_MAXW 6           // domain-bitmask words available per decision
 #define SK_NV 16            // max values per all-reduce
 #define SK_PLW 5            // payload: 10 int32 packed in 5 u64 (T domains + flags)
-#define SK_MAX_WARPS 8      // threads per CTA <= 256
+#define SK_MAX_WARPS 16     // threads per CTA <= 512 (the shipped variants use <= 320)
 #define SK_CSUM_W 16
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
