@@ -167,7 +167,8 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p; P.scache_ready = nullptr;
 }
 
-#define SIMON_MAX_TPB 320u
+#define SIMON_MAX_TPB 320u       // largest compiled variant: 168 registers/thread, no spills (640 threads = 96 registers spilled and measured slower)
+#define SIMON_AUTO_TPB 320u
 
 // choose cluster size / threads / nodes-per-thread for n_active nodes
 int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &TPB, uint32_t &NPT, size_t &smem) {
@@ -189,7 +190,7 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
                 uint32_t per_thread_cta = (n_active + cs * npt - 1) / (cs * npt);
                 t = ((per_thread_cta + 31) / 32) * 32;
                 if (t < 64) t = 64;
-                if (t > SIMON_MAX_TPB) continue;  // 320 threads still leave 200 registers/thread; fewer nodes per thread wins
+                if (t > SIMON_AUTO_TPB) continue; // 320 threads still leave 200 registers/thread; fewer nodes per thread wins
             }
             if (t > SIMON_MAX_TPB) return fail(ctx, SIMON_ERR_LIMIT, "threads per CTA must be <= %u (got %u)", SIMON_MAX_TPB, t);
             size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs);
