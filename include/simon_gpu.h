@@ -149,6 +149,8 @@ enum simon_class_word {
                            engine's counter array (prefix sum of topo_ndom over counter ids) */
     SCW_N_ENT,
     SCW_ANY_TABLE,      /* some soft constraint's topology is too large for the per-decision domain bitmask */
+    SCW_ELIG_SIG,       /* representative class id of this class's own spreading-eligibility signature (the `sig`
+                           of commit-list entries that equals it can be answered from the winner's own flags), -1: none */
     SCW_HDR_WORDS
 };
 

@@ -165,7 +165,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     __syncthreads();
     const SkScenario &SC = *S.scen;
     const uint32_t NA = SC.n_active;
-    SkRed R{&S, &cluster, crank, CS, 0};
+    long long rprof[6] = {0, 0, 0, 0, 0, 0};
+    long long spec_cyc = 0, spec_n = 0;
+    long long owner_cyc = 0, owner_n = 0;     // profiling variants: cycles the committing thread spends in its commit block
+    SkRed R{&S, &cluster, crank, CS, 0, PROF ? rprof : nullptr};
     sk_red_init(R);
     const ReqCtx RC{P.label_bits, N};
     const bool leader = (gtid == 0);
@@ -215,25 +218,25 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     C.n_soft = 0;
     const int64_t *cw = S.blob;
 
-    // NodeResourcesFit verdict + LeastAllocated + BalancedAllocation of one node for the current class
-    auto own_eval = [&](uint32_t idx) {
-        uint8_t nf = A8(C_NFLAGS, idx);
-        bool fit = !(A32(B_NUM_PODS, idx) + 1 > A32(B_ALLOC_PODS, idx));
+    // NodeResourcesFit verdict + LeastAllocated + BalancedAllocation of one node for the current class, with `add` more
+    // pods of this class already on the node (add = 0: the node as it is; add = 1: as it will be after winning this pod).
+    auto own_core = [&](uint32_t idx, int64_t add, bool &fit_out, int32_t &own_out) {
+        bool fit = !(A32(B_NUM_PODS, idx) + (int32_t)add + 1 > A32(B_ALLOC_PODS, idx));
         const int64_t capc = A64(A_ALLOC_MCPU, idx), capm = A64(A_ALLOC_MEM, idx);
         if (fit && (C.cflags & SIMON_CLS_HAS_REQUEST)) {
-            if (capc < cw[SCW_REQ_MCPU] + A64(A_REQ_MCPU, idx)) fit = false;
-            if (capm < cw[SCW_REQ_MEM] + A64(A_REQ_MEM, idx)) fit = false;
-            if (A64(A_ALLOC_EPH, idx) < cw[SCW_REQ_EPH] + A64(A_REQ_EPH, idx)) fit = false;
+            if (capc < cw[SCW_REQ_MCPU] + A64(A_REQ_MCPU, idx) + add * cw[SCW_REQ_MCPU]) fit = false;
+            if (capm < cw[SCW_REQ_MEM] + A64(A_REQ_MEM, idx) + add * cw[SCW_REQ_MEM]) fit = false;
+            if (A64(A_ALLOC_EPH, idx) < cw[SCW_REQ_EPH] + A64(A_REQ_EPH, idx) + add * cw[SCW_REQ_EPH]) fit = false;
             if (K) {
                 uint32_t g = (uint32_t)A32(B_NODE_G, idx);
                 const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
                 #pragma unroll 1
                 for (uint32_t k = 0; k < K; k++)
-                    if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * N + g] < sc_req[k] + SC.req_scalar[(uint64_t)k * N + g]) fit = false;
+                    if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * N + g] < sc_req[k] + SC.req_scalar[(uint64_t)k * N + g] + add * sc_req[k]) fit = false;
             }
         }
-        A8(C_NFLAGS, idx) = (nf & ~NF_FIT_OK) | (fit ? NF_FIT_OK : 0);
-        const int64_t rqc = A64(A_NZ_MCPU, idx) + cw[SCW_SCORE_MCPU], rqm = A64(A_NZ_MEM, idx) + cw[SCW_SCORE_MEM];
+        const int64_t rqc = A64(A_NZ_MCPU, idx) + add * cw[SCW_NZ_MCPU] + cw[SCW_SCORE_MCPU];
+        const int64_t rqm = A64(A_NZ_MEM, idx) + add * cw[SCW_NZ_MEM] + cw[SCW_SCORE_MEM];
         const double ic = ((const double *)S.a64)[A_INV_MCPU * L + idx], im = ((const double *)S.a64)[A_INV_MEM * L + idx];
         int64_t s1 = (capc == 0 || rqc > capc) ? 0 : div_by((capc - rqc) * 100, capc, ic);
         int64_t s2 = (capm == 0 || rqm > capm) ? 0 : div_by((capm - rqm) * 100, capm, im);
@@ -253,7 +256,15 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             }
             ba = (int64_t)fl;
         }
-        A32(B_OWN, idx) = (int32_t)(la + ba);
+        fit_out = fit;
+        own_out = (int32_t)(la + ba);
+    };
+    auto own_eval = [&](uint32_t idx) {
+        bool fit; int32_t own;
+        own_core(idx, 0, fit, own);
+        uint8_t nf = A8(C_NFLAGS, idx);
+        A8(C_NFLAGS, idx) = (nf & ~NF_FIT_OK) | (fit ? NF_FIT_OK : 0);
+        A32(B_OWN, idx) = own;
     };
 
     // filters on cached state; returns the reason bitmask (0 = feasible). hard_min: global minima of hard constraints.
@@ -524,6 +535,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 const uint32_t m = __ballot_sync(0xffffffffu, inc);
                 if (inc) S.inc[__popc(m & ((1u << e) - 1u))] = rec;
                 if (e == 0) S.inc[SK_MAX_ENT] = __popc(m);
+                // counter bases of the commit list: fetched once per class switch, not by the committing thread
+                if ((int64_t)e < cw[SCW_N_INC]) S.incb[e] = (uint32_t)P.cnt_off[(cw + cw[SCW_OFF_INC])[3 * e]];
             }
             cluster.barrier_wait();
             TICK(13);
@@ -749,6 +762,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (C.sum_valid) {
             // steady state: the summary is exact unless some node flipped feasibility since it was taken
             pts_pass(plo, phi);
+            TICK(15);
             uint32_t pv[6] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_flip ? 1u : 0u, (uint32_t)my_dc};
             const int pop[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
             sk_allreduce_w<6>(R, pv, pop);
@@ -909,45 +923,83 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             best = key > best ? key : best;
         }
         TICK(7);
+        // The exchange of the arg-max takes ~1,000 cycles.  Meanwhile the owner of every warp's best candidate evaluates
+        // what its node's Fit verdict and own-state score WOULD be after receiving this pod, so that the one true winner
+        // finds them ready at commit time instead of computing them on the critical path.
         uint32_t who;
-        best = sk_argmax(R, best, CT, TPB, who);
+        const unsigned long long my_best = best;
+        const unsigned long long warp_best = sk_argmax_send(R, best, CT, TPB);
+        bool spec_fit = false;
+        int32_t spec_own = 0;
+        uint32_t spec_idx = 0xffffffffu;
+        if (my_best == warp_best && my_best != 0) {
+            const uint32_t r = 0xFFFFFFu - (uint32_t)(my_best & 0xFFFFFFu);
+            spec_idx = (r / CT) * TPB + tid;
+            const long long sc0 = PROF ? clock64() : 0;
+            own_core(spec_idx, 1, spec_fit, spec_own);
+            if (PROF) { spec_cyc += clock64() - sc0; spec_n++; }
+        }
+        best = sk_argmax_wait(R, who);
         TICK(8);
         const uint32_t win_r = 0xFFFFFFu - (uint32_t)(best & 0xFFFFFFu);
         const int64_t win_total = (int64_t)(best >> 24) - 1;
         const bool win_ignored = ((uint32_t)sk_wpay(S, who, 8) & NF_IGNORED) != 0;
 
         // ---- commit (AssumePod / NodeInfo.AddPod) ----
-        if (win_r % CT == gtid) {
-            uint32_t idx = (win_r / CT) * TPB + tid;
-            uint32_t g = (uint32_t)A32(B_NODE_G, idx);
-            A64(A_REQ_MCPU, idx) += cw[SCW_REQ_MCPU]; A64(A_REQ_MEM, idx) += cw[SCW_REQ_MEM]; A64(A_REQ_EPH, idx) += cw[SCW_REQ_EPH];
-            A64(A_NZ_MCPU, idx) += cw[SCW_NZ_MCPU]; A64(A_NZ_MEM, idx) += cw[SCW_NZ_MEM]; A32(B_NUM_PODS, idx) += 1;
-            const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
-            #pragma unroll 1
-            for (uint32_t k = 0; k < K; k++) SC.req_scalar[(uint64_t)k * N + g] += sc_req[k];
-            const int64_t *inc = cw + cw[SCW_OFF_INC];
-            #pragma unroll 1
-            for (int64_t u = 0; u < cw[SCW_N_INC]; u++) {
-                int64_t k = inc[3 * u], t = inc[3 * u + 1], sig = inc[3 * u + 2];
-                int32_t d = DOM(t, idx);
-                if (d < 0) continue;
-                if (sig >= 0) {
-                    bool el = (sig == (int64_t)cls) ? !win_ignored : elig_eval(P, sig, RC, g);   // the winner passed NodeAffinity
-                    if (!el) continue;
+        // Commit.  The owning thread only touches its node's shared-memory state (its next filter pass needs it); the
+        // NEIGHBOUR warp of the same CTA does everything that goes to global memory - results, scalar aggregates and the
+        // class's commit list, one counter entry per lane - so that no single warp carries the whole serial chain.
+        const uint32_t win_g = win_r % CT;                       // cluster-wide thread index of the owner
+        if (win_g / TPB == crank) {
+            const uint32_t own_tid = win_g % TPB, own_warp = own_tid >> 5, nwarp_cta = (TPB + 31) >> 5;
+            const uint32_t help_warp = own_warp + 1 < nwarp_cta ? own_warp + 1 : 0;
+            const uint32_t idx = (win_r / CT) * TPB + own_tid;
+            if (tid == own_tid) {
+                const long long oc0 = PROF ? clock64() : 0;
+                A64(A_REQ_MCPU, idx) += cw[SCW_REQ_MCPU]; A64(A_REQ_MEM, idx) += cw[SCW_REQ_MEM]; A64(A_REQ_EPH, idx) += cw[SCW_REQ_EPH];
+                A64(A_NZ_MCPU, idx) += cw[SCW_NZ_MCPU]; A64(A_NZ_MEM, idx) += cw[SCW_NZ_MEM]; A32(B_NUM_PODS, idx) += 1;
+                // Fit verdict + LeastAllocated/BalancedAllocation of the node that changed: evaluated during the arg-max exchange
+                uint8_t nf = A8(C_NFLAGS, idx);
+                A8(C_NFLAGS, idx) = (nf & ~NF_FIT_OK) | (spec_fit ? NF_FIT_OK : 0);
+                A32(B_OWN, idx) = spec_own;
+                if (PROF) { owner_cyc += clock64() - oc0; owner_n++; }
+            }
+            if ((tid >> 5) == help_warp) {
+                const uint32_t lane = tid & 31;
+                const uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+                if (lane == 31) {
+                    const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
+                    #pragma unroll 1
+                    for (uint32_t k = 0; k < K; k++)
+                        if (sc_req[k] != 0) SC.req_scalar[(uint64_t)k * N + g] += sc_req[k];
+                    SC.out_node[i] = (int32_t)g;
+                    if (SC.out_score) SC.out_score[i] = C.F > 1 ? win_total : 0;
+                    if (C.has_gpu) {
+                        int slots[64];
+                        int ns = gpu_allocate(P, SC, cw[SCW_GPU_MEM], cw[SCW_GPU_COUNT], g, slots);
+                        #pragma unroll 1
+                        for (int q = 0; q < ns && q < 64; q++) SC.gpu_used[(uint64_t)slots[q] * N + g] += cw[SCW_GPU_MEM];
+                    }
                 }
-                atomicAdd(&SC.cnt[P.cnt_off[k] + d], 1);
-                atomicAdd(&SC.cnt_total[k], 1);
-            }
-            if (C.has_gpu) {
-                int slots[64];
-                int ns = gpu_allocate(P, SC, cw[SCW_GPU_MEM], cw[SCW_GPU_COUNT], g, slots);
+                const int64_t *inc = cw + cw[SCW_OFF_INC];
+                const uint32_t n_inc_list = (uint32_t)cw[SCW_N_INC];
                 #pragma unroll 1
-                for (int q = 0; q < ns && q < 64; q++) SC.gpu_used[(uint64_t)slots[q] * N + g] += cw[SCW_GPU_MEM];
+                for (uint32_t u = lane; u < n_inc_list; u += 32) {
+                    int64_t k = inc[3 * u], t = inc[3 * u + 1], sig = inc[3 * u + 2];
+                    int32_t d = DOM(t, idx);
+                    if (d < 0) continue;
+                    if (sig >= 0) {
+                        bool el = (sig == cw[SCW_ELIG_SIG]) ? !win_ignored : elig_eval(P, sig, RC, g);   // same signature: the winner passed NodeAffinity
+                        if (!el) continue;
+                    }
+                    const uint32_t base = u < 32 ? S.incb[u] : (uint32_t)P.cnt_off[k];
+                    atomicAdd(&SC.cnt[base + d], 1);
+                    atomicAdd(&SC.cnt_total[k], 1);
+                }
+                __syncwarp();
             }
-            SC.out_node[i] = (int32_t)g;
-            if (SC.out_score) SC.out_score[i] = C.F > 1 ? win_total : 0;
-            own_eval(idx);      // Fit verdict + LeastAllocated/BalancedAllocation of the node that changed
         }
+        if (C.has_gpu) __syncthreads();      // the owner's next filter pass reads gpu_used, written by the helper warp
         // every thread folds the winner into its cached counter values (S.inc was built at the class change; the
         // reductions in between contain __syncthreads)
         {
@@ -984,8 +1036,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (SC.n_fail) *SC.n_fail = n_fail;
         if (SC.n_sched) *SC.n_sched = n_sched;
         if (SC.clk) SC.clk[1] = sk_globaltimer();
-        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; for (int q = 0; q < 20; q++) P.stats[8 + q] = (unsigned long long)tk[q]; }
+        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; for (int q = 0; q < 16; q++) P.stats[8 + q] = (unsigned long long)tk[q]; for (int q = 0; q < 6; q++) if (q != 3) P.stats[24 + q] = (unsigned long long)rprof[q]; }
     }
+    if (PROF && P.stats && scen_id == 0 && spec_n) { atomicAdd(&P.stats[27], (unsigned long long)spec_cyc); atomicAdd(&P.stats[5], (unsigned long long)spec_n); }
+    if (PROF && P.stats && scen_id == 0 && owner_n) { atomicAdd(&P.stats[30], (unsigned long long)owner_cyc); atomicAdd(&P.stats[31], (unsigned long long)owner_n); }
     cluster.sync();   // no CTA may exit while peers can still address its shared memory
 }
 

@@ -115,6 +115,7 @@ struct SkSmem {
     int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
     uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
     uint32_t *inc;       // [SK_MAX_ENT + 1] compact list of the entries the current class increments; [SK_MAX_ENT] = count
+    uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
     int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
     SkScenario *scen;    // this cluster's scenario descriptor
@@ -130,7 +131,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * blob_words);
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
-    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1));
+    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32);
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
@@ -147,6 +148,7 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.ent = (int32_t *)p; p += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.inc = (uint32_t *)p; p += sk_align(4ull * (SK_MAX_ENT + 1));
+    S.incb = (uint32_t *)p; p += sk_align(4ull * 32);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
@@ -191,6 +193,7 @@ struct SkRed {
     cg::cluster_group *cluster;
     uint32_t crank, CS;
     uint32_t mph;      // reduction phase counter (selects inbox buffer, mbarrier and parity)
+    long long *prof;   // profiling variants: [0] cycles in the reductions' __syncthreads, [1] from there to the mbarrier release, [2] count
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -308,7 +311,9 @@ __device__ __forceinline__ void sk_allreduce_w(SkRed &R, uint32_t (&w)[NW], cons
 #pragma unroll
         for (int i = 0; i < NW; i++) wp[i * SK_MAX_WARPS + warp] = w[i];
     }
+    const long long pt0 = R.prof ? clock64() : 0;
     __syncthreads();
+    const long long pt1 = R.prof ? clock64() : 0;
     if (warp == 0) {
         uint32_t c[NW];
 #pragma unroll
@@ -324,6 +329,7 @@ __device__ __forceinline__ void sk_allreduce_w(SkRed &R, uint32_t (&w)[NW], cons
         }
     }
     sk_mbar_wait(&S.mbar[buf], parity);
+    if (R.prof) { R.prof[0] += pt1 - pt0; R.prof[1] += clock64() - pt1; R.prof[2] += 1; }
     const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
 #pragma unroll
     for (int m = 0; m < NM; m++) {
@@ -336,16 +342,19 @@ __device__ __forceinline__ void sk_allreduce_w(SkRed &R, uint32_t (&w)[NW], cons
 }
 
 // Arg-max: value 0 of the message is the key (0 = no candidate); values 1..SK_PLW carry the payload of the CTA-local
-// winner (its topology domains + node flags, read from this CTA's shared memory by warp 0).
-// Returns the winning key; `who` addresses the winner's message for sk_wpay().
-__device__ __forceinline__ unsigned long long sk_argmax(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, uint32_t &who) {
+// winner (its topology domains + node flags, read from this CTA's shared memory by warp 0).  Split in two so that the
+// caller can work while the messages travel: sk_argmax_send returns the WARP-level maximum of the keys,
+// sk_argmax_wait the winning key; `who` addresses the winner's message for sk_wpay().
+__device__ __forceinline__ unsigned long long sk_argmax_send(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     SkSmem &S = *R.S;
-    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, ns = S.nslots;
+    const uint32_t ph = R.mph, buf = ph & 1, ns = S.nslots;
     if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (1 + SK_PLW) * 8u);
     key = warp_maxu64(key);
     if (lane == 0) S.wpart[warp] = key;
+    const long long pt0 = R.prof ? clock64() : 0;
     __syncthreads();
+    if (R.prof) R.prof[3] += clock64() - pt0;
     if (warp == 0) {
         const unsigned long long k = warp_maxu64(lane < nwarp ? S.wpart[lane] : 0ull);
         int32_t pw = -1;
@@ -369,13 +378,25 @@ __device__ __forceinline__ unsigned long long sk_argmax(SkRed &R, unsigned long 
             for (int j = 0; j < SK_PLW; j++) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
         }
     }
+    return key;
+}
+__device__ __forceinline__ unsigned long long sk_argmax_wait(SkRed &R, uint32_t &who) {
+    const unsigned lane = threadIdx.x & 31;
+    SkSmem &S = *R.S;
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, ns = S.nslots;
+    const long long pt1 = R.prof ? clock64() : 0;
     sk_mbar_wait(&S.mbar[buf], parity);
+    if (R.prof) { R.prof[4] += clock64() - pt1; R.prof[5] += 1; }
     const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
     const unsigned long long y = lane < ns ? bx[lane] : 0ull;
     const unsigned long long m = warp_maxu64(y);
     who = buf * SK_NV * ns + (__ffs(__ballot_sync(0xffffffffu, y == m)) - 1);
     R.mph++;
     return m;
+}
+__device__ __forceinline__ unsigned long long sk_argmax(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB, uint32_t &who) {
+    sk_argmax_send(R, key, CT, TPB);
+    return sk_argmax_wait(R, who);
 }
 // word j (0..9) of the winner's payload: j < T -> domain of topology j, 8 -> node flags
 __device__ __forceinline__ int32_t sk_wpay(const SkSmem &S, uint32_t who, uint32_t j) {

@@ -49,7 +49,7 @@ NODE_HAS_LABELS = 2
  SCW_OFF_PREF, SCW_N_PREF, SCW_OFF_PORTS, SCW_N_PORTS, SCW_OFF_PTS_HARD, SCW_N_PTS_HARD, SCW_OFF_PTS_SOFT,
  SCW_N_PTS_SOFT, SCW_OFF_IPA_AFF, SCW_N_IPA_AFF, SCW_OFF_IPA_ANTI, SCW_N_IPA_ANTI, SCW_OFF_IPA_EXIST,
  SCW_N_IPA_EXIST, SCW_OFF_IPA_SCORE, SCW_N_IPA_SCORE, SCW_OFF_INC, SCW_N_INC, SCW_OFF_ENT, SCW_N_ENT, SCW_ANY_TABLE,
- SCW_HDR_WORDS) = range(40)
+ SCW_ELIG_SIG, SCW_HDR_WORDS) = range(41)
 CLS_HAS_REQUEST = 1
 CLS_TOL_UNSCHED = 2
 CLS_IPA_SELF_MATCH = 4
@@ -947,6 +947,8 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
             r.extend([inc, wo, int(cnt_base[kid])])
         w[SCW_N_ENT] = len(ent_rows)
         w[SCW_ANY_TABLE] = any_table
+        es = elig_sig(c)
+        w[SCW_ELIG_SIG] = -1 if es is None else es
         for r in ent_rows:
             body.extend(r)
         # static signature: everything the per-(class, node) static evaluation depends on

@@ -146,8 +146,11 @@ class Engine:
         self._check(lib().simon_stats(self.h, a.ctypes.data))
         return dict(decisions=int(a[0]), class_switches=int(a[1]), summary_rebuilds=int(a[2]), redone=int(a[3]), static_evals=int(a[4]),
                     cycles=dict(zip(['loop', 'fixed', 'class_change_tail', 'r1', 'p1', 'reduce_steady', 'reduce_summary', 'p3', 'argmax', 'commit',
-                                     'cc_pre', 'cc_sync', 'cc_blob', 'cc_entry', 'cc_static'],
-                                    [int(x) for x in a[8:23]])))
+                                     'cc_pre', 'cc_sync', 'cc_blob', 'cc_entry', 'cc_static', 'pts_pass_steady'],
+                                    [int(x) for x in a[8:24]])),
+                    reductions=dict(zip(['allreduce_bar', 'allreduce_exchange', 'allreduce_n', 'argmax_bar', 'argmax_exchange', 'argmax_n'],
+                                        [int(x) for x in a[24:30]])),
+                    owner_commit=dict(cycles=int(a[30]), n=int(a[31])), spec_own=dict(cycles=int(a[27]), n=int(a[5])))
 
     def last_kernel_ms(self) -> float:
         return float(lib().simon_last_kernel_ms(self.h))

@@ -10,7 +10,7 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
     sk_carve(S, smem_raw, blockDim.x, 2, 4, 64, cluster.num_blocks());
     for (uint32_t q = threadIdx.x; q < (B_N32 + 2 + 4) * blockDim.x; q += blockDim.x) S.a32[q] = (int32_t)q;
     for (uint32_t q = threadIdx.x; q < C_N8 * blockDim.x; q += blockDim.x) S.a8[q] = (uint8_t)q;
-    SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0};
+    SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0, nullptr};
     sk_red_init(R);
     long long t0 = clock64();
     unsigned long long acc = threadIdx.x;
