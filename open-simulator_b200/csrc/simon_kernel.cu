@@ -1004,18 +1004,29 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // reductions in between contain __syncthreads)
         {
             const uint32_t n_inc = S.inc[SK_MAX_ENT];
+            uint32_t cur_row = 0xffffffffu;
+            unsigned long long match = 0;                        // which of this thread's nodes share the winner's domain of cur_row (NPT <= 64)
             #pragma unroll 1
             for (uint32_t k = 0; k < n_inc; k++) {
                 const uint32_t rec = S.inc[k], e = rec & 0xff, trow = (rec >> 8) & 0xff;
-                if ((rec & (1u << 16)) && win_ignored) continue;
-                const int32_t wd = sk_wpay(S, who, trow);
-                if (wd < 0) continue;
-                #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-                for (uint32_t s = 0; s < NPT; s++) {
-                    uint32_t idx = s * TPB + tid;
-                    if ((A8(C_NFLAGS, idx) & NF_VALID) && DOM(trow, idx) == wd) VAL(e, idx) += 1;
+                if (trow != cur_row) {
+                    cur_row = trow;
+                    match = 0;
+                    const int32_t wd = sk_wpay(S, who, trow);
+                    if (wd >= 0) {
+                        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+                        for (uint32_t s = 0; s < NPT; s++) {
+                            uint32_t idx = s * TPB + tid;
+                            if ((A8(C_NFLAGS, idx) & NF_VALID) && DOM(trow, idx) == wd) match |= 1ull << s;
+                        }
+                    }
                 }
-                if (rec & (1u << 17)) C.aff_total += 1;
+                if ((rec & (1u << 16)) && win_ignored) continue;
+                if (rec & (1u << 17)) { if (sk_wpay(S, who, trow) >= 0) C.aff_total += 1; }
+                if (!match) continue;
+                #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+                for (uint32_t s = 0; s < NPT; s++)
+                    if (match >> s & 1) VAL(e, s * TPB + tid) += 1;
             }
         }
         n_sched++;
