@@ -172,7 +172,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     sk_red_init(R);
     const ReqCtx RC{P.label_bits, N};
     const bool leader = (gtid == 0);
-    unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0;
+    unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0, st_fast = 0;
+    uint32_t last_win_r = 0xffffffffu;     // scenario rank of the last winner while its class stays current
+    bool last_win_ign = false;
     long long tk[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_prev = PROF ? clock64() : 0;
     (void)t_prev;
@@ -456,6 +458,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // =================================================================================================
         if (cls != cur_class) {
             st_class++;
+            last_win_r = 0xffffffffu;
             // remember the summary of the class we leave: it is the prediction for its next visit
             // remember the class we leave: its summary AND the feasibility bits it is exact for.  On the next visit the
             // bits are restored and P1 detects any change against them, exactly as between two pods of one class.
@@ -720,7 +723,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
 
         TICK(3);
         // ---- P1: filters on cached state ----
-        bool my_flip = false;
+        uint32_t my_fl = 0;                 // bit 0: some node flipped; bit 1: the last winner became infeasible; bits 2..5: it held an extreme
+        uint32_t my_nf = 0;
         int32_t my_dc = 0;                  // net change of the counted (feasible, not ignored) set seen by this thread
         int64_t ipa_lo = 0, ipa_hi = 0;     // min/max of raw InterPodAffinity scores (initialised to 0: scoring.go:255)
         #pragma unroll (NPT_T > 0 ? NPT_T : 1)
@@ -729,7 +733,12 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             uint8_t nf = A8(C_NFLAGS, idx);
             if (!(nf & NF_VALID)) continue;
             bool feas = filter_node(idx, nf, hard_min, false) == 0;
-            if (feas != ((nf & NF_FEASIBLE) != 0)) my_flip = true;
+            if (feas != ((nf & NF_FEASIBLE) != 0)) {
+                my_fl |= 1u; my_nf++;
+                if (!feas && s * CT + gtid == last_win_r)
+                    my_fl |= 2u | ((int64_t)(uint32_t)A32(B_RAW_NA, idx) == C.na_max ? 4u : 0u) | ((int64_t)(uint32_t)A32(B_RAW_TT, idx) == C.tt_max ? 8u : 0u) |
+                             (A64(A_SIMON, idx) == C.simon_max ? 16u : 0u) | (A64(A_SIMON, idx) == C.simon_min ? 32u : 0u);
+            }
             bool counted = feas && !(nf & NF_IGNORED);
             my_dc += (int32_t)counted - (int32_t)((nf & NF_COUNTED) != 0);
             if (C.any_table && counted != ((nf & NF_COUNTED) != 0)) {
@@ -763,13 +772,12 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             // steady state: the summary is exact unless some node flipped feasibility since it was taken
             pts_pass(plo, phi);
             TICK(15);
-            uint32_t pv[6] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_flip ? 1u : 0u, (uint32_t)my_dc};
-            const int pop[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
-            sk_allreduce_w<6>(R, pv, pop);
+            uint32_t pv[7] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_fl, (uint32_t)my_dc, my_nf};
+            const int pop[7] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM, W_SUM};
+            sk_allreduce_w<7>(R, pv, pop);
             pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]); ipa_min = w_dec(pv[2]); ipa_max = w_dec(pv[3]);
-            if (pv[4] != 0) {
-                // some node flipped: the summary is rebuilt below.  The hostname-topology sizes (= counted nodes) are known
-                // already from the net change, so the rebuild's spread pass runs under exact weights (no second pass)
+            if (pv[4] & 1u) {
+                // some node flipped.  The hostname-topology sizes (= counted nodes) follow from the net change at once.
                 C.sum_valid = false; st_redo++;
                 const int32_t dc = (int32_t)pv[5];
                 bool ch = false;
@@ -777,6 +785,47 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 for (int js = 0; js < SK_MAX_SOFT; js++)
                     if ((uint32_t)js < C.n_soft && ENT(ER_B, C.e_soft + js) && psz[js] + dc >= 0 && (long long)psz[js] + dc + 2 < (long long)P.n_log) { psz[js] += dc; ch = true; }
                 if (ch && dc != 0) set_weights();
+                if (pv[6] == 1 && (pv[4] & 2u) && !C.any_table) {
+                    // The ONLY change is that the last winner left the feasible set (the usual effect of required
+                    // anti-affinity or of a node filling up).  The summary of F \ {w} equals the old one with F-1 (and the
+                    // ignored count) unless w was the last holder of an extreme or of a topology domain: check exactly that
+                    // with one small reduction, together with the spread range under the new weights.
+                    const uint32_t need_ext = (pv[4] >> 2) & 15u;
+                    uint32_t need = need_ext, got = 0;
+                    pts_pass(plo, phi);
+                    #pragma unroll 1
+                    for (uint32_t js = 0; js < C.n_soft; js++)
+                        if (!last_win_ign && !ENT(ER_B, C.e_soft + js)) need |= 16u << js;
+                    #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+                    for (uint32_t s = 0; s < NPT; s++) {
+                        uint32_t idx = s * TPB + tid;
+                        uint8_t nf = A8(C_NFLAGS, idx);
+                        if (!(nf & NF_FEASIBLE)) continue;
+                        if (need_ext) {
+                            if ((int64_t)(uint32_t)A32(B_RAW_NA, idx) == C.na_max) got |= 1u;
+                            if ((int64_t)(uint32_t)A32(B_RAW_TT, idx) == C.tt_max) got |= 2u;
+                            if (A64(A_SIMON, idx) == C.simon_max) got |= 4u;
+                            if (A64(A_SIMON, idx) == C.simon_min) got |= 8u;
+                        }
+                        if ((need >> 4) && (nf & NF_COUNTED)) {
+                            #pragma unroll 1
+                            for (uint32_t js = 0; js < C.n_soft; js++) {
+                                const uint32_t t = (uint32_t)ENT(ER_T, C.e_soft + js);
+                                if (!ENT(ER_B, C.e_soft + js) && DOM(t, idx) == S.lastdom[t]) got |= 16u << js;
+                            }
+                        }
+                    }
+                    uint32_t qv[3] = {e32(plo), e32(phi), got};
+                    const int qop[3] = {W_MIN, W_MAX, W_OR};
+                    sk_allreduce_w<3>(R, qv, qop);
+                    if ((qv[2] & need) == need) {
+                        C.F -= 1;
+                        if (last_win_ign) C.n_ign -= 1;
+                        pts_min = w_dec(qv[0]); pts_max = w_dec(qv[1]);
+                        C.sum_valid = true;
+                        st_fast++;
+                    }
+                }
             }
         }
         TICK(5);
@@ -950,6 +999,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // NEIGHBOUR warp of the same CTA does everything that goes to global memory - results, scalar aggregates and the
         // class's commit list, one counter entry per lane - so that no single warp carries the whole serial chain.
         const uint32_t win_g = win_r % CT;                       // cluster-wide thread index of the owner
+        last_win_r = win_r; last_win_ign = win_ignored;
+        if (tid < T) S.lastdom[tid] = sk_wpay(S, who, tid);
         if (win_g / TPB == crank) {
             const uint32_t own_tid = win_g % TPB, own_warp = own_tid >> 5, nwarp_cta = (TPB + 31) >> 5;
             const uint32_t help_warp = own_warp + 1 < nwarp_cta ? own_warp + 1 : 0;
@@ -1047,7 +1098,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (SC.n_fail) *SC.n_fail = n_fail;
         if (SC.n_sched) *SC.n_sched = n_sched;
         if (SC.clk) SC.clk[1] = sk_globaltimer();
-        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; for (int q = 0; q < 16; q++) P.stats[8 + q] = (unsigned long long)tk[q]; for (int q = 0; q < 6; q++) if (q != 3) P.stats[24 + q] = (unsigned long long)rprof[q]; }
+        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; P.stats[6] = st_fast; for (int q = 0; q < 16; q++) P.stats[8 + q] = (unsigned long long)tk[q]; for (int q = 0; q < 6; q++) if (q != 3) P.stats[24 + q] = (unsigned long long)rprof[q]; }
     }
     if (PROF && P.stats && scen_id == 0 && spec_n) { atomicAdd(&P.stats[27], (unsigned long long)spec_cyc); atomicAdd(&P.stats[5], (unsigned long long)spec_n); }
     if (PROF && P.stats && scen_id == 0 && owner_n) { atomicAdd(&P.stats[30], (unsigned long long)owner_cyc); atomicAdd(&P.stats[31], (unsigned long long)owner_n); }

@@ -115,6 +115,7 @@ struct SkSmem {
     int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
     uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
     uint32_t *inc;       // [SK_MAX_ENT + 1] compact list of the entries the current class increments; [SK_MAX_ENT] = count
+    int32_t *lastdom;    // [SIMON_MAX_TOPOS] topology domains of the last winner (single-node flip fast path)
     uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
     int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
@@ -131,7 +132,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * blob_words);
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
-    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32);
+    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS);
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
@@ -149,6 +150,7 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.inc = (uint32_t *)p; p += sk_align(4ull * (SK_MAX_ENT + 1));
     S.incb = (uint32_t *)p; p += sk_align(4ull * 32);
+    S.lastdom = (int32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));

@@ -144,7 +144,7 @@ class Engine:
     def stats(self):
         a = np.zeros(32, np.uint64)
         self._check(lib().simon_stats(self.h, a.ctypes.data))
-        return dict(decisions=int(a[0]), class_switches=int(a[1]), summary_rebuilds=int(a[2]), redone=int(a[3]), static_evals=int(a[4]),
+        return dict(decisions=int(a[0]), class_switches=int(a[1]), summary_rebuilds=int(a[2]), redone=int(a[3]), static_evals=int(a[4]), single_flip_fast=int(a[6]),
                     cycles=dict(zip(['loop', 'fixed', 'class_change_tail', 'r1', 'p1', 'reduce_steady', 'reduce_summary', 'p3', 'argmax', 'commit',
                                      'cc_pre', 'cc_sync', 'cc_blob', 'cc_entry', 'cc_static', 'pts_pass_steady'],
                                     [int(x) for x in a[8:24]])),
