@@ -458,7 +458,6 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // =================================================================================================
         if (cls != cur_class) {
             st_class++;
-            last_win_r = 0xffffffffu;
             // remember the summary of the class we leave: it is the prediction for its next visit
             // remember the class we leave: its summary AND the feasibility bits it is exact for.  On the next visit the
             // bits are restored and P1 detects any change against them, exactly as between two pods of one class.
@@ -468,6 +467,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
 #pragma unroll
                     for (int js = 0; js < SK_MAX_SOFT; js++) rec[1 + js] = (uint32_t)js < C.n_soft ? psz[js] : 0;
                     rec[9] = C.F; rec[10] = C.n_ign; rec[11] = C.na_max; rec[12] = C.tt_max; rec[13] = C.simon_max; rec[14] = C.simon_min;
+                    // the last winner: it is the node most likely to have flipped when the class is visited again
+                    rec[15] = last_win_r == 0xffffffffu ? -1ll : (long long)last_win_r; rec[16] = last_win_ign ? 1 : 0;
+#pragma unroll
+                    for (int q = 0; q < SIMON_MAX_TOPOS; q++) rec[17 + q] = (uint32_t)q < T ? S.lastdom[q] : -1;
                     rec[0] = 1;
                 }
                 #pragma unroll 1
@@ -490,10 +493,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             #pragma unroll 1
             for (uint32_t w = tid; w < words; w += TPB) S.blob[w] = gw[w];
             // prediction of the topology sizes from the previous visit of this class (any value is safe: verified)
-            long long pred[SK_CSUM_W];
-#pragma unroll
-            for (int q = 0; q < SK_CSUM_W; q++) pred[q] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + q) : 0;
+            if (tid < SK_CSUM_W) S.pred[tid] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + tid) : 0;
             __syncthreads();
+            const long long *pred = S.pred;
             TICK(12);
             C.cflags = (uint32_t)cw[SCW_FLAGS];
             C.n_ports = (uint32_t)cw[SCW_N_PORTS]; C.n_hard = (uint32_t)cw[SCW_N_PTS_HARD]; C.n_soft = (uint32_t)cw[SCW_N_PTS_SOFT];
@@ -507,8 +509,15 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             C.any_table = cw[SCW_ANY_TABLE] != 0;
             C.have_pred = pred[0] == 1;
             const bool restore = C.have_pred && !C.any_table && SC.fbits;
+            last_win_r = 0xffffffffu;
             if (restore) {
                 C.F = pred[9]; C.n_ign = pred[10]; C.na_max = pred[11]; C.tt_max = pred[12]; C.simon_max = pred[13]; C.simon_min = pred[14];
+                if (pred[15] >= 0) {
+                    last_win_r = (uint32_t)pred[15]; last_win_ign = pred[16] != 0;
+#pragma unroll
+                    for (int q = 0; q < SIMON_MAX_TOPOS; q++)
+                        if (tid == (uint32_t)q && (uint32_t)q < T) S.lastdom[q] = (int32_t)pred[17 + q];
+                }
                 C.sum_valid = true;
             }
 #pragma unroll

@@ -25,7 +25,7 @@ namespace cg = cooperative_groups;
 #define SK_NV 16            // max values per all-reduce
 #define SK_PLW 5            // payload: 10 int32 packed in 5 u64 (T domains + flags)
 #define SK_MAX_WARPS 16     // threads per CTA <= 512 (the shipped variants use <= 320)
-#define SK_CSUM_W 16
+#define SK_CSUM_W 26          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains (+1 spare)
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
 enum { ER_KIND = 0, ER_K, ER_T, ER_A, ER_B, ER_INC, ER_WOFF, ER_BASE, ER_ROWS };   // ER_BASE: offset of the counter in cnt[]
@@ -115,6 +115,7 @@ struct SkSmem {
     int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
     uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
     uint32_t *inc;       // [SK_MAX_ENT + 1] compact list of the entries the current class increments; [SK_MAX_ENT] = count
+    long long *pred;     // [SK_CSUM_W] the entered class's stored summary record (one global read per CTA)
     int32_t *lastdom;    // [SIMON_MAX_TOPOS] topology domains of the last winner (single-node flip fast path)
     uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
@@ -132,7 +133,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * blob_words);
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
-    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS);
+    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(8ull * SK_CSUM_W);
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
@@ -151,6 +152,7 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.inc = (uint32_t *)p; p += sk_align(4ull * (SK_MAX_ENT + 1));
     S.incb = (uint32_t *)p; p += sk_align(4ull * 32);
     S.lastdom = (int32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
+    S.pred = (long long *)p; p += sk_align(8ull * SK_CSUM_W);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
