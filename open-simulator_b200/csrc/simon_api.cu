@@ -44,6 +44,7 @@ struct ScenState {
     DevBuf<int32_t> num_pods, cnt, cnt_total, tp, fcount, size;
     DevBuf<long long> csum;
     DevBuf<uint8_t> fbits;
+    DevBuf<unsigned long long> ocache;
     DevBuf<uint8_t> hard_reg;
     DevBuf<int32_t> out_node;
     DevBuf<int64_t> out_score;
@@ -116,6 +117,8 @@ int alloc_state(simon_ctx *ctx, ScenState &s, uint32_t max_fail, bool scores) {
     CU(s.size.alloc(SK_MAX_SOFT)); CU(s.hard_reg.alloc((size_t)SK_MAX_HARD * ctx->max_dom));
     CU(s.csum.alloc((size_t)ctx->n_classes * SK_CSUM_W));
     CU(s.fbits.alloc((size_t)ctx->n_classes * N));
+    CU(s.ocache.alloc((size_t)ctx->n_classes * N));
+    CU(cudaMemsetAsync(s.ocache.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * N), ctx->stream));
     CU(cudaMemsetAsync(s.csum.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * SK_CSUM_W), ctx->stream));
     CU(s.out_node.alloc(ctx->n_pods));
     if (scores) CU(s.out_score.alloc(ctx->n_pods));
@@ -133,6 +136,8 @@ int reset_state(simon_ctx *ctx, ScenState &s) {
     CU(cudaMemsetAsync(s.gpu_used.p, 0, 8ull * SIMON_MAX_GPU_DEV * N, st)); CU(cudaMemsetAsync(s.num_pods.p, 0, 4ull * N, st));
     CU(cudaMemsetAsync(s.cnt.p, 0, 4ull * (ctx->cnt_words ? ctx->cnt_words : 1), st));
     CU(cudaMemsetAsync(s.cnt_total.p, 0, 4ull * (ctx->n_counters ? ctx->n_counters : 1), st));
+    // the own-score cache is keyed by the node's pod count, which restarts with the state
+    if (s.ocache.p) CU(cudaMemsetAsync(s.ocache.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * N), st));
     return SIMON_OK;
 }
 
@@ -143,7 +148,7 @@ void fill_scen(simon_ctx *ctx, ScenState &s, SkScenario &o, uint32_t n_active, b
     o.pad = 0;
     o.req_mcpu = s.req_mcpu.p; o.req_mem = s.req_mem.p; o.req_eph = s.req_eph.p; o.nz_mcpu = s.nz_mcpu.p; o.nz_mem = s.nz_mem.p;
     o.req_scalar = s.req_scalar.p; o.gpu_used = s.gpu_used.p; o.num_pods = s.num_pods.p; o.cnt = s.cnt.p; o.cnt_total = s.cnt_total.p;
-    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p; o.csum = s.csum.p; o.fbits = s.fbits.p;
+    o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p; o.csum = s.csum.p; o.fbits = s.fbits.p; o.ocache = s.ocache.p;
     o.out_node = s.out_node.p; o.out_score = s.out_score.p;
     o.fail_counts = s.fail_counts.p; o.fail_pod = s.fail_pod.p; o.n_fail = s.counters.p; o.n_sched = s.counters.p + 1;
     o.clk = s.clk.p;

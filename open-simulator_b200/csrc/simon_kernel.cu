@@ -565,12 +565,13 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 long long sim4[4];
                 int32_t v4[4][4], ex4[4];
                 uint8_t fb4[4];
+                unsigned long long oc4[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     uint32_t s = s0 + u;
                     uint32_t idx = s * TPB + tid;
                     bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
-                    rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000; fb4[u] = 0;
+                    rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000; fb4[u] = 0; oc4[u] = 0;
 #pragma unroll
                     for (int e = 0; e < 4; e++) v4[u][e] = 0;
                     if (valid) {
@@ -579,6 +580,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         sim4[u] = __ldg(&simon_row[A32(B_NODE_CLASS, idx)]);
                         if (extra) ex4[u] = __ldg(&extra[g]);
                         if (restore) fb4[u] = __ldcg(&SC.fbits[(uint64_t)cls * N + g]);
+                        if (SC.ocache) oc4[u] = __ldcg(&SC.ocache[(uint64_t)cls * N + g]);
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                             if ((uint32_t)e < C.E) {
@@ -650,7 +652,18 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         VAL(e, idx) = d >= 0 ? ldcg32(&SC.cnt[(uint32_t)ENT(ER_BASE, e) + (uint32_t)d]) : 0;
                     }
                     A8(C_REGBITS, idx) = 0;
-                    own_eval(idx);
+                    // own-state score: unchanged since the class's last visit unless the node received a pod in between
+                    const uint32_t ver = (uint32_t)A32(B_NUM_PODS, idx) + 1u;
+                    if ((uint32_t)(oc4[u] >> 32) == ver) {
+                        const uint32_t lo = (uint32_t)oc4[u];
+                        A8(C_NFLAGS, idx) = (nf & ~NF_FIT_OK) | ((lo & 1u) ? NF_FIT_OK : 0);
+                        A32(B_OWN, idx) = (int32_t)lo >> 1;
+                    } else {
+                        own_eval(idx);
+                        if (SC.ocache)
+                            SC.ocache[(uint64_t)cls * N + g] = ((unsigned long long)ver << 32) | ((uint32_t)A32(B_OWN, idx) << 1) |
+                                                               ((A8(C_NFLAGS, idx) & NF_FIT_OK) ? 1u : 0u);
+                    }
                 }
             }
             if (restore) snorm_pass();

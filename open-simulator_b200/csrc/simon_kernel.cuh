@@ -60,6 +60,7 @@ struct SkScenario {
     // scratch tables [SK_MAX_SOFT or SK_MAX_HARD][max_dom]
     int32_t *tp, *fcount, *size;   // size: [SK_MAX_SOFT]
     long long *csum;           // [n_classes][SK_CSUM_W] feasible-set summary per class as of its last visit
+    unsigned long long *ocache; // [n_classes][N] own-state score cache: {node version (num_pods + 1):32, fit:1, own score:31}; 0 = empty
     uint8_t *fbits;            // [n_classes][N] NF_FEASIBLE|NF_COUNTED per node as of that visit (what csum is exact for)
     uint8_t *hard_reg;
     // outputs
