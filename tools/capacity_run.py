@@ -40,7 +40,11 @@ t0 = time.perf_counter()
 cluster, apps, specs = synth.make_c4(n_nodes=a.nodes, n_workloads=a.workloads, replicas=a.replicas)
 ss = capacity.build_scenarios(cluster, apps, specs, list(range(1, a.ks + 1)))
 t_build = time.perf_counter() - t0
+# warm-up pass: CUDA context, engine buffers and the first NCCL collective (communicator set-up) are not part of the search time
+capacity.search(ss, capacity.gpu_runner(local), rank=rank, world=world, all_reduce_min=reduce_fn)
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 t1 = time.perf_counter()
 best, local_res = capacity.search(ss, capacity.gpu_runner(local), rank=rank, world=world, all_reduce_min=reduce_fn)
 torch.cuda.synchronize()
