@@ -475,7 +475,12 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
     for n in snodes:
         lst = []
         for t in ((n.get("spec") or {}).get("taints") or []):
-            lst.append(taint_ids.get((t.get("key") or "", t.get("value") or "", t.get("effect") or "")))
+            tid = taint_ids.get((t.get("key") or "", t.get("value") or "", t.get("effect") or ""))
+            if tid in lst:
+                # the API server rejects duplicate (key, effect) taints; the reference would count such a taint twice in
+                # TaintToleration's score (taint_toleration.go:122-135), which a presence bitmask cannot express
+                raise CompileError(f"node {n['metadata'].get('name')}: duplicate taint {t.get('key')}:{t.get('effect')}")
+            lst.append(tid)
         node_taints.append(lst)
     n_taints = len(taint_ids.items)
     WT = max(1, (n_taints + 63) // 64)

@@ -242,3 +242,211 @@ def make_c4(n_nodes: int = 2000, n_workloads: int = 50, replicas: int = 100, fil
     for si, cores in enumerate(CPU_SHAPES):
         specs.append(_node(f"spec-{si}", cores, f"zone-{si % 16:02d}", "", 500))
     return cluster, [app], specs
+
+
+def make_mix(seed_no: int = 100, n_nodes: int = 40, n_workloads: int = 30, max_replicas: int = 6):
+    """Small clusters that exercise EVERY predicate / score input the path knows, in random combinations: unschedulable
+    nodes, NoSchedule / NoExecute / PreferNoSchedule taints and all toleration shapes, nodeSelector, required and
+    preferred node affinity with In / NotIn / Exists / DoesNotExist / Gt / Lt and matchFields, host ports (with and
+    without hostIP), extended (scalar) resources, ephemeral storage, init containers and overhead, required and
+    preferred pod (anti-)affinity incl. self-affinity, hard and soft topology spread over hostname / zone / region with
+    nodes that lack the zone label, GPU-share pods and nodes, pre-bound pods, DaemonSets, StatefulSets, Jobs and
+    bare Pods.  Used by the parity tests (C oracle vs object-level restatement vs GPU)."""
+    rng = SplitMix64(SEED_BASE + 0x1000 + seed_no)
+    cluster = ResourceTypes()
+    hard_taints = [{"key": f"dedicated-{i}", "value": f"team-{i}", "effect": "NoSchedule"} for i in range(3)]
+    hard_taints.append({"key": "maintenance", "value": "true", "effect": "NoExecute"})
+    soft_taints = [{"key": f"degraded-{i}", "value": "true", "effect": "PreferNoSchedule"} for i in range(3)]
+    label_keys = [f"feature-{k}" for k in range(6)]
+    node_names = []
+    for i in range(n_nodes):
+        cores = rng.pick([4, 8, 16, 32])
+        region = f"region-{i % 2}"
+        zone = f"{region}-zone-{(i // 2) % 4}"
+        labels = {"rank": str(rng.below(100))}
+        for k in label_keys:
+            if rng.chance(50):
+                labels[k] = f"v{rng.below(3)}"
+        taints = []
+        if rng.chance(15):
+            taints.append(dict(rng.pick(hard_taints)))
+        if rng.chance(15):
+            taints.append(dict(rng.pick(soft_taints)))
+        if rng.chance(5):
+            t2 = dict(rng.pick(soft_taints))
+            if all((t["key"], t["effect"]) != (t2["key"], t2["effect"]) for t in taints):   # the API server rejects duplicate (key, effect)
+                taints.append(t2)
+        name = f"node-{i:03d}"
+        node_names.append(name)
+        n = _node(name, cores, zone, region, rng.pick([50, 100, 200]), labels, taints or None, pods=rng.pick([8, 16, 110]))
+        if rng.chance(10):
+            del n["metadata"]["labels"]["topology.kubernetes.io/zone"]          # spreading / affinity over a missing key
+        if rng.chance(5):
+            n["spec"]["unschedulable"] = True
+        if rng.chance(30):
+            w = str(rng.pick([2, 4, 8]))
+            n["status"]["allocatable"]["example.com/widget"] = w
+            n["status"]["capacity"]["example.com/widget"] = w
+        if rng.chance(25):
+            cnt = rng.pick([1, 2, 4])
+            mem = f"{cnt * rng.pick([8, 16])}Gi"
+            for sect in ("allocatable", "capacity"):
+                n["status"][sect]["alibabacloud.com/gpu-count"] = str(cnt)
+                n["status"][sect]["alibabacloud.com/gpu-mem"] = mem
+        cluster.Nodes.append(n)
+    # pre-bound pods (some carry labels that later selectors match, some hold host ports)
+    for i in range(n_nodes):
+        if not rng.chance(30):
+            continue
+        for j in range(1 + rng.below(3)):
+            c = {"name": "c", "image": "registry.local/sys:v1",
+                 "resources": {"requests": {"cpu": f"{rng.pick([100, 250, 500])}m", "memory": f"{rng.pick([128, 256, 1024])}Mi"}}}
+            if rng.chance(20):
+                c["ports"] = [{"containerPort": 8080, "hostPort": rng.pick([8080, 8081]), "protocol": "TCP"}]
+            cluster.Pods.append({"apiVersion": "v1", "kind": "Pod",
+                                 "metadata": {"name": f"running-{i:03d}-{j}", "namespace": rng.pick(["default", "kube-system"]),
+                                              "labels": {"app": f"wl-{rng.below(n_workloads):03d}" if rng.chance(50) else f"sys-{j}"}},
+                                 "spec": {"nodeName": node_names[i], "containers": [c]}})
+    app = AppResource("mix", ResourceTypes())
+    names = [f"wl-{w:03d}" for w in range(n_workloads)]
+    zone_key, host_key, region_key = "topology.kubernetes.io/zone", "kubernetes.io/hostname", "topology.kubernetes.io/region"
+
+    def pod_term(target: str, key: str, ns=None):
+        t = {"labelSelector": {"matchLabels": {"app": target}}, "topologyKey": key}
+        if ns is not None:
+            t["namespaces"] = ns
+        return t
+
+    for w in range(n_workloads):
+        name = names[w]
+        ns = rng.pick(["default", "team-a"])
+        labels = {"app": name, "tier": rng.pick(["web", "db"])}
+        req = {}
+        if not rng.chance(10):
+            req["cpu"] = f"{_log_uniform(rng, 100, 4000, 50)}m"
+            req["memory"] = f"{_log_uniform(rng, 128, 8192, 64)}Mi"
+        if rng.chance(20):
+            req["ephemeral-storage"] = f"{rng.pick([1, 5, 20])}Gi"
+        if rng.chance(15):
+            req["example.com/widget"] = str(1 + rng.below(2))
+        cont = {"name": "c", "image": f"registry.local/{name}:v1"}
+        if req:
+            cont["resources"] = {"requests": req}
+        if rng.chance(12):
+            port = {"containerPort": 80, "hostPort": rng.pick([8080, 8081, 9090]), "protocol": rng.pick(["TCP", "UDP"])}
+            if rng.chance(30):
+                port["hostIP"] = rng.pick(["10.0.0.1", "0.0.0.0"])
+            cont["ports"] = [port]
+        spec: dict = {"containers": [cont]}
+        if rng.chance(10):
+            spec["initContainers"] = [{"name": "init", "image": "registry.local/init:v1",
+                                       "resources": {"requests": {"cpu": f"{rng.pick([100, 2000, 6000])}m", "memory": "256Mi"}}}]
+        if rng.chance(5):
+            spec["overhead"] = {"cpu": "100m", "memory": "64Mi"}
+        tols = []
+        if rng.chance(30):
+            t = rng.pick(hard_taints)
+            tols.append({"key": t["key"], "operator": "Equal", "value": t["value"], "effect": t["effect"]})
+        if rng.chance(15):
+            tols.append({"key": rng.pick(soft_taints)["key"], "operator": "Exists"})
+        if rng.chance(5):
+            tols.append({"operator": "Exists"})                                   # tolerates everything
+        if rng.chance(5):
+            tols.append({"key": "node.kubernetes.io/unschedulable", "operator": "Exists", "effect": "NoSchedule"})
+        if tols:
+            spec["tolerations"] = tols
+        if rng.chance(15):
+            spec["nodeSelector"] = {rng.pick(label_keys): f"v{rng.below(3)}"}
+        aff: dict = {}
+        if rng.chance(25):
+            terms = []
+            for _ in range(1 + rng.below(2)):
+                exprs = []
+                for _ in range(1 + rng.below(2)):
+                    kind = rng.below(6)
+                    k = rng.pick(label_keys)
+                    if kind == 0:
+                        exprs.append({"key": k, "operator": "In", "values": [f"v{rng.below(3)}", f"v{rng.below(3)}"]})
+                    elif kind == 1:
+                        exprs.append({"key": k, "operator": "NotIn", "values": [f"v{rng.below(3)}"]})
+                    elif kind == 2:
+                        exprs.append({"key": k, "operator": "Exists"})
+                    elif kind == 3:
+                        exprs.append({"key": k, "operator": "DoesNotExist"})
+                    elif kind == 4:
+                        exprs.append({"key": "rank", "operator": "Gt", "values": [str(rng.below(60))]})
+                    else:
+                        exprs.append({"key": "rank", "operator": "Lt", "values": [str(40 + rng.below(60))]})
+                term = {"matchExpressions": exprs}
+                if rng.chance(10):
+                    term = {"matchFields": [{"key": "metadata.name", "operator": rng.pick(["In", "NotIn"]), "values": [rng.pick(node_names)]}]}
+                terms.append(term)
+            na = {"requiredDuringSchedulingIgnoredDuringExecution": {"nodeSelectorTerms": terms}}
+            aff["nodeAffinity"] = na
+        if rng.chance(20):
+            prefs = []
+            for _ in range(1 + rng.below(2)):
+                prefs.append({"weight": 1 + rng.below(100),
+                              "preference": {"matchExpressions": [{"key": rng.pick(label_keys), "operator": rng.pick(["In", "Exists"]),
+                                                                   "values": [f"v{rng.below(3)}"]}]}})
+            for pr in prefs:
+                if pr["preference"]["matchExpressions"][0]["operator"] == "Exists":
+                    del pr["preference"]["matchExpressions"][0]["values"]
+            aff.setdefault("nodeAffinity", {})["preferredDuringSchedulingIgnoredDuringExecution"] = prefs
+        if rng.chance(12):
+            target = name if rng.chance(40) else names[rng.below(n_workloads)]
+            aff.setdefault("podAffinity", {})["requiredDuringSchedulingIgnoredDuringExecution"] = [
+                pod_term(target, rng.pick([zone_key, host_key, region_key]), ns=["default", "team-a"] if rng.chance(50) else None)]
+        if rng.chance(20):
+            aff.setdefault("podAntiAffinity", {})["requiredDuringSchedulingIgnoredDuringExecution"] = [
+                pod_term(name if rng.chance(70) else names[rng.below(n_workloads)], rng.pick([host_key, host_key, zone_key]))]
+        if rng.chance(15):
+            aff.setdefault("podAffinity", {})["preferredDuringSchedulingIgnoredDuringExecution"] = [
+                {"weight": 1 + rng.below(100), "podAffinityTerm": pod_term(names[rng.below(n_workloads)], rng.pick([zone_key, host_key]),
+                                                                           ns=["default", "team-a"])}]
+        if rng.chance(15):
+            aff.setdefault("podAntiAffinity", {})["preferredDuringSchedulingIgnoredDuringExecution"] = [
+                {"weight": 1 + rng.below(100), "podAffinityTerm": pod_term(name, rng.pick([zone_key, host_key]))}]
+        if aff:
+            spec["affinity"] = aff
+        if rng.chance(25):
+            cons = []
+            for key in ([host_key, zone_key] if rng.chance(40) else [rng.pick([host_key, zone_key, region_key])]):
+                cons.append({"maxSkew": 1 + rng.below(3), "topologyKey": key,
+                             "whenUnsatisfiable": rng.pick(["DoNotSchedule", "ScheduleAnyway"]),
+                             "labelSelector": {"matchLabels": {"app": name}}})
+            spec["topologySpreadConstraints"] = cons
+        tmeta = {"labels": dict(labels)}
+        if rng.chance(12):
+            tmeta["annotations"] = {"alibabacloud.com/gpu-mem": f"{rng.pick([2, 4, 8])}Gi", "alibabacloud.com/gpu-count": str(rng.pick([1, 1, 2]))}
+        replicas = 1 + rng.below(max_replicas)
+        kind = rng.below(10)
+        if kind < 6:
+            app.Resource.Deployments.append({"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": name, "namespace": ns},
+                                             "spec": {"replicas": replicas, "selector": {"matchLabels": {"app": name}},
+                                                      "template": {"metadata": tmeta, "spec": spec}}})
+        elif kind < 8:
+            app.Resource.StatefulSets.append({"apiVersion": "apps/v1", "kind": "StatefulSet", "metadata": {"name": name, "namespace": ns},
+                                              "spec": {"replicas": replicas, "serviceName": name, "selector": {"matchLabels": {"app": name}},
+                                                       "template": {"metadata": tmeta, "spec": spec}}})
+        elif kind == 8:
+            app.Resource.Jobs.append({"apiVersion": "batch/v1", "kind": "Job", "metadata": {"name": name, "namespace": ns},
+                                      "spec": {"completions": replicas, "template": {"metadata": tmeta, "spec": dict(spec, restartPolicy="Never")}}})
+        else:
+            app.Resource.Pods.append({"apiVersion": "v1", "kind": "Pod", "metadata": dict(tmeta, name=name, namespace=ns), "spec": spec})
+        if rng.chance(70):
+            cluster.Services.append(_service(name, ns, {"app": name}))
+    # one DaemonSet in the cluster and one in the app
+    ds_spec = {"containers": [{"name": "agent", "image": "registry.local/agent:v1",
+                               "resources": {"requests": {"cpu": "50m", "memory": "64Mi"}}}],
+               "tolerations": [{"operator": "Exists"}]}
+    cluster.DaemonSets.append({"apiVersion": "apps/v1", "kind": "DaemonSet", "metadata": {"name": "node-agent", "namespace": "kube-system"},
+                               "spec": {"selector": {"matchLabels": {"app": "node-agent"}},
+                                        "template": {"metadata": {"labels": {"app": "node-agent"}}, "spec": ds_spec}}})
+    app.Resource.DaemonSets.append({"apiVersion": "apps/v1", "kind": "DaemonSet", "metadata": {"name": "log-shipper", "namespace": "default"},
+                                    "spec": {"selector": {"matchLabels": {"app": "log-shipper"}},
+                                             "template": {"metadata": {"labels": {"app": "log-shipper"}},
+                                                          "spec": {"containers": [{"name": "ship", "image": "registry.local/ship:v1",
+                                                                                   "resources": {"requests": {"cpu": "100m", "memory": "128Mi"}}}],
+                                                                   "nodeSelector": {label_keys[0]: "v0"}}}}})
+    return cluster, [app]

@@ -39,7 +39,25 @@ def test_parity_with_oracle(kind, kw):
         np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
 
 
-@pytest.mark.parametrize("cs,tpb", [(1, 256), (2, 128), (4, 64), (8, 128), (16, 64)])
+@pytest.mark.parametrize("seed", [100, 101, 102, 103, 206, 209, 212, 215, 219, 223, 228, 238])
+def test_parity_mixed_features(seed):
+    """synth.make_mix: every predicate / score input in random combination (see tests/test_oracle_cpu.py), incl. GPU share,
+    host ports, extended resources, hard spread constraints, required pod affinity, DaemonSets and pre-bound pods."""
+    p, c = make_case("mix", seed_no=seed, n_nodes=20 + (seed % 5) * 25, n_workloads=20 + (seed % 7) * 10, max_replicas=4 + seed % 6)
+    (ref, rscore, rfc, rfp), rstate = run_oracle(c)
+    with _engine(c) as eng:
+        out, score, fc, fp = eng.schedule()
+        st = eng.state()
+    np.testing.assert_array_equal(out, ref)
+    sched = ref >= 0
+    np.testing.assert_array_equal(score[sched & (rscore > 0)], rscore[sched & (rscore > 0)])
+    np.testing.assert_array_equal(fp, rfp)
+    np.testing.assert_array_equal(fc, rfc)
+    for k in rstate:
+        np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
+
+
+@pytest.mark.parametrize("cs,tpb", [(1, 256), (2, 128), (4, 64), (8, 128), (16, 64), (16, 320), (4, 320)])
 def test_parity_cluster_geometries(cs, tpb):
     p, c = make_case("c3", n_nodes=700, n_workloads=80, replicas=12, n_apps=2, seed_no=13)
     (ref, _, rfc, _), _ = run_oracle(c)

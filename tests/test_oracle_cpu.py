@@ -20,6 +20,31 @@ def test_c_oracle_matches_pyref_c2():
     assert (out >= 0).sum() > 0
 
 
+@pytest.mark.parametrize("seed", [100, 101, 206, 209, 215, 223])
+def test_c_oracle_matches_pyref_mixed_features(seed):
+    """Every predicate / score input in random combination (synth.make_mix): unschedulable nodes, all taint effects and
+    toleration shapes, Gt/Lt/DoesNotExist/matchFields node affinity, host ports, extended resources, ephemeral storage,
+    init containers, overhead, required + preferred pod (anti-)affinity incl. self-affinity, hard + soft spread over
+    hostname/zone/region with missing keys, GPU share, pre-bound pods, DaemonSets, StatefulSets, Jobs, bare Pods."""
+    p, c = make_case("mix", seed_no=seed, n_nodes=20 + (seed % 5) * 25, n_workloads=20 + (seed % 7) * 10, max_replicas=4 + seed % 6)
+    (out, _, fc, _), _ = run_oracle(c)
+    ref = run_pyref(p, c)
+    np.testing.assert_array_equal(out, ref)
+    assert (out == -1).sum() > 0 and (out >= 0).sum() > 0          # both outcomes are exercised
+    assert fc.sum() > 0
+
+
+def test_duplicate_taints_are_rejected():
+    """A presence bitmask cannot count a taint twice (the reference's score would): such nodes are refused, not mis-scored."""
+    from simon_b200 import simulator, synth
+    from simon_b200.compiler import CompileError, compile_cluster
+    cluster, apps = synth.make_c2(n_nodes=4, n_workloads=2, replicas=2)
+    cluster.Nodes[0]["spec"]["taints"] = [{"key": "k", "value": "v", "effect": "PreferNoSchedule"}] * 2
+    p = simulator.plan(cluster, apps)
+    with pytest.raises(CompileError):
+        compile_cluster(p.nodes, p.pods, p.ctx)
+
+
 def test_abi_library_exports():
     """The C-ABI library loads and exports every symbol include/simon_gpu.h declares (no compute calls)."""
     import os, re

@@ -6,7 +6,7 @@ from simon_b200.compiler import compile_cluster
 
 
 def make_case(kind="c3", **kw):
-    cluster, apps = (synth.make_c3 if kind == "c3" else synth.make_c2)(**kw)
+    cluster, apps = {"c3": synth.make_c3, "c2": synth.make_c2, "mix": synth.make_mix}[kind](**kw)
     p = simulator.plan(cluster, apps)
     c = compile_cluster(p.nodes, p.pods, p.ctx)
     return p, c
