@@ -544,9 +544,14 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     rec = e | ((host ? 0u : (uint32_t)ENT(ER_T, e)) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) |
                           (kind == EK_AFF ? 1u << 17 : 0u);
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, inc);
-                if (inc) S.inc[__popc(m & ((1u << e) - 1u))] = rec;
-                if (e == 0) S.inc[SK_MAX_ENT] = __popc(m);
+                // entries on topology row 0 (the node itself) can only match the winner's own node: they go to the end of the
+                // list and are applied by the owning thread alone; every thread walks the others
+                const bool node_lvl = inc && ((rec >> 8) & 0xff) == 0;
+                const uint32_t m_all = __ballot_sync(0xffffffffu, inc), m_node = __ballot_sync(0xffffffffu, node_lvl);
+                const uint32_t m_dom = m_all & ~m_node, lt = (1u << e) - 1u;
+                if (inc) S.inc[node_lvl ? __popc(m_dom) + __popc(m_node & lt) : __popc(m_dom & lt)] = rec;
+                const uint32_t n_aff_node = __popc(__ballot_sync(0xffffffffu, node_lvl && (rec & (1u << 17))));
+                if (e == 0) S.inc[SK_MAX_ENT] = __popc(m_dom) | (__popc(m_all) << 8) | (n_aff_node << 16);
                 // counter bases of the commit list: fetched once per class switch, not by the committing thread
                 if ((int64_t)e < cw[SCW_N_INC]) S.incb[e] = (uint32_t)P.cnt_off[(cw + cw[SCW_OFF_INC])[3 * e]];
             }
@@ -1022,6 +1027,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // class's commit list, one counter entry per lane - so that no single warp carries the whole serial chain.
         const uint32_t win_g = win_r % CT;                       // cluster-wide thread index of the owner
         last_win_r = win_r; last_win_ign = win_ignored;
+        const bool own_thread = win_g == gtid;
+        const uint32_t own_idx = (win_r / CT) * TPB + tid;
         if (tid < T) S.lastdom[tid] = sk_wpay(S, who, tid);
         if (win_g / TPB == crank) {
             const uint32_t own_tid = win_g % TPB, own_warp = own_tid >> 5, nwarp_cta = (TPB + 31) >> 5;
@@ -1076,11 +1083,16 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // every thread folds the winner into its cached counter values (S.inc was built at the class change; the
         // reductions in between contain __syncthreads)
         {
-            const uint32_t n_inc = S.inc[SK_MAX_ENT];
+            const uint32_t inc_meta = S.inc[SK_MAX_ENT], n_dom = inc_meta & 0xff, n_all = (inc_meta >> 8) & 0xff;
+            C.aff_total += (inc_meta >> 16) & 0xff;              // node-level required-affinity counters always match the winner's node
+            if (own_thread) {
+                #pragma unroll 1
+                for (uint32_t k = n_dom; k < n_all; k++) VAL(S.inc[k] & 0xff, own_idx) += 1;
+            }
             uint32_t cur_row = 0xffffffffu;
             unsigned long long match = 0;                        // which of this thread's nodes share the winner's domain of cur_row (NPT <= 64)
             #pragma unroll 1
-            for (uint32_t k = 0; k < n_inc; k++) {
+            for (uint32_t k = 0; k < n_dom; k++) {
                 const uint32_t rec = S.inc[k], e = rec & 0xff, trow = (rec >> 8) & 0xff;
                 if (trow != cur_row) {
                     cur_row = trow;
