@@ -175,6 +175,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0, st_fast = 0;
     uint32_t last_win_r = 0xffffffffu;     // scenario rank of the last winner while its class stays current
     bool last_win_ign = false;
+    bool bits_dirty = true;                // the feasibility bits changed since they were loaded from / stored to fbits
     long long tk[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_prev = PROF ? clock64() : 0;
     (void)t_prev;
@@ -473,11 +474,13 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     for (int q = 0; q < SIMON_MAX_TOPOS; q++) rec[17 + q] = (uint32_t)q < T ? S.lastdom[q] : -1;
                     rec[0] = 1;
                 }
-                #pragma unroll 1
-                for (uint32_t s = 0; s < NPT; s++) {
-                    uint32_t idx = s * TPB + tid;
-                    uint8_t nf = A8(C_NFLAGS, idx);
-                    if (nf & NF_VALID) SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = nf & (NF_FEASIBLE | NF_COUNTED);
+                if (bits_dirty) {
+                    #pragma unroll 1
+                    for (uint32_t s = 0; s < NPT; s++) {
+                        uint32_t idx = s * TPB + tid;
+                        uint8_t nf = A8(C_NFLAGS, idx);
+                        if (nf & NF_VALID) SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = nf & (NF_FEASIBLE | NF_COUNTED);
+                    }
                 }
             }
             TICK(10);
@@ -510,6 +513,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             C.have_pred = pred[0] == 1;
             const bool restore = C.have_pred && !C.any_table && SC.fbits;
             last_win_r = 0xffffffffu;
+            bits_dirty = !restore;
             if (restore) {
                 C.F = pred[9]; C.n_ign = pred[10]; C.na_max = pred[11]; C.tt_max = pred[12]; C.simon_max = pred[13]; C.simon_min = pred[14];
                 if (pred[15] >= 0) {
@@ -555,30 +559,26 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 // counter bases of the commit list: fetched once per class switch, not by the committing thread
                 if ((int64_t)e < cw[SCW_N_INC]) S.incb[e] = (uint32_t)P.cnt_off[(cw + cw[SCW_OFF_INC])[3 * e]];
             }
-            cluster.barrier_wait();
-            TICK(13);
             // ---- node-static verdicts: from the per-(static signature, node) cache, or computed and cached ----
-            // All long-latency loads of up to 4 nodes (cache record, Simon row, first 4 counter values each) are issued
-            // back to back before any of them is consumed: the class switch costs ~one memory round trip.
+            // All long-latency loads of up to 4 nodes (cache records, Simon row, first 4 counter values each) are issued back
+            // to back before any of them is consumed.  The loads that do not depend on the counters (everything but the
+            // counter values) of the first batch are issued BEFORE the cluster barrier is awaited.
             const int64_t sig = cw[SCW_STATIC_SIG];
             const int64_t *tol = cw + cw[SCW_OFF_TOL];
             const int64_t *simon_row = P.simon_raw + (uint64_t)cw[SCW_STATIC_ROW] * P.NC;
             const int32_t *extra = cw[SCW_EXTRA_ROW] >= 0 ? P.extra_score + (uint64_t)cw[SCW_EXTRA_ROW] * N : nullptr;
-            #pragma unroll 1
-            for (uint32_t s0 = 0; s0 < NPT; s0 += 4) {
-                unsigned long long rec4[4];
-                long long sim4[4];
-                int32_t v4[4][4], ex4[4];
-                uint8_t fb4[4];
-                unsigned long long oc4[4];
+            unsigned long long rec4[4];
+            long long sim4[4];
+            int32_t ex4[4];
+            uint8_t fb4[4];
+            unsigned long long oc4[4];
+            auto prefetch_static = [&](uint32_t s0) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     uint32_t s = s0 + u;
                     uint32_t idx = s * TPB + tid;
                     bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
                     rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000; fb4[u] = 0; oc4[u] = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; e++) v4[u][e] = 0;
                     if (valid) {
                         uint32_t g = (uint32_t)A32(B_NODE_G, idx);
                         if (P.use_scache) rec4[u] = __ldcg(&P.scache[(uint64_t)sig * N + g]);
@@ -586,6 +586,25 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         if (extra) ex4[u] = __ldg(&extra[g]);
                         if (restore) fb4[u] = __ldcg(&SC.fbits[(uint64_t)cls * N + g]);
                         if (SC.ocache) oc4[u] = __ldcg(&SC.ocache[(uint64_t)cls * N + g]);
+                    }
+                }
+            };
+            prefetch_static(0);
+            cluster.barrier_wait();
+            TICK(13);
+            #pragma unroll 1
+            for (uint32_t s0 = 0; s0 < NPT; s0 += 4) {
+                int32_t v4[4][4];
+                if (s0 > 0) prefetch_static(s0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t s = s0 + u;
+                    uint32_t idx = s * TPB + tid;
+                    bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) v4[u][e] = 0;
+                    if (valid) {
+                        uint32_t g = (uint32_t)A32(B_NODE_G, idx);
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                             if ((uint32_t)e < C.E) {
@@ -804,6 +823,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             sk_allreduce_w<7>(R, pv, pop);
             pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]); ipa_min = w_dec(pv[2]); ipa_max = w_dec(pv[3]);
             if (pv[4] & 1u) {
+                bits_dirty = true;
                 // some node flipped.  The hostname-topology sizes (= counted nodes) follow from the net change at once.
                 C.sum_valid = false; st_redo++;
                 const int32_t dc = (int32_t)pv[5];
