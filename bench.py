@@ -234,11 +234,11 @@ def main():
     e2e_value = world * D * len(e2e_times) / float(te.item())
     placed = int((out_node >= 0).sum())
 
-    # ---- batch of independent what-if replicas on ONE GPU: one 16-CTA cluster each; a cluster lives inside one GPC and
-    # a B200 has 8 GPCs, so 8 scenarios are co-resident (a 9th would wait for a second wave) ----
+    # ---- batch of independent what-if replicas on ONE GPU: one 16-CTA cluster each.  A cluster lives inside one GPC; on this
+    # part 7 such clusters are co-resident (tools/batch_scale.py: 1..7 scenarios take the same time, the 8th starts a second wave) ----
     batch = None
     if not args.no_batch:
-        nb = 8
+        nb = 7
         act = np.arange(int(c.n_nodes), dtype=np.uint32)
         eng.run_scenarios([act] * nb)                                   # warm-up
         flush.zero_()
@@ -247,7 +247,7 @@ def main():
         bms = eng.last_kernel_ms()
         same = all(r["n_scheduled"] == placed - (P - D) or r["n_scheduled"] == placed for r in res)
         batch = {"scenarios": nb, "value": nb * D / (bms * 1e-3), "unit": "decisions/s", "ms": bms, "identical_counts": bool(same),
-                 "note": "simon_scenarios_run: 8 independent replicas of the same workload placed concurrently on one GPU "
+                 "note": "simon_scenarios_run: 7 independent replicas of the same workload placed concurrently on one GPU "
                          "(the capacity-planning batch shape); aggregate, not the headline value"}
 
     if rank == 0:
