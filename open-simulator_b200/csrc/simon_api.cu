@@ -18,12 +18,16 @@ namespace {
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
+    // buffers are reused across uploads of the same (or a smaller) shape: cudaFree synchronises the device and
+    // cudaMalloc of the large per-(class, node) caches is slow, both would sit inside every end-to-end call
     cudaError_t alloc(size_t count) {
+        const size_t want = count ? count : 1;
+        if (p && want <= cap) { n = count; return cudaSuccess; }
         release();
         n = count;
-        if (count == 0) count = 1;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        cap = want;
+        return cudaMalloc((void **)&p, want * sizeof(T));
     }
     cudaError_t upload(const T *h, size_t count, cudaStream_t st) {
         cudaError_t e = alloc(count);
@@ -35,6 +39,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        cap = 0;
     }
     ~DevBuf() { release(); }
 };
