@@ -109,3 +109,61 @@ def test_full_size_c3_properties():
     o = Oracle(c)
     ref, _, _, _ = o.schedule(0, first + 3000)
     np.testing.assert_array_equal(out[: first + 3000], ref)
+
+
+def _cmp(c):
+    (ref, rscore, rfc, rfp), rstate = run_oracle(c)
+    with _engine(c) as eng:
+        out, score, fc, fp = eng.schedule()
+        st = eng.state()
+    np.testing.assert_array_equal(out, ref)
+    np.testing.assert_array_equal(fp, rfp)
+    np.testing.assert_array_equal(fc, rfc)
+    for k in rstate:
+        np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
+    return out
+
+
+def test_edge_empty_pod_list():
+    from simon_b200 import simulator, synth
+    from simon_b200.compiler import compile_cluster
+    cluster, apps = synth.make_c2(n_nodes=5, n_workloads=0, replicas=1)
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    assert len(_cmp(c)) == 0
+
+
+def test_edge_single_node_fills_up():
+    p, c = make_case("c2", n_nodes=1, n_workloads=3, replicas=50, seed_no=2)
+    out = _cmp(c)
+    assert (out == 0).sum() > 0 and (out == -1).sum() > 0        # F == 1 short-circuit, then "Insufficient ..." for the rest
+
+
+def test_edge_no_nodes():
+    p, c = make_case("c2", n_nodes=0, n_workloads=2, replicas=2, seed_no=2)
+    out = _cmp(c)
+    assert (out == -1).all()
+
+
+def test_edge_zero_count_and_tail_calls():
+    p, c = make_case("c3", n_nodes=40, n_workloads=10, replicas=4, n_apps=1, seed_no=4)
+    (ref, _, _, _), _ = run_oracle(c)
+    P = c.pods_dims["n_pods"]
+    with _engine(c) as eng:
+        o0 = eng.schedule(0, 0)[0]
+        a = eng.schedule(0, P - 1)[0]
+        b = eng.schedule(P - 1, 1)[0]
+    assert len(o0) == 0
+    np.testing.assert_array_equal(np.concatenate([a, b]), ref)
+
+
+def test_limit_too_many_nodes_is_an_error_not_a_fallback():
+    """A scenario that does not fit one 16-CTA cluster's shared memory is refused with a message (no CPU path)."""
+    from simon_b200 import simulator, synth
+    from simon_b200.compiler import compile_cluster
+    cluster, apps = synth.make_c2(n_nodes=40000, n_workloads=1, replicas=1, seed_no=2)
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    with _engine(c) as eng:
+        with pytest.raises(RuntimeError, match="shared memory|fit"):
+            eng.schedule()
