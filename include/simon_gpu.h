@@ -263,9 +263,12 @@ int simon_results_download(simon_ctx *ctx, uint32_t first, uint32_t count, int32
  * the device; *out_ms_total = device time of the whole sequence (CUDA events on the ctx stream). */
 int simon_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total);
 
-/* Counters of the last single-scenario kernel: out8[0] decisions, [1] pod-class switches, [2] feasible-set summary
- * rebuilds, [3] decisions redone after a feasibility flip, [4] static evaluations; [8..19] SM cycles spent per
- * kernel phase by the leader thread. out32 must hold 32 words. */
+/* Counters of the last single-scenario kernel (out32 must hold 32 words): [0] decisions, [1] pod-class switches,
+ * [2] feasible-set summary rebuilds, [3] decisions that saw a feasibility flip, [4] static evaluations by the leader
+ * thread, [6] flips absorbed by the single-node fast path.  With SIMON_PROFILE=1 in the environment the kernel variants
+ * with clock64 timers run and also fill: [8..23] SM cycles per kernel phase (leader thread), [24..29] cycles and call
+ * counts inside the cluster reductions, [27]/[5] cycles / count of the speculative own-state evaluations,
+ * [30]/[31] cycles / count of the committing thread's commit block.  Diagnostic only: no placement depends on it. */
 int simon_stats(simon_ctx *ctx, uint64_t *out32);
 
 /* Device time (CUDA events on the ctx stream) of the last simon_schedule / simon_scenarios_run kernel, ms. */
