@@ -37,16 +37,26 @@ def lib():
         _LIB.simon_oracle_schedule.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _LIB.simon_oracle_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        _LIB.simon_oracle_set_threads.restype = C.c_int
+        _LIB.simon_oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
     return _LIB
 
 
 class Oracle:
-    def __init__(self, compiled):
+    def __init__(self, compiled, threads: int = 1):
         self.c = compiled
         self.snap, self.pods, self._keep = abi.marshal(compiled)
         self.h = lib().simon_oracle_create(C.byref(self.snap), C.byref(self.pods))
         if not self.h:
             raise MemoryError("simon_oracle_create failed")
+        self.threads = 1
+        if threads > 1:
+            self.set_threads(threads)
+
+    def set_threads(self, n: int) -> int:
+        """Share the per-node loops between n host threads (spin-waiting pool); placements do not depend on n."""
+        self.threads = int(lib().simon_oracle_set_threads(self.h, int(n)))
+        return self.threads
 
     def close(self):
         if self.h:

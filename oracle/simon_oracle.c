@@ -32,16 +32,23 @@
  *   AssumePod / NodeInfo.AddPod            K8S/internal/cache/cache.go:361-380, K8S/framework/types.go:482-508
  *
  * Floating point: IEEE double, no contraction (compile with -ffp-contract=off), truncation by (int64_t) cast.
+ *
+ * Threads: simon_oracle_set_threads(o, n) shares the per-node loops of a cycle between n host threads (pthread pool,
+ * spin-waiting between stages); every cross-node quantity is folded from per-thread partials in node order, so the
+ * placements do not depend on n.  Used by bench.py's CPU legs ("all the host threads it can use").
  */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
+
+#include <pthread.h>
+#include <sched.h>
 
 #include "../include/simon_gpu.h"
+
+struct simon_oracle;
+struct pool_arg { struct simon_oracle *o; int tid; };
 
 typedef struct simon_oracle {
     simon_snapshot s;
@@ -67,6 +74,13 @@ typedef struct simon_oracle {
     uint8_t *dom_flag;
     uint32_t max_dom;
     int threads;
+    /* thread pool (simon_oracle_set_threads) and per-thread scratch tables */
+    uint8_t *t_flag;     /* [threads][16][max_dom] */
+    int64_t *t_tmp;      /* [threads][16][max_dom] */
+    struct sched_ctx *pool_ctx;
+    int pool_gen, pool_done, pool_stop;
+    void *pool_threads;  /* pthread_t[threads-1] */
+    void *pool_args;
     int64_t plugin_dump_enabled;
     int64_t *dump; /* [N][10] optional */
 } simon_oracle;
@@ -197,135 +211,375 @@ static inline int64_t f2i(double x) {
     return (int64_t)x;
 }
 
-static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, uint32_t *fail_hist) {
-    const int64_t *cw = CW(o, cls);
-    const uint32_t N = o->N, NA = o->n_active;
-    const uint32_t K = o->s.n_scalars, WT = o->s.n_taint_words;
-    const uint32_t flags = (uint32_t)cw[SCW_FLAGS];
-    const int64_t *tol = cw + cw[SCW_OFF_TOL];
-    const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
-    const int64_t n_hard = cw[SCW_N_PTS_HARD], n_soft = cw[SCW_N_PTS_SOFT];
-    const int64_t *hard = cw + cw[SCW_OFF_PTS_HARD], *soft = cw + cw[SCW_OFF_PTS_SOFT];
-    const int64_t n_aff = cw[SCW_N_IPA_AFF], n_anti = cw[SCW_N_IPA_ANTI], n_exist = cw[SCW_N_IPA_EXIST];
-    const int64_t *aff = cw + cw[SCW_OFF_IPA_AFF], *anti = cw + cw[SCW_OFF_IPA_ANTI], *exist = cw + cw[SCW_OFF_IPA_EXIST];
-    const int64_t n_isc = cw[SCW_N_IPA_SCORE];
-    const int64_t *isc = cw + cw[SCW_OFF_IPA_SCORE];
-    const int64_t n_ports = cw[SCW_N_PORTS];
-    const int64_t *ports = cw + cw[SCW_OFF_PORTS];
+/* ---- one scheduling cycle, written as stages over ranges of the node order so that the per-node loops can be shared
+ * between threads (simon_oracle_set_threads).  The stages and their order are exactly the serial algorithm; every
+ * cross-node quantity (feasible count, extrema, domain tables, arg-max) is folded from per-thread partials in thread
+ * order, so the result does not depend on the thread count. ---- */
+#define ORACLE_MAX_THREADS 64
+enum { ST_SEL = 0, ST_HARDREG, ST_FILTER, ST_IGN, ST_SOFTREG, ST_SOFTTP, ST_RAW, ST_TOTAL };
 
-    /* ---- node-static part: selection + static filters ---- */
-    for (uint32_t r = 0; r < NA; r++) {
-        uint32_t n = o->order[r];
-        o->sel_ok[n] = (uint8_t)node_selection_ok(o, cw, n);
-    }
+typedef struct {
+    uint32_t F, n_ign;
+    int64_t pts_min, pts_max, na_max, tt_max, simon_min, simon_max, ipa_min, ipa_max;
+    int64_t best, best_n;
+    char pad[64];
+} sched_part;
 
-    /* ---- PodTopologySpread hard constraints: registered domains and global minimum (filtering.go:198-273) ---- */
+typedef struct sched_ctx {
+    simon_oracle *o;
+    const int64_t *cw, *tol, *sc_req, *hard, *soft, *aff, *anti, *exist, *isc, *ports, *simon_row;
+    const int32_t *extra;
+    int64_t n_hard, n_soft, n_aff, n_anti, n_exist, n_isc, n_ports;
+    uint32_t flags, N, NA, K, WT;
     int64_t hard_min[16];
     uint8_t *hard_reg[16];
-    if (n_hard > 16) return -2;
-    for (int64_t j = 0; j < n_hard; j++) {
-        int64_t k = hard[4 * j], t = hard[4 * j + 1];
-        uint32_t nd = o->s.topo_ndom[t];
-        uint8_t *reg = o->dom_flag + (uint64_t)j * o->max_dom;
-        memset(reg, 0, nd);
-        hard_reg[j] = reg;
-        hard_min[j] = INT32_MAX;
-        for (uint32_t r = 0; r < NA; r++) {
+    int64_t aff_total;
+    double soft_w[16];
+    int64_t *soft_cnt[16];
+    int64_t pts_min, pts_max, na_max, tt_max, simon_min, simon_max, ipa_min, ipa_max, simon_range, ipa_diff;
+    int j;                       /* constraint index of the table stages */
+    int stage;
+    sched_part part[ORACLE_MAX_THREADS];
+} sched_ctx;
+
+static void stage_run(sched_ctx *c, uint32_t r0, uint32_t r1, int tid) {
+    simon_oracle *o = c->o;
+    const int64_t *cw = c->cw;
+    const uint32_t N = c->N;
+    sched_part *pt = &c->part[tid];
+    switch (c->stage) {
+    case ST_SEL:
+        for (uint32_t r = r0; r < r1; r++) { uint32_t n = o->order[r]; o->sel_ok[n] = (uint8_t)node_selection_ok(o, cw, n); }
+        break;
+    case ST_HARDREG: {   /* registered domains of hard constraint j, per-thread table (filtering.go:221-243) */
+        uint8_t *reg = o->t_flag + ((uint64_t)tid * 16 + c->j) * o->max_dom;
+        memset(reg, 0, o->s.topo_ndom[c->hard[4 * c->j + 1]]);
+        for (uint32_t r = r0; r < r1; r++) {
             uint32_t n = o->order[r];
             if (!o->sel_ok[n]) continue;
             int all = 1;
-            for (int64_t jj = 0; jj < n_hard; jj++)
-                if (dom_of(o, hard[4 * jj + 1], n) < 0) all = 0;
-            if (!all) continue;
+            for (int64_t jj = 0; jj < c->n_hard; jj++)
+                if (dom_of(o, c->hard[4 * jj + 1], n) < 0) all = 0;
+            if (all) reg[dom_of(o, c->hard[4 * c->j + 1], n)] = 1;
+        }
+        break;
+    }
+    case ST_FILTER: {
+        uint32_t F = 0;
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t n = o->order[r];
+            uint32_t reasons = 0;
+            int32_t code = 0;
+            /* 1 NodeUnschedulable, 2 NodeName, 3 TaintToleration, 4 NodeAffinity */
+            if ((o->s.node_flags[n] & SIMON_NODE_UNSCHEDULABLE) && !(c->flags & SIMON_CLS_TOL_UNSCHED)) code = 1;
+            if (!code && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)n) code = 2;
+            if (!code) {
+                for (uint32_t w = 0; w < c->WT; w++)
+                    if (o->s.taint_hard[(uint64_t)w * N + n] & ~(uint64_t)c->tol[w]) code = 3;
+            }
+            if (!code && !o->sel_ok[n]) code = 4;
+            if (code) reasons |= 1u << SFC_STATIC;
+            /* 5 NodePorts */
+            if (!code) {
+                for (int64_t j = 0; j < c->n_ports; j++)
+                    if (cnt_at(o, c->ports[j], (int32_t)n) > 0) { code = 5; reasons |= 1u << SFC_PORTS; }
+            }
+            /* 6 NodeResourcesFit */
+            if (!code) {
+                if (o->num_pods[n] + 1 > o->s.alloc_pods[n]) reasons |= 1u << SFC_TOO_MANY_PODS;
+                if (c->flags & SIMON_CLS_HAS_REQUEST) {
+                    if (o->s.alloc_mcpu[n] < cw[SCW_REQ_MCPU] + o->req_mcpu[n]) reasons |= 1u << SFC_CPU;
+                    if (o->s.alloc_mem[n] < cw[SCW_REQ_MEM] + o->req_mem[n]) reasons |= 1u << SFC_MEM;
+                    if (o->s.alloc_eph[n] < cw[SCW_REQ_EPH] + o->req_eph[n]) reasons |= 1u << SFC_EPH;
+                    for (uint32_t k = 0; k < c->K; k++)
+                        if (c->sc_req[k] != 0 &&
+                            o->s.alloc_scalar[(uint64_t)k * N + n] < c->sc_req[k] + o->req_scalar[(uint64_t)k * N + n])
+                            reasons |= 1u << (SFC_SCALAR0 + k);
+                }
+                if (reasons) code = 6;
+            }
+            /* 14 PodTopologySpread (hard) */
+            if (!code) {
+                for (int64_t j = 0; j < c->n_hard && !code; j++) {
+                    int64_t k = c->hard[4 * j], t = c->hard[4 * j + 1], skew_max = c->hard[4 * j + 2], self = c->hard[4 * j + 3];
+                    int32_t d = dom_of(o, t, n);
+                    if (d < 0) { code = 14; reasons |= 1u << SFC_PTS_MISSING; break; }
+                    int64_t match = c->hard_reg[j][d] ? cnt_at(o, k, d) : 0;
+                    int64_t skew = match + self - c->hard_min[j];
+                    if (skew > skew_max) { code = 14; reasons |= 1u << SFC_PTS_SKEW; }
+                }
+            }
+            /* 15 InterPodAffinity */
+            if (!code && c->n_aff > 0) {
+                int pods_exist = 1, missing = 0;
+                for (int64_t j = 0; j < c->n_aff; j++) {
+                    int32_t d = dom_of(o, c->aff[2 * j + 1], n);
+                    if (d < 0) { missing = 1; break; }
+                    if (cnt_at(o, c->aff[2 * j], d) <= 0) pods_exist = 0;
+                }
+                int ok = 1;
+                if (missing) ok = 0;
+                else if (!pods_exist) ok = (c->aff_total == 0 && (c->flags & SIMON_CLS_IPA_SELF_MATCH)) ? 1 : 0;
+                if (!ok) { code = 15; reasons |= 1u << SFC_IPA_AFF; }
+            }
+            if (!code) {
+                for (int64_t j = 0; j < c->n_anti; j++) {
+                    int32_t d = dom_of(o, c->anti[2 * j + 1], n);
+                    if (d >= 0 && cnt_at(o, c->anti[2 * j], d) > 0) { code = 15; reasons |= 1u << SFC_IPA_ANTI; break; }
+                }
+            }
+            if (!code) {
+                for (int64_t j = 0; j < c->n_exist; j++) {
+                    int32_t d = dom_of(o, c->exist[2 * j + 1], n);
+                    if (d >= 0 && cnt_at(o, c->exist[2 * j], d) > 0) { code = 15; reasons |= 1u << SFC_IPA_EXIST; break; }
+                }
+            }
+            /* 17 Open-Gpu-Share */
+            if (!code && cw[SCW_GPU_MEM] > 0) {
+                int slots[64];
+                int64_t total = o->s.gpu_total_mem ? o->s.gpu_total_mem[n] : 0;
+                if (total < cw[SCW_GPU_MEM] || gpu_allocate(o, cw, n, slots) == 0) { code = 17; reasons |= 1u << SFC_GPU; }
+            }
+            o->code[n] = code;
+            o->reasons[n] = reasons;
+            if (!code) F++;
+        }
+        pt->F = F;
+        break;
+    }
+    case ST_IGN: {
+        uint32_t n_ign = 0;
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t n = o->order[r];
+            o->ignored[n] = 0;
+            if (o->code[n]) continue;
+            for (int64_t j = 0; j < c->n_soft; j++)
+                if (dom_of(o, c->soft[5 * j + 1], n) < 0) o->ignored[n] = 1;
+            if (o->ignored[n]) n_ign++;
+        }
+        pt->n_ign = n_ign;
+        break;
+    }
+    case ST_SOFTREG: {   /* domains of soft constraint j present among the counted nodes (scoring.go:85-99) */
+        int64_t t = c->soft[5 * c->j + 1];
+        uint8_t *reg = o->t_flag + ((uint64_t)tid * 16 + c->j) * o->max_dom;
+        memset(reg, 0, o->s.topo_ndom[t]);
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t n = o->order[r];
+            if (o->code[n] || o->ignored[n]) continue;
             reg[dom_of(o, t, n)] = 1;
         }
+        break;
+    }
+    case ST_SOFTTP: {    /* matching pods per registered domain (scoring.go:140-166), per-thread partial sums */
+        int64_t k = c->soft[5 * c->j], t = c->soft[5 * c->j + 1];
+        const uint8_t *reg = o->dom_flag + (uint64_t)c->j * o->max_dom;
+        int64_t *tp = o->t_tmp + ((uint64_t)tid * 16 + c->j) * o->max_dom;
+        memset(tp, 0, sizeof(int64_t) * o->s.topo_ndom[t]);
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t n = o->order[r];
+            if (!o->sel_ok[n]) continue;
+            int all = 1;
+            for (int64_t jj = 0; jj < c->n_soft; jj++)
+                if (dom_of(o, c->soft[5 * jj + 1], n) < 0) all = 0;
+            if (!all) continue;
+            int32_t d = dom_of(o, t, n);
+            if (reg[d]) tp[d] += cnt_at(o, k, (int32_t)n);
+        }
+        break;
+    }
+    case ST_RAW: {
+        int64_t pts_min = INT64_MAX, pts_max = 0;
+        int64_t na_max = 0, tt_max = 0, simon_min = INT64_MAX, simon_max = -INT64_MAX, ipa_min = 0, ipa_max = 0;
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t n = o->order[r];
+            if (o->code[n]) continue;
+            /* PTS raw */
+            int64_t raw = 0;
+            if (!o->ignored[n] && c->n_soft > 0) {
+                double score = 0.0;
+                for (int64_t j = 0; j < c->n_soft; j++) {
+                    int64_t k = c->soft[5 * j], t = c->soft[5 * j + 1], ms = c->soft[5 * j + 2], is_host = c->soft[5 * j + 3];
+                    int64_t cc = is_host ? (int64_t)cnt_at(o, k, (int32_t)n) : c->soft_cnt[j][dom_of(o, t, n)];
+                    double sfc = (double)cc * c->soft_w[j] + (double)(ms - 1);
+                    score = score + sfc;
+                }
+                raw = f2i(score);
+            }
+            o->raw_pts[n] = raw;
+            if (!o->ignored[n]) {
+                if (raw < pts_min) pts_min = raw;
+                if (raw > pts_max) pts_max = raw;
+            }
+            /* NodeAffinity preferred, TaintToleration */
+            int64_t na = pref_score(o, cw, n);
+            o->raw_na[n] = na;
+            if (na > na_max) na_max = na;
+            int64_t tt = 0;
+            for (uint32_t w = 0; w < c->WT; w++)
+                tt += __builtin_popcountll(o->s.taint_soft[(uint64_t)w * N + n] & ~(uint64_t)c->tol[c->WT + w]);
+            o->raw_tt[n] = tt;
+            if (tt > tt_max) tt_max = tt;
+            /* Simon */
+            int64_t sr = c->simon_row[o->s.node_class[n]];
+            o->raw_simon[n] = sr;
+            if (sr > simon_max) simon_max = sr;
+            if (sr < simon_min) simon_min = sr;
+            /* InterPodAffinity raw */
+            int64_t ip = 0;
+            for (int64_t j = 0; j < c->n_isc; j++) {
+                int32_t d = dom_of(o, c->isc[3 * j + 1], n);
+                if (d >= 0) ip += c->isc[3 * j + 2] * (int64_t)cnt_at(o, c->isc[3 * j], d);
+            }
+            o->raw_ipa[n] = ip;
+            if (ip > ipa_max) ipa_max = ip;
+            if (ip < ipa_min) ipa_min = ip;
+        }
+        pt->pts_min = pts_min; pt->pts_max = pts_max; pt->na_max = na_max; pt->tt_max = tt_max;
+        pt->simon_min = simon_min; pt->simon_max = simon_max; pt->ipa_min = ipa_min; pt->ipa_max = ipa_max;
+        break;
+    }
+    case ST_TOTAL: {
+        int64_t best = INT64_MIN, best_n = -1;
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t n = o->order[r];
+            if (o->code[n]) continue;
+            /* LeastAllocated */
+            int64_t la = 0;
+            {
+                int64_t cap = o->s.alloc_mcpu[n], rq = o->nz_mcpu[n] + cw[SCW_SCORE_MCPU];
+                int64_t s1 = (cap == 0 || rq > cap) ? 0 : ((cap - rq) * 100) / cap;
+                cap = o->s.alloc_mem[n]; rq = o->nz_mem[n] + cw[SCW_SCORE_MEM];
+                int64_t s2 = (cap == 0 || rq > cap) ? 0 : ((cap - rq) * 100) / cap;
+                la = (s1 + s2) / 2;
+            }
+            /* BalancedAllocation */
+            int64_t ba = 0;
+            {
+                int64_t capc = o->s.alloc_mcpu[n], rqc = o->nz_mcpu[n] + cw[SCW_SCORE_MCPU];
+                int64_t capm = o->s.alloc_mem[n], rqm = o->nz_mem[n] + cw[SCW_SCORE_MEM];
+                double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
+                double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
+                if (cf >= 1.0 || mf >= 1.0) ba = 0;
+                else {
+                    double diff = fabs(cf - mf);
+                    ba = f2i((1.0 - diff) * 100.0);
+                }
+            }
+            int64_t na = c->na_max == 0 ? o->raw_na[n] : (100 * o->raw_na[n]) / c->na_max;
+            int64_t tt = c->tt_max == 0 ? 100 : 100 - (100 * o->raw_tt[n]) / c->tt_max;
+            int64_t sm = c->simon_range == 0 ? 0 : ((o->raw_simon[n] - c->simon_min) * 100) / c->simon_range;
+            int64_t ip = 0;
+            if (c->ipa_diff > 0) ip = f2i(100.0 * ((double)(o->raw_ipa[n] - c->ipa_min) / (double)c->ipa_diff));
+            int64_t pts;
+            if (o->ignored[n]) pts = 0;
+            else if (c->pts_max == 0) pts = 100;
+            else pts = (100 * (c->pts_max + c->pts_min - o->raw_pts[n])) / c->pts_max;
+            int64_t ex = c->extra ? (int64_t)c->extra[n] : 1000000;
+            int64_t total = ba + la + ip + na + 2 * pts + tt + 2 * sm + ex;
+            o->total[n] = total;
+            if (o->dump) {
+                int64_t *dd = o->dump + (uint64_t)n * 10;
+                dd[0] = ba; dd[1] = la; dd[2] = ip; dd[3] = na; dd[4] = pts; dd[5] = tt; dd[6] = sm; dd[7] = ex; dd[8] = total; dd[9] = 0;
+            }
+            if (total > best) { best = total; best_n = (int64_t)n; }
+        }
+        pt->best = best; pt->best_n = best_n;
+        break;
+    }
+    }
+}
+
+/* contiguous chunk of the node order for thread tid: chunks in thread order = the serial order */
+static void chunk_of(const sched_ctx *c, int T, int tid, uint32_t *r0, uint32_t *r1) {
+    *r0 = (uint32_t)((uint64_t)c->NA * (uint64_t)tid / (uint64_t)T);
+    *r1 = (uint32_t)((uint64_t)c->NA * (uint64_t)(tid + 1) / (uint64_t)T);
+}
+
+static void *pool_worker(void *arg) {
+    struct pool_arg *pa = (struct pool_arg *)arg;
+    simon_oracle *o = pa->o;
+    const int tid = pa->tid;
+    int last = 0;
+    for (;;) {
+        int g;
+        unsigned spins = 0;
+        while ((g = __atomic_load_n(&o->pool_gen, __ATOMIC_ACQUIRE)) == last) {
+            if (++spins > 20000) { sched_yield(); spins = 0; }
+            else __builtin_ia32_pause();
+        }
+        last = g;
+        if (o->pool_stop) break;
+        uint32_t r0, r1;
+        chunk_of(o->pool_ctx, o->threads, tid, &r0, &r1);
+        stage_run(o->pool_ctx, r0, r1, tid);
+        __atomic_fetch_add(&o->pool_done, 1, __ATOMIC_RELEASE);
+    }
+    return NULL;
+}
+
+static void run_stage(sched_ctx *c, int stage) {
+    simon_oracle *o = c->o;
+    c->stage = stage;
+    const int T = o->threads;
+    if (T <= 1) { stage_run(c, 0, c->NA, 0); return; }
+    o->pool_ctx = c;
+    __atomic_store_n(&o->pool_done, 0, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&o->pool_gen, 1, __ATOMIC_RELEASE);
+    uint32_t r0, r1;
+    chunk_of(c, T, 0, &r0, &r1);
+    stage_run(c, r0, r1, 0);
+    while (__atomic_load_n(&o->pool_done, __ATOMIC_ACQUIRE) != T - 1) __builtin_ia32_pause();
+}
+
+static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, uint32_t *fail_hist) {
+    sched_ctx ctx;
+    sched_ctx *c = &ctx;
+    const int64_t *cw = CW(o, cls);
+    const int T = o->threads > 1 ? o->threads : 1;
+    c->o = o; c->cw = cw;
+    c->N = o->N; c->NA = o->n_active; c->K = o->s.n_scalars; c->WT = o->s.n_taint_words;
+    c->flags = (uint32_t)cw[SCW_FLAGS];
+    c->tol = cw + cw[SCW_OFF_TOL];
+    c->sc_req = cw + cw[SCW_OFF_SCALARS];
+    c->n_hard = cw[SCW_N_PTS_HARD]; c->n_soft = cw[SCW_N_PTS_SOFT];
+    c->hard = cw + cw[SCW_OFF_PTS_HARD]; c->soft = cw + cw[SCW_OFF_PTS_SOFT];
+    c->n_aff = cw[SCW_N_IPA_AFF]; c->n_anti = cw[SCW_N_IPA_ANTI]; c->n_exist = cw[SCW_N_IPA_EXIST];
+    c->aff = cw + cw[SCW_OFF_IPA_AFF]; c->anti = cw + cw[SCW_OFF_IPA_ANTI]; c->exist = cw + cw[SCW_OFF_IPA_EXIST];
+    c->n_isc = cw[SCW_N_IPA_SCORE]; c->isc = cw + cw[SCW_OFF_IPA_SCORE];
+    c->n_ports = cw[SCW_N_PORTS]; c->ports = cw + cw[SCW_OFF_PORTS];
+    const uint32_t NA = c->NA;
+    const int64_t n_hard = c->n_hard, n_soft = c->n_soft;
+    if (n_hard > 16 || n_soft > 16) return -2;
+
+    /* ---- node-static part: selection + static filters ---- */
+    run_stage(c, ST_SEL);
+
+    /* ---- PodTopologySpread hard constraints: registered domains and global minimum (filtering.go:198-273) ---- */
+    for (int64_t j = 0; j < n_hard; j++) {
+        int64_t k = c->hard[4 * j], t = c->hard[4 * j + 1];
+        uint32_t nd = o->s.topo_ndom[t];
+        uint8_t *reg = o->dom_flag + (uint64_t)j * o->max_dom;
+        c->j = (int)j;
+        run_stage(c, ST_HARDREG);
+        memset(reg, 0, nd);
+        for (int t2 = 0; t2 < T; t2++) {
+            const uint8_t *pr = o->t_flag + ((uint64_t)t2 * 16 + j) * o->max_dom;
+            for (uint32_t d = 0; d < nd; d++) reg[d] |= pr[d];
+        }
+        c->hard_reg[j] = reg;
+        c->hard_min[j] = INT32_MAX;
         for (uint32_t d = 0; d < nd; d++)
-            if (reg[d] && cnt_at(o, k, (int32_t)d) < hard_min[j]) hard_min[j] = cnt_at(o, k, (int32_t)d);
+            if (reg[d] && cnt_at(o, k, (int32_t)d) < c->hard_min[j]) c->hard_min[j] = cnt_at(o, k, (int32_t)d);
     }
     /* InterPodAffinity: is the incoming-affinity map empty? (filtering.go:361-372) */
-    int64_t aff_total = 0;
-    for (int64_t j = 0; j < n_aff; j++) aff_total += o->cnt_total[aff[2 * j]];
+    c->aff_total = 0;
+    for (int64_t j = 0; j < c->n_aff; j++) c->aff_total += o->cnt_total[c->aff[2 * j]];
 
     /* ---- filters ---- */
+    run_stage(c, ST_FILTER);
     uint32_t F = 0;
-    for (uint32_t r = 0; r < NA; r++) {
-        uint32_t n = o->order[r];
-        uint32_t reasons = 0;
-        int32_t code = 0;
-        /* 1 NodeUnschedulable, 2 NodeName, 3 TaintToleration, 4 NodeAffinity */
-        if ((o->s.node_flags[n] & SIMON_NODE_UNSCHEDULABLE) && !(flags & SIMON_CLS_TOL_UNSCHED)) code = 1;
-        if (!code && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)n) code = 2;
-        if (!code) {
-            for (uint32_t w = 0; w < WT; w++)
-                if (o->s.taint_hard[(uint64_t)w * N + n] & ~(uint64_t)tol[w]) code = 3;
-        }
-        if (!code && !o->sel_ok[n]) code = 4;
-        if (code) reasons |= 1u << SFC_STATIC;
-        /* 5 NodePorts */
-        if (!code) {
-            for (int64_t j = 0; j < n_ports; j++)
-                if (cnt_at(o, ports[j], (int32_t)n) > 0) { code = 5; reasons |= 1u << SFC_PORTS; }
-        }
-        /* 6 NodeResourcesFit */
-        if (!code) {
-            if (o->num_pods[n] + 1 > o->s.alloc_pods[n]) reasons |= 1u << SFC_TOO_MANY_PODS;
-            if (flags & SIMON_CLS_HAS_REQUEST) {
-                if (o->s.alloc_mcpu[n] < cw[SCW_REQ_MCPU] + o->req_mcpu[n]) reasons |= 1u << SFC_CPU;
-                if (o->s.alloc_mem[n] < cw[SCW_REQ_MEM] + o->req_mem[n]) reasons |= 1u << SFC_MEM;
-                if (o->s.alloc_eph[n] < cw[SCW_REQ_EPH] + o->req_eph[n]) reasons |= 1u << SFC_EPH;
-                for (uint32_t k = 0; k < K; k++)
-                    if (sc_req[k] != 0 &&
-                        o->s.alloc_scalar[(uint64_t)k * N + n] < sc_req[k] + o->req_scalar[(uint64_t)k * N + n])
-                        reasons |= 1u << (SFC_SCALAR0 + k);
-            }
-            if (reasons) code = 6;
-        }
-        /* 14 PodTopologySpread (hard) */
-        if (!code) {
-            for (int64_t j = 0; j < n_hard && !code; j++) {
-                int64_t k = hard[4 * j], t = hard[4 * j + 1], skew_max = hard[4 * j + 2], self = hard[4 * j + 3];
-                int32_t d = dom_of(o, t, n);
-                if (d < 0) { code = 14; reasons |= 1u << SFC_PTS_MISSING; break; }
-                int64_t match = hard_reg[j][d] ? cnt_at(o, k, d) : 0;
-                int64_t skew = match + self - hard_min[j];
-                if (skew > skew_max) { code = 14; reasons |= 1u << SFC_PTS_SKEW; }
-            }
-        }
-        /* 15 InterPodAffinity */
-        if (!code && n_aff > 0) {
-            int pods_exist = 1, missing = 0;
-            for (int64_t j = 0; j < n_aff; j++) {
-                int32_t d = dom_of(o, aff[2 * j + 1], n);
-                if (d < 0) { missing = 1; break; }
-                if (cnt_at(o, aff[2 * j], d) <= 0) pods_exist = 0;
-            }
-            int ok = 1;
-            if (missing) ok = 0;
-            else if (!pods_exist) ok = (aff_total == 0 && (flags & SIMON_CLS_IPA_SELF_MATCH)) ? 1 : 0;
-            if (!ok) { code = 15; reasons |= 1u << SFC_IPA_AFF; }
-        }
-        if (!code) {
-            for (int64_t j = 0; j < n_anti; j++) {
-                int32_t d = dom_of(o, anti[2 * j + 1], n);
-                if (d >= 0 && cnt_at(o, anti[2 * j], d) > 0) { code = 15; reasons |= 1u << SFC_IPA_ANTI; break; }
-            }
-        }
-        if (!code) {
-            for (int64_t j = 0; j < n_exist; j++) {
-                int32_t d = dom_of(o, exist[2 * j + 1], n);
-                if (d >= 0 && cnt_at(o, exist[2 * j], d) > 0) { code = 15; reasons |= 1u << SFC_IPA_EXIST; break; }
-            }
-        }
-        /* 17 Open-Gpu-Share */
-        if (!code && cw[SCW_GPU_MEM] > 0) {
-            int slots[64];
-            int64_t total = o->s.gpu_total_mem ? o->s.gpu_total_mem[n] : 0;
-            if (total < cw[SCW_GPU_MEM] || gpu_allocate(o, cw, n, slots) == 0) { code = 17; reasons |= 1u << SFC_GPU; }
-        }
-        o->code[n] = code;
-        o->reasons[n] = reasons;
-        if (!code) F++;
-    }
+    for (int t2 = 0; t2 < T; t2++) F += c->part[t2].F;
     if (F == 0) {
         if (fail_hist) {
             memset(fail_hist, 0, sizeof(uint32_t) * SIMON_N_FAIL_CODES);
@@ -345,146 +599,60 @@ static int64_t schedule_one(simon_oracle *o, uint32_t cls, int64_t *out_score, u
 
     /* ---- scores over the feasible set ---- */
     /* PodTopologySpread soft constraints (scoring.go:60-250) */
+    run_stage(c, ST_IGN);
     uint32_t n_ignored = 0;
-    double soft_w[16];
-    int64_t *soft_cnt[16];
-    if (n_soft > 16) return -2;
-    for (uint32_t r = 0; r < NA; r++) {
-        uint32_t n = o->order[r];
-        o->ignored[n] = 0;
-        if (o->code[n]) continue;
-        for (int64_t j = 0; j < n_soft; j++)
-            if (dom_of(o, soft[5 * j + 1], n) < 0) o->ignored[n] = 1;
-        if (o->ignored[n]) n_ignored++;
-    }
+    for (int t2 = 0; t2 < T; t2++) n_ignored += c->part[t2].n_ign;
     for (int64_t j = 0; j < n_soft; j++) {
-        int64_t k = soft[5 * j], t = soft[5 * j + 1], is_host = soft[5 * j + 3];
+        int64_t t = c->soft[5 * j + 1], is_host = c->soft[5 * j + 3];
         int64_t size;
-        soft_cnt[j] = NULL;
+        c->soft_cnt[j] = NULL;
         if (is_host) {
             size = (int64_t)F - (int64_t)n_ignored;
         } else {
             uint32_t nd = o->s.topo_ndom[t];
             uint8_t *reg = o->dom_flag + (uint64_t)j * o->max_dom;
             int64_t *tp = o->dom_tmp + (uint64_t)j * o->max_dom;
+            c->j = (int)j;
+            run_stage(c, ST_SOFTREG);
             memset(reg, 0, nd);
-            memset(tp, 0, sizeof(int64_t) * nd);
             size = 0;
-            for (uint32_t r = 0; r < NA; r++) {
-                uint32_t n = o->order[r];
-                if (o->code[n] || o->ignored[n]) continue;
-                int32_t d = dom_of(o, t, n);
-                if (!reg[d]) { reg[d] = 1; size++; }
+            for (int t2 = 0; t2 < T; t2++) {
+                const uint8_t *pr = o->t_flag + ((uint64_t)t2 * 16 + j) * o->max_dom;
+                for (uint32_t d = 0; d < nd; d++) reg[d] |= pr[d];
             }
-            for (uint32_t r = 0; r < NA; r++) {
-                uint32_t n = o->order[r];
-                if (!o->sel_ok[n]) continue;
-                int all = 1;
-                for (int64_t jj = 0; jj < n_soft; jj++)
-                    if (dom_of(o, soft[5 * jj + 1], n) < 0) all = 0;
-                if (!all) continue;
-                int32_t d = dom_of(o, t, n);
-                if (reg[d]) tp[d] += cnt_at(o, k, (int32_t)n);
+            for (uint32_t d = 0; d < nd; d++) size += reg[d];
+            run_stage(c, ST_SOFTTP);
+            memset(tp, 0, sizeof(int64_t) * nd);
+            for (int t2 = 0; t2 < T; t2++) {
+                const int64_t *pp = o->t_tmp + ((uint64_t)t2 * 16 + j) * o->max_dom;
+                for (uint32_t d = 0; d < nd; d++) tp[d] += pp[d];
             }
-            soft_cnt[j] = tp;
+            c->soft_cnt[j] = tp;
         }
-        soft_w[j] = o->s.log_table[size + 2];
+        c->soft_w[j] = o->s.log_table[size + 2];
     }
-    int64_t pts_min = INT64_MAX, pts_max = 0;
-    int64_t na_max = 0, tt_max = 0, simon_min = INT64_MAX, simon_max = -INT64_MAX, ipa_min = 0, ipa_max = 0;
-    const int64_t *simon_row = o->p.simon_raw + (uint64_t)cw[SCW_STATIC_ROW] * o->s.n_node_classes;
-    for (uint32_t r = 0; r < NA; r++) {
-        uint32_t n = o->order[r];
-        if (o->code[n]) continue;
-        /* PTS raw */
-        int64_t raw = 0;
-        if (!o->ignored[n] && n_soft > 0) {
-            double score = 0.0;
-            for (int64_t j = 0; j < n_soft; j++) {
-                int64_t k = soft[5 * j], t = soft[5 * j + 1], ms = soft[5 * j + 2], is_host = soft[5 * j + 3];
-                int64_t c = is_host ? (int64_t)cnt_at(o, k, (int32_t)n) : soft_cnt[j][dom_of(o, t, n)];
-                double sfc = (double)c * soft_w[j] + (double)(ms - 1);
-                score = score + sfc;
-            }
-            raw = f2i(score);
-        }
-        o->raw_pts[n] = raw;
-        if (!o->ignored[n]) {
-            if (raw < pts_min) pts_min = raw;
-            if (raw > pts_max) pts_max = raw;
-        }
-        /* NodeAffinity preferred, TaintToleration */
-        int64_t na = pref_score(o, cw, n);
-        o->raw_na[n] = na;
-        if (na > na_max) na_max = na;
-        int64_t tt = 0;
-        for (uint32_t w = 0; w < WT; w++)
-            tt += __builtin_popcountll(o->s.taint_soft[(uint64_t)w * N + n] & ~(uint64_t)tol[WT + w]);
-        o->raw_tt[n] = tt;
-        if (tt > tt_max) tt_max = tt;
-        /* Simon */
-        int64_t sr = simon_row[o->s.node_class[n]];
-        o->raw_simon[n] = sr;
-        if (sr > simon_max) simon_max = sr;
-        if (sr < simon_min) simon_min = sr;
-        /* InterPodAffinity raw */
-        int64_t ip = 0;
-        for (int64_t j = 0; j < n_isc; j++) {
-            int32_t d = dom_of(o, isc[3 * j + 1], n);
-            if (d >= 0) ip += isc[3 * j + 2] * (int64_t)cnt_at(o, isc[3 * j], d);
-        }
-        o->raw_ipa[n] = ip;
-        if (ip > ipa_max) ipa_max = ip;
-        if (ip < ipa_min) ipa_min = ip;
+    c->simon_row = o->p.simon_raw + (uint64_t)cw[SCW_STATIC_ROW] * o->s.n_node_classes;
+    run_stage(c, ST_RAW);
+    c->pts_min = INT64_MAX; c->pts_max = 0; c->na_max = 0; c->tt_max = 0;
+    c->simon_min = INT64_MAX; c->simon_max = -INT64_MAX; c->ipa_min = 0; c->ipa_max = 0;
+    for (int t2 = 0; t2 < T; t2++) {
+        const sched_part *pt = &c->part[t2];
+        if (pt->pts_min < c->pts_min) c->pts_min = pt->pts_min;
+        if (pt->pts_max > c->pts_max) c->pts_max = pt->pts_max;
+        if (pt->na_max > c->na_max) c->na_max = pt->na_max;
+        if (pt->tt_max > c->tt_max) c->tt_max = pt->tt_max;
+        if (pt->simon_min < c->simon_min) c->simon_min = pt->simon_min;
+        if (pt->simon_max > c->simon_max) c->simon_max = pt->simon_max;
+        if (pt->ipa_min < c->ipa_min) c->ipa_min = pt->ipa_min;
+        if (pt->ipa_max > c->ipa_max) c->ipa_max = pt->ipa_max;
     }
-    int64_t best = INT64_MIN;
-    int64_t best_n = -1;
-    const int64_t simon_range = simon_max - simon_min;
-    const int64_t ipa_diff = ipa_max - ipa_min;
-    const int32_t *extra = cw[SCW_EXTRA_ROW] >= 0 ? o->p.extra_score + (uint64_t)cw[SCW_EXTRA_ROW] * N : NULL;
-    for (uint32_t r = 0; r < NA; r++) {
-        uint32_t n = o->order[r];
-        if (o->code[n]) continue;
-        /* LeastAllocated */
-        int64_t la = 0;
-        {
-            int64_t cap = o->s.alloc_mcpu[n], rq = o->nz_mcpu[n] + cw[SCW_SCORE_MCPU];
-            int64_t s1 = (cap == 0 || rq > cap) ? 0 : ((cap - rq) * 100) / cap;
-            cap = o->s.alloc_mem[n]; rq = o->nz_mem[n] + cw[SCW_SCORE_MEM];
-            int64_t s2 = (cap == 0 || rq > cap) ? 0 : ((cap - rq) * 100) / cap;
-            la = (s1 + s2) / 2;
-        }
-        /* BalancedAllocation */
-        int64_t ba = 0;
-        {
-            int64_t capc = o->s.alloc_mcpu[n], rqc = o->nz_mcpu[n] + cw[SCW_SCORE_MCPU];
-            int64_t capm = o->s.alloc_mem[n], rqm = o->nz_mem[n] + cw[SCW_SCORE_MEM];
-            double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
-            double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
-            if (cf >= 1.0 || mf >= 1.0) ba = 0;
-            else {
-                double diff = fabs(cf - mf);
-                ba = f2i((1.0 - diff) * 100.0);
-            }
-        }
-        int64_t na = na_max == 0 ? o->raw_na[n] : (100 * o->raw_na[n]) / na_max;
-        int64_t tt = tt_max == 0 ? 100 : 100 - (100 * o->raw_tt[n]) / tt_max;
-        int64_t sm = simon_range == 0 ? 0 : ((o->raw_simon[n] - simon_min) * 100) / simon_range;
-        int64_t ip = 0;
-        if (ipa_diff > 0) ip = f2i(100.0 * ((double)(o->raw_ipa[n] - ipa_min) / (double)ipa_diff));
-        int64_t pts;
-        if (o->ignored[n]) pts = 0;
-        else if (pts_max == 0) pts = 100;
-        else pts = (100 * (pts_max + pts_min - o->raw_pts[n])) / pts_max;
-        int64_t ex = extra ? (int64_t)extra[n] : 1000000;
-        int64_t total = ba + la + ip + na + 2 * pts + tt + 2 * sm + ex;
-        o->total[n] = total;
-        if (o->dump) {
-            int64_t *dd = o->dump + (uint64_t)n * 10;
-            dd[0] = ba; dd[1] = la; dd[2] = ip; dd[3] = na; dd[4] = pts; dd[5] = tt; dd[6] = sm; dd[7] = ex; dd[8] = total; dd[9] = 0;
-        }
-        if (total > best) { best = total; best_n = (int64_t)n; }
-    }
+    c->simon_range = c->simon_max - c->simon_min;
+    c->ipa_diff = c->ipa_max - c->ipa_min;
+    c->extra = cw[SCW_EXTRA_ROW] >= 0 ? o->p.extra_score + (uint64_t)cw[SCW_EXTRA_ROW] * c->N : NULL;
+    run_stage(c, ST_TOTAL);
+    int64_t best = INT64_MIN, best_n = -1;
+    for (int t2 = 0; t2 < T; t2++)      /* chunks are in node order: strictly greater keeps the first maximum */
+        if (c->part[t2].best_n >= 0 && c->part[t2].best > best) { best = c->part[t2].best; best_n = c->part[t2].best_n; }
     if (out_score) *out_score = best;
     return best_n;
 }
@@ -525,11 +693,48 @@ simon_oracle *simon_oracle_create(const simon_snapshot *s, const simon_podset *p
     o->dom_tmp = (int64_t *)calloc((uint64_t)16 * max_dom, 8);
     o->dom_flag = (uint8_t *)calloc((uint64_t)16 * max_dom, 1);
     o->threads = 1;
+    o->t_flag = (uint8_t *)calloc((uint64_t)16 * max_dom, 1);
+    o->t_tmp = (int64_t *)calloc((uint64_t)16 * max_dom, 8);
     return o;
+}
+
+static void pool_shutdown(simon_oracle *o) {
+    if (o->threads > 1 && o->pool_threads) {
+        o->pool_stop = 1;
+        __atomic_fetch_add(&o->pool_gen, 1, __ATOMIC_RELEASE);
+        pthread_t *th = (pthread_t *)o->pool_threads;
+        for (int t = 0; t < o->threads - 1; t++) pthread_join(th[t], NULL);
+    }
+    free(o->pool_threads); free(o->pool_args);
+    o->pool_threads = NULL; o->pool_args = NULL;
+    o->pool_stop = 0;
+    o->threads = 1;
+}
+
+/* Share the per-node loops of every cycle between n threads (1 = serial).  Placements do not depend on n. */
+int simon_oracle_set_threads(simon_oracle *o, int n) {
+    if (n < 1) n = 1;
+    if (n > ORACLE_MAX_THREADS) n = ORACLE_MAX_THREADS;
+    pool_shutdown(o);
+    free(o->t_flag); free(o->t_tmp);
+    o->t_flag = (uint8_t *)calloc((uint64_t)n * 16 * o->max_dom, 1);
+    o->t_tmp = (int64_t *)calloc((uint64_t)n * 16 * o->max_dom, 8);
+    if (n == 1) return 1;
+    pthread_t *th = (pthread_t *)calloc(n - 1, sizeof(pthread_t));
+    struct pool_arg *pa = (struct pool_arg *)calloc(n - 1, sizeof(struct pool_arg));
+    o->pool_threads = th; o->pool_args = pa;
+    o->threads = n;
+    for (int t = 0; t < n - 1; t++) {
+        pa[t].o = o; pa[t].tid = t + 1;
+        if (pthread_create(&th[t], NULL, pool_worker, &pa[t]) != 0) { o->threads = t + 1; break; }
+    }
+    return o->threads;
 }
 
 void simon_oracle_destroy(simon_oracle *o) {
     if (!o) return;
+    pool_shutdown(o);
+    free(o->t_flag); free(o->t_tmp);
     free(o->order); free(o->active); free(o->req_mcpu); free(o->req_mem); free(o->req_eph); free(o->nz_mcpu);
     free(o->nz_mem); free(o->req_scalar); free(o->gpu_used); free(o->num_pods); free(o->cnt_off); free(o->cnt);
     free(o->cnt_total); free(o->code); free(o->reasons); free(o->sel_ok); free(o->ignored); free(o->raw_na);

@@ -34,6 +34,28 @@ def test_c_oracle_matches_pyref_mixed_features(seed):
     assert fc.sum() > 0
 
 
+def test_threaded_oracle_is_thread_count_invariant():
+    """The CPU port may share its per-node loops between host threads (bench.py's reference arm): same placements,
+    scores, failure histograms and final state for any thread count."""
+    from oracle.binding import Oracle
+    for kind, kw in (("c3", dict(n_nodes=500, n_workloads=60, replicas=8, n_apps=2, seed_no=7)),
+                     ("mix", dict(seed_no=209, n_nodes=120, n_workloads=40, max_replicas=7))):
+        p, c = make_case(kind, **kw)
+        ref = Oracle(c)
+        a = ref.schedule()
+        sa = ref.state()
+        for t in (2, 3, 5):
+            o = Oracle(c, threads=t)
+            assert o.threads == t
+            b = o.schedule()
+            sb = o.state()
+            o.close()
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x, y)
+            for k in sa:
+                np.testing.assert_array_equal(sa[k], sb[k])
+
+
 def test_duplicate_taints_are_rejected():
     """A presence bitmask cannot count a taint twice (the reference's score would): such nodes are refused, not mis-scored."""
     from simon_b200 import simulator, synth
