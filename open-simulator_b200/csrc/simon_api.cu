@@ -174,7 +174,7 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.simon_raw = ctx->d_simon_raw.p; P.extra_score = ctx->d_extra.p;
     P.emax = ctx->emax;
     P.stats = ctx->d_stats.p;
-    P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p; P.scache_ready = nullptr;
+    P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p;
 }
 
 #define SIMON_MAX_TPB 320u       // largest compiled variant: 168 registers/thread, no spills (640 threads = 96 registers spilled and measured slower)

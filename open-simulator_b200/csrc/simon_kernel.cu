@@ -3,14 +3,16 @@
 // Per pod class the kernel keeps, per node, in shared memory:
 //   static     : first failing static filter, node-selection / topology-key flags, raw NodeAffinity / TaintToleration /
 //                Simon scores (reloaded from a per-(static signature, node) cache in HBM/L2 filled on first use)
-//   own-state  : NodeResourcesFit verdict and LeastAllocated+BalancedAllocation score  -> recomputed only for the
-//                node that just received a pod
+//   own-state  : NodeResourcesFit verdict and LeastAllocated+BalancedAllocation score: evaluated speculatively for every
+//                warp's best candidate while the arg-max messages travel, so the winner finds its post-placement values
+//                ready; cached per (class, node) in HBM keyed by the node's pod count for later visits of the class
 //   counters   : the value of every constraint/term counter at the node's domain       -> bumped by every thread
 //                from the winner's domain vector that travels with the arg-max
-// and, per class, the summary of the feasible set (F, normaliser inputs, topology sizes).  The spread score of a
-// decision is computed speculatively with the summary predicted from the previous decision / previous visit of
-// the class and verified by the same all-reduce that produces its min/max, so the steady state is two cluster
-// all-reduces per decision: {verify + min/max} and {arg-max}.
+// and, per class, the summary of the feasible set (F, normaliser inputs, topology sizes), stored together with the
+// feasibility bits it is exact for when the class is left and restored on the next visit.  The steady state is two
+// cluster all-reduces per decision, {spread/affinity ranges + flip detection} and {arg-max}; when the only flip is the
+// last winner leaving the feasible set, one more 3-word reduction updates the summary in place; anything else rebuilds
+// it with a 22-word reduction.
 #include "simon_kernel.cuh"
 
 // ---- small helpers --------------------------------------------------------------------------------------
@@ -138,7 +140,7 @@ struct ClassState {
     int64_t aff_total;
     // summary of the feasible set
     bool sum_valid;      // exact for the current feasibility bits
-    bool have_pred;      // soft_sz holds a prediction (previous visit of the class)
+    bool have_pred;      // psz[] holds sizes the weights were computed from (prediction or exact)
     int64_t F, n_ign, na_max, tt_max, simon_min, simon_max;
     int64_t nm_na_max, nm_tt_max, nm_simon_min, nm_simon_max;   // normalisers B_SNORM was computed with
     bool snorm_valid;

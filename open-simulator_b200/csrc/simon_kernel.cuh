@@ -3,7 +3,8 @@
 // One scenario = one thread-block cluster (up to 16 CTAs, DSMEM).  Every node of the scenario is owned by
 // one thread slot for the whole kernel; its static columns, its dynamic NodeInfo aggregates and the values
 // cached for the current pod class live in that CTA's shared memory, so a placement decision touches no
-// global memory on its critical path: filter -> score -> cluster-wide reductions over DSMEM -> argmax -> commit.
+// global memory on its critical path: filter -> score -> cluster-wide reductions over DSMEM (st.async + mbarrier,
+// no barrier.cluster) -> argmax -> commit.
 //
 // Semantics follow oracle/simon_oracle.c line by line (which cites the reference file:line of every
 // plugin); the data layout is include/simon_gpu.h.  Integer work is exact; the float64 plugin formulas use
@@ -100,7 +101,6 @@ struct SkParams {
     uint32_t n_sigs, use_scache;
     uint32_t simon32, pad32;       // simon32: every raw Simon score lies in [0, 2^31) -> reduced as a 32-bit word
     unsigned long long *scache;    // [n_sigs][N] packed {st_code, flags, tt, 0, na:int32}
-    uint32_t *scache_ready;        // [n_sigs]
 };
 
 __host__ __device__ inline size_t sk_align(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -120,7 +120,6 @@ struct SkSmem {
     int32_t *lastdom;    // [SIMON_MAX_TOPOS] topology domains of the last winner (single-node flip fast path)
     uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
-    int32_t *soft_sz;    // [SK_MAX_SOFT] (unused)
     SkScenario *scen;    // this cluster's scenario descriptor
     unsigned long long *mbar;    // [2] mbarriers guarding the two inbox buffers
     uint32_t L, T, nslots;
@@ -135,7 +134,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(8ull * SK_CSUM_W);
-    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(4ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
+    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
 }
@@ -155,7 +154,6 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.lastdom = (int32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.pred = (long long *)p; p += sk_align(8ull * SK_CSUM_W);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
-    S.soft_sz = (int32_t *)p; p += sk_align(4ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
     S.mbar = (unsigned long long *)p;
     S.L = L; S.T = T; S.nslots = nslots;
