@@ -31,7 +31,7 @@ def _dump(tmp_path, **kw):
 
 def _build():
     import __graft_entry__ as g
-    g.build()
+    g.build_client()            # never rebuilds libsimon_gpu.so (it may be loaded in this process)
     assert os.path.exists(CLIENT)
 
 
