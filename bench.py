@@ -264,7 +264,7 @@ def main():
     # ---- batch of independent what-if replicas on ONE GPU: one 16-CTA cluster each.  A cluster lives inside one GPC; on this
     # part 7 such clusters are co-resident (tools/batch_scale.py: 1..7 scenarios take the same time, the 8th starts a second wave) ----
     batch = None
-    if not args.no_batch:
+    if not args.no_batch and world == 1:
         nb = 7
         act = np.arange(int(c.n_nodes), dtype=np.uint32)
         eng.run_scenarios([act] * nb)                                   # warm-up
@@ -292,7 +292,7 @@ def main():
                 "note": f"algorithmic bytes = {ALGO_BYTES_PER_NODE_DECISION} B/node-decision x {args.nodes} nodes x {D} decisions per launch; "
                         "the snapshot is cluster-resident in shared memory, so DRAM traffic << algorithmic bytes"}
         cb = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N = 1 only
             from oracle.binding import Oracle
             first_sched = int(np.argmax(c.pods["pod_fixed_node"] == -1))
             o = Oracle(c, threads=cpu_threads(args, c, first_sched))
