@@ -118,6 +118,9 @@ def _parse_quantity_string(s: str):
     raise QuantityError("quantities must match the regular expression")
 
 
+_PARSE_CACHE: dict = {}      # quantity strings repeat heavily across nodes and pod templates
+
+
 @dataclass
 class Quantity:
     """Either an int64Amount (value * 10^scale) or an inf.Dec (unscaled * 10^-dscale)."""
@@ -143,6 +146,16 @@ class Quantity:
             raise QuantityError("empty quantity")
         if s == "0":
             return Quantity(format=DECIMAL_SI)
+        hit = _PARSE_CACHE.get(s)
+        if hit is not None:
+            return hit.copy()
+        q = Quantity._parse_uncached(s)
+        if len(_PARSE_CACHE) < 65536:
+            _PARSE_CACHE[s] = q.copy()
+        return q
+
+    @staticmethod
+    def _parse_uncached(s: str) -> "Quantity":
         positive, value, num, denom, suf = _parse_quantity_string(s)
         base, exponent, fmt = _interpret_suffix(suf)
         precision = 0
