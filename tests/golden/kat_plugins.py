@@ -1,0 +1,139 @@
+"""Hand-derived known answers for the score plugins (no tool of this repository was used to obtain the expected numbers;
+the derivations below follow the reference's formulas, file:line given, with plain arithmetic).
+
+Common: every node has 4 CPU / 8Gi / 110 pods.  ImageLocality 0 + NodePreferAvoidPods 100 x 10000 = ex 1,000,000.
+total = ba + la + ip + na + 2*pts + tt + 2*sm + ex     (weights: pkg/simulator/utils.go:326-339, registry.go:110-123)
+Simon raw = int64(100 * max_r share(podReq_r, alloc_r - podReq_r)) is the same on all nodes of a case (equal allocatable),
+so its min-max normalisation gives sm = 0 everywhere (simon.go:76-101).
+"""
+
+N = "kubernetes.io/hostname"
+Z = "topology.kubernetes.io/zone"
+
+
+def node(name, labels=None, taints=None):
+    lab = {N: name}
+    lab.update(labels or {})
+    n = {"kind": "Node", "metadata": {"name": name, "labels": lab}, "spec": {},
+         "status": {"allocatable": {"cpu": "4", "memory": "8Gi", "pods": "110"}}}
+    if taints:
+        n["spec"]["taints"] = taints
+    return n
+
+
+def running(name, nodename, labels=None, requests=None, ns="default"):
+    c = {"name": "c", "image": "x"}
+    if requests:
+        c["resources"] = {"requests": requests}
+    return {"kind": "Pod", "metadata": {"name": name, "namespace": ns, "labels": labels or {}},
+            "spec": {"nodeName": nodename, "containers": [c]}}
+
+
+def incoming(spec_extra=None, labels=None, requests=None):
+    c = {"name": "c", "image": "x"}
+    if requests:
+        c["resources"] = {"requests": requests}
+    spec = {"containers": [c]}
+    spec.update(spec_extra or {})
+    return {"kind": "Pod", "metadata": {"name": "incoming", "namespace": "default", "labels": labels or {}}, "spec": spec}
+
+
+CASES = {}
+
+# ---- A: TaintToleration score + preferred NodeAffinity ------------------------------------------------------------
+# n1: 2 PreferNoSchedule taints, labels disk=ssd.  n2: 1 PreferNoSchedule taint, disk=ssd, gpu=yes.  n3: nothing.
+# Pod 1 CPU / 1Gi, no tolerations, preferred node affinity {weight 10: disk In [ssd]; weight 5: gpu Exists}.
+#   TaintToleration (taint_toleration.go:138-157): intolerable PreferNoSchedule taints 2 / 1 / 0, max 2;
+#       reverse normalise 100 - 100*cnt/max  ->  0 / 50 / 100
+#   NodeAffinity (node_affinity.go:77-112): raw 10 / 15 / 0, max 15; 100*raw/max -> 66 (1000/15 = 66.67) / 100 / 0
+#   LeastAllocated (least_allocated.go:93-117): cpu (4000-1000)*100/4000 = 75; mem (8192-1024)*100/8192 = 87.5 -> 87; (75+87)/2 = 81
+#   BalancedAllocation (balanced_allocation.go:82-119): |0.25 - 0.125| = 0.125; (1-0.125)*100 = 87.5 -> 87
+#   PodTopologySpread: no constraints and no Service selects the pod -> 100.  InterPodAffinity 0.
+#   totals: n1 87+81+0+66+200+0+0   = 434 ; n2 87+81+0+100+200+50+0 = 518 ; n3 87+81+0+0+200+100+0 = 468   (+1,000,000)
+CASES["taints_and_preferred_node_affinity"] = {
+    "nodes": [node("n1", {"disk": "ssd"}, [{"key": "t1", "value": "a", "effect": "PreferNoSchedule"},
+                                           {"key": "t2", "value": "b", "effect": "PreferNoSchedule"}]),
+              node("n2", {"disk": "ssd", "gpu": "yes"}, [{"key": "t1", "value": "a", "effect": "PreferNoSchedule"}]),
+              node("n3")],
+    "running": [], "services": [],
+    "pod": incoming({"affinity": {"nodeAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+        {"weight": 10, "preference": {"matchExpressions": [{"key": "disk", "operator": "In", "values": ["ssd"]}]}},
+        {"weight": 5, "preference": {"matchExpressions": [{"key": "gpu", "operator": "Exists"}]}}]}}},
+        requests={"cpu": "1", "memory": "1Gi"}),
+    "expect": {"n1": {"ba": 87, "la": 81, "ip": 0, "na": 66, "pts": 100, "tt": 0, "sm": 0, "ex": 1000000, "total": 1000434},
+               "n2": {"ba": 87, "la": 81, "ip": 0, "na": 100, "pts": 100, "tt": 50, "sm": 0, "ex": 1000000, "total": 1000518},
+               "n3": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000468}},
+    "winner": "n2",
+}
+
+# ---- B: system default PodTopologySpread (a Service selects the pod) ------------------------------------------------
+# zone z1 = {n1, n2}, zone z2 = {n3, n4}.  Running pods with label app=web (100m / 128Mi each): 2 on n1, 1 on n3.
+# Service default/web selects app=web -> default constraints hostname maxSkew 3, zone maxSkew 5, ScheduleAnyway
+# (plugin.go:39-50, helper/spread.go:29-72).  Pod app=web, 500m / 512Mi.
+#   weights (scoring.go:279-281): hostname size = 4 nodes -> ln(4+2) = 1.791759469228055; zone size = 2 -> ln(2+2) = 1.3862943611198906
+#   raw (scoring.go:175-208) = cnt_host*ln6 + (3-1) + cnt_zone*ln4 + (5-1), truncated:
+#       n1: 2*1.791759+2 + 2*1.386294+4 = 12.356  -> 12      n2: 0+2 + 2.772589+4 = 8.77 -> 8
+#       n3: 1.791759+2 + 1.386294+4 = 9.178     -> 9        n4: 0+2 + 1.386294+4 = 7.39 -> 7
+#   normalise (scoring.go:211-250) 100*(max+min-s)/max with min 7, max 12: 58 (700/12) / 91 (1100/12) / 83 (1000/12) / 100
+#   LeastAllocated: n1 cpu (4000-700)*100/4000 = 82.5 -> 82, mem (8192-768)*100/8192 = 90.6 -> 90, (82+90)/2 = 86
+#                   n2 cpu 87.5 -> 87, mem (8192-512)*100/8192 = 93.75 -> 93, 90        n4 = n2
+#                   n3 cpu (4000-600)*100/4000 = 85, mem (8192-640)*100/8192 = 92.19 -> 92, (85+92)/2 = 88.5 -> 88
+#   BalancedAllocation: n1 |0.175-0.09375| = 0.08125 -> 91.875 -> 91 ; n2/n4 |0.125-0.0625| -> 93.75 -> 93 ; n3 |0.15-0.078125| -> 92.81 -> 92
+#   totals: n1 91+86+116+100 = 393 ; n2 93+90+182+100 = 465 ; n3 92+88+166+100 = 446 ; n4 93+90+200+100 = 483
+CASES["default_topology_spread"] = {
+    "nodes": [node("n1", {Z: "z1"}), node("n2", {Z: "z1"}), node("n3", {Z: "z2"}), node("n4", {Z: "z2"})],
+    "running": [running("w1", "n1", {"app": "web"}, {"cpu": "100m", "memory": "128Mi"}),
+                running("w2", "n1", {"app": "web"}, {"cpu": "100m", "memory": "128Mi"}),
+                running("w3", "n3", {"app": "web"}, {"cpu": "100m", "memory": "128Mi"})],
+    "services": [{"kind": "Service", "metadata": {"name": "web", "namespace": "default"}, "spec": {"selector": {"app": "web"}}}],
+    "pod": incoming(labels={"app": "web"}, requests={"cpu": "500m", "memory": "512Mi"}),
+    "expect": {"n1": {"ba": 91, "la": 86, "ip": 0, "na": 0, "pts": 58, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000393},
+               "n2": {"ba": 93, "la": 90, "ip": 0, "na": 0, "pts": 91, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000465},
+               "n3": {"ba": 92, "la": 88, "ip": 0, "na": 0, "pts": 83, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000446},
+               "n4": {"ba": 93, "la": 90, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000483}},
+    "winner": "n4",
+}
+
+# ---- C: preferred InterPodAffinity (+ NonZeroRequested defaults of request-less pods) ----------------------------------
+# n1 in zone za, n2 and n3 in zone zb.  Running pods WITHOUT requests: db on n1, two db on n2, cache on n3.
+# Pod 1 CPU / 1Gi: preferred podAffinity weight 10 to app=db over the zone, preferred podAntiAffinity weight 30 to
+# app=cache over the hostname.
+#   topology scores (scoring.go:87-205): zone za +10, zone zb +20, hostname n3 -30  -> node raw 10 / 20 / 20-30 = -10
+#   normalise (scoring.go:246-277) with min,max initialised to 0: min -10, max 20; int64(100*((s-min)/(max-min))):
+#       n1 100*(20/30) = 66.67 -> 66 ; n2 100 ; n3 0
+#   request-less containers count 100m / 200Mi towards the scoring aggregates only (non_zero.go:40-62):
+#       n1, n3: 100m / 200Mi ; n2: 200m / 400Mi
+#   LeastAllocated: n1 cpu (4000-1100)*100/4000 = 72.5 -> 72, mem (8192-1224)*100/8192 = 85.06 -> 85, (72+85)/2 = 78.5 -> 78 ; n3 = n1
+#                   n2 cpu (4000-1200)*100/4000 = 70, mem (8192-1424)*100/8192 = 82.6 -> 82, 76
+#   BalancedAllocation: n1 |0.275 - 0.149414| = 0.125586 -> 87.44 -> 87 ; n2 |0.3 - 0.173828| = 0.126172 -> 87.38 -> 87
+#   totals: n1 87+78+66+200+100 = 531 ; n2 87+76+100+200+100 = 563 ; n3 87+78+0+200+100 = 465
+CASES["preferred_inter_pod_affinity"] = {
+    "nodes": [node("n1", {Z: "za"}), node("n2", {Z: "zb"}), node("n3", {Z: "zb"})],
+    "running": [running("d1", "n1", {"app": "db"}), running("d2", "n2", {"app": "db"}), running("d3", "n2", {"app": "db"}),
+                running("c1", "n3", {"app": "cache"})],
+    "services": [],
+    "pod": incoming({"affinity": {
+        "podAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+            {"weight": 10, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "db"}}, "topologyKey": Z}}]},
+        "podAntiAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+            {"weight": 30, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "cache"}}, "topologyKey": N}}]}}},
+        requests={"cpu": "1", "memory": "1Gi"}),
+    "expect": {"n1": {"ba": 87, "la": 78, "ip": 66, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000531},
+               "n2": {"ba": 87, "la": 76, "ip": 100, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000563},
+               "n3": {"ba": 87, "la": 78, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000465}},
+    "winner": "n2",
+}
+
+# ---- D: DoNotSchedule spread constraint leaves one node: "When only one node after predicate, just use it" ------------
+# zone za = {n1} holds two app=x pods, zone zb = {n2} none.  Pod app=x with {maxSkew 1, zone, DoNotSchedule, app=x}:
+#   skew(n1) = 2 + 1 - min(2, 0) = 3 > 1 -> Unschedulable (filtering.go:276-328); skew(n2) = 0 + 1 - 0 = 1 -> fits.
+#   F == 1 -> the node is returned without scoring (generic_scheduler.go:159-165): reported score 0.
+CASES["hard_spread_single_survivor"] = {
+    "nodes": [node("n1", {Z: "za"}), node("n2", {Z: "zb"})],
+    "running": [running("x1", "n1", {"app": "x"}), running("x2", "n1", {"app": "x"})],
+    "services": [],
+    "pod": incoming({"topologySpreadConstraints": [{"maxSkew": 1, "topologyKey": Z, "whenUnsatisfiable": "DoNotSchedule",
+                                                    "labelSelector": {"matchLabels": {"app": "x"}}}]},
+                    labels={"app": "x"}, requests={"cpu": "1", "memory": "1Gi"}),
+    "expect": {}, "winner": "n2", "winner_score": 0, "infeasible": {"n1": 14},
+}

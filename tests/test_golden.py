@@ -118,3 +118,73 @@ def test_simulate_api_on_simple_scenario_gpu():
         for rec in st.Pods:
             got[((rec.tmpl.workload_kind, rec.tmpl.workload_namespace, rec.tmpl.workload_name), rec.ordinal)] = st.Node["metadata"]["name"]
     assert got == want
+
+
+def _plugin_kats():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import kat_plugins
+    return kat_plugins.CASES
+
+
+@pytest.mark.parametrize("name", ["taints_and_preferred_node_affinity", "default_topology_spread",
+                                  "preferred_inter_pod_affinity", "hard_spread_single_survivor"])
+def test_oracle_reproduces_hand_derived_plugin_kats(name):
+    """tests/golden/kat_plugins.py: expected numbers derived by hand from the reference's formulas (file:line there)."""
+    from oracle.binding import Oracle
+    from oracle.pyref import PyRef
+    from simon_b200 import simulator
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.objects import AppResource, ResourceTypes
+    kat = _plugin_kats()[name]
+    cluster = ResourceTypes()
+    cluster.Nodes.extend(kat["nodes"])
+    cluster.Pods.extend(kat["running"])
+    cluster.Services.extend(kat["services"])
+    app = AppResource("kat", ResourceTypes())
+    app.Resource.Pods.append(kat["pod"])
+    p = simulator.plan(cluster, [app])
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    o = Oracle(c)
+    o.enable_dump()
+    out, score, _, _ = o.schedule()
+    code, sc = o.last_detail()
+    names = ["ba", "la", "ip", "na", "pts", "tt", "sm", "ex", "total"]
+    for node, exp in kat["expect"].items():
+        i = c.node_index(node)
+        got = dict(zip(names, [int(x) for x in sc[i][:9]]))
+        assert got == exp, (node, got, exp)
+    for node, cde in kat.get("infeasible", {}).items():
+        assert int(code[c.node_index(node)]) == cde
+    assert c.node_names[out[-1]] == kat["winner"]
+    want_score = kat.get("winner_score", kat["expect"].get(kat["winner"], {}).get("total"))
+    assert int(score[-1]) == want_score
+    # the independent object-level restatement picks the same node
+    ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets)
+    py = ref.run([x.tmpl.pod for x in p.pods], [x.node_name for x in p.pods])
+    assert c.node_names[py[-1]] == kat["winner"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["taints_and_preferred_node_affinity", "default_topology_spread",
+                                  "preferred_inter_pod_affinity", "hard_spread_single_survivor"])
+def test_engine_reproduces_hand_derived_plugin_kats(name):
+    """The CUDA engine picks the hand-derived winner with the hand-derived total (tests/golden/kat_plugins.py)."""
+    from simon_b200 import simulator
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.engine import Engine
+    from simon_b200.objects import AppResource, ResourceTypes
+    kat = _plugin_kats()[name]
+    cluster = ResourceTypes()
+    cluster.Nodes.extend(kat["nodes"])
+    cluster.Pods.extend(kat["running"])
+    cluster.Services.extend(kat["services"])
+    app = AppResource("kat", ResourceTypes())
+    app.Resource.Pods.append(kat["pod"])
+    p = simulator.plan(cluster, [app])
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    with Engine(c, device=0, record_scores=True) as eng:
+        out, score, _, _ = eng.schedule()
+    assert c.node_names[out[-1]] == kat["winner"]
+    want_score = kat.get("winner_score", kat["expect"].get(kat["winner"], {}).get("total"))
+    assert int(score[-1]) == want_score
