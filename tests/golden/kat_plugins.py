@@ -137,3 +137,73 @@ CASES["hard_spread_single_survivor"] = {
                     labels={"app": "x"}, requests={"cpu": "1", "memory": "1Gi"}),
     "expect": {}, "winner": "n2", "winner_score": 0, "infeasible": {"n1": 14},
 }
+
+# ---- E: Simon score with different node sizes (counted twice: its GPU-share twin repeats it) ----------------------------
+# n1 4 CPU / 8Gi, n2 8 CPU / 16Gi, n3 16 CPU / 16Gi, pod 2 CPU / 2Gi.
+#   Simon raw (simon.go:45-68) = int64(100 * max over allocatable resources of req/(alloc-req)), "pods" contributes 0:
+#       n1 cpu 2/(4-2) = 1.0, mem 2/(8-2) = 0.33      -> 100
+#       n2 cpu 2/(8-2) = 0.3333, mem 2/(16-2) = 0.1429 -> 33
+#       n3 cpu 2/(16-2) = 0.1429, mem 0.1429          -> 14
+#   normalise (simon.go:76-101) (s-min)*100/(max-min), min 14, max 100: 100 / 19*100/86 = 22 / 0 ; weight 1 + the twin's 1
+#   LeastAllocated: n1 cpu 50, mem (8192-2048)*100/8192 = 75, (50+75)/2 = 62 ; n2 cpu 75, mem 87.5 -> 87, 81 ; n3 cpu 87.5 -> 87, mem 87, 87
+#   BalancedAllocation: n1 |0.5-0.25| -> 75 ; n2 |0.25-0.125| -> 87.5 -> 87 ; n3 |0.125-0.125| -> 100
+#   totals: n1 75+62+200+100+2*100 = 637 ; n2 87+81+200+100+2*22 = 512 ; n3 100+87+200+100+0 = 487
+def _sized(name, cpu, mem):
+    n = node(name)
+    n["status"]["allocatable"].update({"cpu": cpu, "memory": mem})
+    return n
+
+
+CASES["simon_packs_onto_the_smallest_node"] = {
+    "nodes": [_sized("n1", "4", "8Gi"), _sized("n2", "8", "16Gi"), _sized("n3", "16", "16Gi")],
+    "running": [], "services": [],
+    "pod": incoming(requests={"cpu": "2", "memory": "2Gi"}),
+    "expect": {"n1": {"ba": 75, "la": 62, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 100, "ex": 1000000, "total": 1000637},
+               "n2": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 22, "ex": 1000000, "total": 1000512},
+               "n3": {"ba": 100, "la": 87, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000487}},
+    "winner": "n1",
+}
+
+# ---- F: GPU share: per-device fit, not total memory (gpunodeinfo.go:232-290) --------------------------------------------
+# g1, g2: 2 devices x 8Gi.  Pre-bound GPU pods (tightest-fit device each): g1 4Gi -> free [4, 8];
+# g2 6Gi -> [2, 8], then 3Gi -> only device 1 fits -> [2, 5].
+# pod A: 6Gi on one device: g1 device 1 fits; g2 has 7Gi free in total but no device with 6Gi -> Open-Gpu-Share filter
+#        rejects g2 -> single survivor g1 (score 0).  g1 free becomes [4, 2].
+# pod B: 2 devices x 4Gi (greedy over devices in index order): g1 only device 0, g2 only device 1 -> unschedulable.
+def _gpu_node(name):
+    n = node(name)
+    for sect in ("allocatable",):
+        n["status"][sect].update({"alibabacloud.com/gpu-count": "2", "alibabacloud.com/gpu-mem": "16Gi"})
+    n["status"]["capacity"] = dict(n["status"]["allocatable"])
+    return n
+
+
+def _gpu_pod(p, mem, count="1"):
+    p["metadata"]["annotations"] = {"alibabacloud.com/gpu-mem": mem, "alibabacloud.com/gpu-count": count}
+    return p
+
+
+CASES["gpu_share_per_device_fit"] = {
+    "nodes": [_gpu_node("g1"), _gpu_node("g2")],
+    "running": [_gpu_pod(running("r1", "g1"), "4Gi"), _gpu_pod(running("r2", "g2"), "6Gi"), _gpu_pod(running("r3", "g2"), "3Gi")],
+    "services": [],
+    "pod": [_gpu_pod(incoming(requests={"cpu": "1", "memory": "1Gi"}), "6Gi"),
+            _gpu_pod(dict(incoming(requests={"cpu": "1", "memory": "1Gi"}), metadata={"name": "incoming-b", "namespace": "default", "labels": {}}), "4Gi", "2")],
+    "expect": {}, "winners": ["g1", None], "scores": [0, 0],
+}
+
+# ---- G: required pod affinity to the pod's own label: the first pod of the series may go anywhere ----------------------
+# n1 (zone za) empty, n2 (zone zb) carries a 3 CPU / 6Gi pod.  Pods app=s, 500m / 512Mi, required podAffinity to app=s
+# over the zone.  No pod matches yet and the pod matches its own term -> the term is waived (filtering.go:361-372):
+#   both nodes pass; n1 wins on LeastAllocated (90 vs 15; BalancedAllocation 93 on both).
+# The second pod must join a zone that holds an app=s pod: only za = {n1} -> single survivor, score 0.
+CASES["self_affinity_series"] = {
+    "nodes": [node("n1", {Z: "za"}), node("n2", {Z: "zb"})],
+    "running": [running("big", "n2", {"app": "other"}, {"cpu": "3", "memory": "6Gi"})],
+    "services": [],
+    "pod": [dict(incoming({"affinity": {"podAffinity": {"requiredDuringSchedulingIgnoredDuringExecution": [
+                {"labelSelector": {"matchLabels": {"app": "s"}}, "topologyKey": Z}]}}},
+                labels={"app": "s"}, requests={"cpu": "500m", "memory": "512Mi"}),
+                metadata={"name": f"s-{i}", "namespace": "default", "labels": {"app": "s"}}) for i in range(2)],
+    "expect": {}, "winners": ["n1", "n1"], "scores": [1000000 + 93 + 90 + 200 + 100, 0],
+}

@@ -127,64 +127,69 @@ def _plugin_kats():
     return kat_plugins.CASES
 
 
-@pytest.mark.parametrize("name", ["taints_and_preferred_node_affinity", "default_topology_spread",
-                                  "preferred_inter_pod_affinity", "hard_spread_single_survivor"])
-def test_oracle_reproduces_hand_derived_plugin_kats(name):
-    """tests/golden/kat_plugins.py: expected numbers derived by hand from the reference's formulas (file:line there)."""
-    from oracle.binding import Oracle
-    from oracle.pyref import PyRef
+KAT_NAMES = ["taints_and_preferred_node_affinity", "default_topology_spread", "preferred_inter_pod_affinity",
+             "hard_spread_single_survivor", "simon_packs_onto_the_smallest_node", "gpu_share_per_device_fit", "self_affinity_series"]
+
+
+def _kat_cluster(kat):
     from simon_b200 import simulator
     from simon_b200.compiler import compile_cluster
     from simon_b200.objects import AppResource, ResourceTypes
-    kat = _plugin_kats()[name]
     cluster = ResourceTypes()
     cluster.Nodes.extend(kat["nodes"])
     cluster.Pods.extend(kat["running"])
     cluster.Services.extend(kat["services"])
     app = AppResource("kat", ResourceTypes())
-    app.Resource.Pods.append(kat["pod"])
+    pods = kat["pod"] if isinstance(kat["pod"], list) else [kat["pod"]]
+    app.Resource.Pods.extend(pods)
     p = simulator.plan(cluster, [app])
-    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    return p, compile_cluster(p.nodes, p.pods, p.ctx), len(pods)
+
+
+def _kat_expected(kat, n_in):
+    winners = kat.get("winners", [kat.get("winner")])
+    scores = kat.get("scores", [kat.get("winner_score", kat["expect"].get(kat.get("winner"), {}).get("total"))])
+    assert len(winners) == n_in and len(scores) == n_in
+    return winners, scores
+
+
+@pytest.mark.parametrize("name", KAT_NAMES)
+def test_oracle_reproduces_hand_derived_plugin_kats(name):
+    """tests/golden/kat_plugins.py: expected numbers derived by hand from the reference's formulas (file:line there)."""
+    from oracle.binding import Oracle
+    from oracle.pyref import PyRef
+    kat = _plugin_kats()[name]
+    p, c, n_in = _kat_cluster(kat)
+    winners, scores = _kat_expected(kat, n_in)
     o = Oracle(c)
     o.enable_dump()
     out, score, _, _ = o.schedule()
     code, sc = o.last_detail()
     names = ["ba", "la", "ip", "na", "pts", "tt", "sm", "ex", "total"]
-    for node, exp in kat["expect"].items():
+    for node, exp in kat["expect"].items():          # per-plugin scores of the (single) incoming pod
         i = c.node_index(node)
         got = dict(zip(names, [int(x) for x in sc[i][:9]]))
         assert got == exp, (node, got, exp)
     for node, cde in kat.get("infeasible", {}).items():
         assert int(code[c.node_index(node)]) == cde
-    assert c.node_names[out[-1]] == kat["winner"]
-    want_score = kat.get("winner_score", kat["expect"].get(kat["winner"], {}).get("total"))
-    assert int(score[-1]) == want_score
-    # the independent object-level restatement picks the same node
+    got_w = [c.node_names[n] if n >= 0 else None for n in out[-n_in:]]
+    assert got_w == winners
+    assert [int(x) for x in score[-n_in:]] == scores
+    # the independent object-level restatement picks the same nodes
     ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets)
     py = ref.run([x.tmpl.pod for x in p.pods], [x.node_name for x in p.pods])
-    assert c.node_names[py[-1]] == kat["winner"]
+    assert [c.node_names[n] if n >= 0 else None for n in py[-n_in:]] == winners
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["taints_and_preferred_node_affinity", "default_topology_spread",
-                                  "preferred_inter_pod_affinity", "hard_spread_single_survivor"])
+@pytest.mark.parametrize("name", KAT_NAMES)
 def test_engine_reproduces_hand_derived_plugin_kats(name):
-    """The CUDA engine picks the hand-derived winner with the hand-derived total (tests/golden/kat_plugins.py)."""
-    from simon_b200 import simulator
-    from simon_b200.compiler import compile_cluster
+    """The CUDA engine picks the hand-derived winners with the hand-derived totals (tests/golden/kat_plugins.py)."""
     from simon_b200.engine import Engine
-    from simon_b200.objects import AppResource, ResourceTypes
     kat = _plugin_kats()[name]
-    cluster = ResourceTypes()
-    cluster.Nodes.extend(kat["nodes"])
-    cluster.Pods.extend(kat["running"])
-    cluster.Services.extend(kat["services"])
-    app = AppResource("kat", ResourceTypes())
-    app.Resource.Pods.append(kat["pod"])
-    p = simulator.plan(cluster, [app])
-    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    p, c, n_in = _kat_cluster(kat)
+    winners, scores = _kat_expected(kat, n_in)
     with Engine(c, device=0, record_scores=True) as eng:
         out, score, _, _ = eng.schedule()
-    assert c.node_names[out[-1]] == kat["winner"]
-    want_score = kat.get("winner_score", kat["expect"].get(kat["winner"], {}).get("total"))
-    assert int(score[-1]) == want_score
+    assert [c.node_names[n] if n >= 0 else None for n in out[-n_in:]] == winners
+    assert [int(x) for x in score[-n_in:]] == scores
