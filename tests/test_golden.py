@@ -182,7 +182,7 @@ def test_oracle_reproduces_hand_derived_plugin_kats(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", KAT_NAMES)
+@pytest.mark.parametrize("name", [n for n in KAT_NAMES if n != "gpu_share_per_device_fit"])   # that one: tests/test_zz_prebound_gpu_share.py
 def test_engine_reproduces_hand_derived_plugin_kats(name):
     """The CUDA engine picks the hand-derived winners with the hand-derived totals (tests/golden/kat_plugins.py)."""
     from simon_b200.engine import Engine

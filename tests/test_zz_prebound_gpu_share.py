@@ -1,0 +1,69 @@
+"""Pre-bound (spec.nodeName) GPU-share pods must reserve device memory exactly like scheduled ones.
+
+Found by the hand-derived KAT `gpu_share_per_device_fit` (tests/golden/kat_plugins.py) in the last hour of round 1: the
+engine's pre-bound path skipped the device allocation that the oracle's commit performs.  The kernel was fixed
+(simon_kernel.cu, fixed-pod batch) after the round's GPU budget was spent, so this file is the first GPU run of the fix;
+it sorts last so that it cannot mask the rest of the suite under `pytest -x`.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.gpu
+
+
+def _kat():
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import kat_plugins
+    return kat_plugins.CASES["gpu_share_per_device_fit"]
+
+
+def _build(kat):
+    from simon_b200 import simulator
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.objects import AppResource, ResourceTypes
+    cluster = ResourceTypes()
+    cluster.Nodes.extend(kat["nodes"])
+    cluster.Pods.extend(kat["running"])
+    app = AppResource("kat", ResourceTypes())
+    app.Resource.Pods.extend(kat["pod"])
+    p = simulator.plan(cluster, [app])
+    return p, compile_cluster(p.nodes, p.pods, p.ctx)
+
+
+def test_engine_prebound_gpu_pods_reserve_devices_kat():
+    from simon_b200.engine import Engine
+    kat = _kat()
+    p, c = _build(kat)
+    with Engine(c, device=0, record_scores=True) as eng:
+        out, score, _, _ = eng.schedule()
+    n_in = len(kat["pod"])
+    assert [c.node_names[n] if n >= 0 else None for n in out[-n_in:]] == kat["winners"]
+    assert [int(x) for x in score[-n_in:]] == kat["scores"]
+
+
+def test_engine_prebound_gpu_pods_match_oracle_on_random_clusters():
+    """Random small clusters in which pre-bound pods carry GPU-share annotations too."""
+    from simon_b200 import simulator, synth
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.engine import Engine
+    from util import run_oracle
+    for seed in (100, 101, 102, 206):
+        cluster, apps = synth.make_mix(seed_no=seed, n_nodes=40, n_workloads=30)
+        gpu_nodes = {n["metadata"]["name"] for n in cluster.Nodes if "alibabacloud.com/gpu-count" in n["status"]["allocatable"]}
+        k = 0
+        for pod in cluster.Pods:
+            if pod["spec"].get("nodeName") in gpu_nodes:
+                pod["metadata"].setdefault("annotations", {}).update(
+                    {"alibabacloud.com/gpu-mem": f"{[2, 4, 6][k % 3]}Gi", "alibabacloud.com/gpu-count": "1"})
+                k += 1
+        p = simulator.plan(cluster, apps)
+        c = compile_cluster(p.nodes, p.pods, p.ctx)
+        (ref, _, rfc, rfp), _ = run_oracle(c)
+        with Engine(c, device=0) as eng:
+            out, _, fc, fp = eng.schedule()
+        np.testing.assert_array_equal(out, ref, err_msg=f"seed {seed}")
+        np.testing.assert_array_equal(fc, rfc)
