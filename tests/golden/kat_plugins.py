@@ -207,3 +207,50 @@ CASES["self_affinity_series"] = {
                 metadata={"name": f"s-{i}", "namespace": "default", "labels": {"app": "s"}}) for i in range(2)],
     "expect": {}, "winners": ["n1", "n1"], "scores": [1000000 + 93 + 90 + 200 + 100, 0],
 }
+
+# ---- H: ImageLocality and NodePreferAvoidPods (the "extra" column) ------------------------------------------------------
+# Image registry.local/app:v1 (500 MiB) is present on n1 and n2 of four nodes created in the order n1..n4.
+#   The scheduler cache summarises an image when a node is ADDED (cache.go:673-697): n1 sees 1 node with the image,
+#   n2 sees 2; summaries are not refreshed.  ImageLocality (image_locality.go:82-118):
+#       scaled = int64(size * numNodes/totalNodes): n1 524288000*1/4 = 131072000 ; n2 524288000*2/4 = 262144000
+#       clamp to [23 MiB, 1000 MiB * containers] and 100*(s-min)/(max-min):
+#       n1 100*(131072000-24117248)/1024458752 = 10 ; n2 100*(262144000-24117248)/1024458752 = 23 ; n3, n4 0
+#   NodePreferAvoidPods 100 * weight 10000 everywhere -> ex = 1,000,010 / 1,000,023 / 1,000,000.
+#   Everything else is equal on the four empty nodes (pod 1 CPU / 1Gi: ba 87, la 81, pts 100, tt 100 as in case A).
+def _img_node(name, with_image, avoid_uid=None):
+    n = node(name)
+    if with_image:
+        n["status"]["images"] = [{"names": ["registry.local/app:v1"], "sizeBytes": 500 * 1024 * 1024}]
+    if avoid_uid:
+        import json as _json
+        n["metadata"]["annotations"] = {"scheduler.alpha.kubernetes.io/preferAvoidPods": _json.dumps(
+            {"preferAvoidPods": [{"podSignature": {"podController": {"kind": "ReplicaSet", "uid": avoid_uid}}}]})}
+    return n
+
+
+def _img_pod(owner_uid=None):
+    p = incoming(requests={"cpu": "1", "memory": "1Gi"})
+    p["spec"]["containers"][0]["image"] = "registry.local/app:v1"
+    if owner_uid:
+        p["metadata"]["ownerReferences"] = [{"apiVersion": "apps/v1", "kind": "ReplicaSet", "name": "rs", "uid": owner_uid, "controller": True}]
+    return p
+
+
+CASES["image_locality"] = {
+    "nodes": [_img_node("n1", True), _img_node("n2", True), _img_node("n3", False), _img_node("n4", False)],
+    "running": [], "services": [], "pod": _img_pod(), "skip_pyref": True,
+    "expect": {"n1": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000010, "total": 1000478},
+               "n2": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000023, "total": 1000491},
+               "n3": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000000, "total": 1000468}},
+    "winner": "n2",
+}
+
+# the same with n2 asking to avoid the pod's controller (node_prefer_avoid_pods.go:47-82): its 10000-weighted score drops to
+# 0, ex(n2) = 23, and n1 wins with 1,000,478.
+CASES["prefer_avoid_pods"] = {
+    "nodes": [_img_node("n1", True), _img_node("n2", True, avoid_uid="u1"), _img_node("n3", False), _img_node("n4", False)],
+    "running": [], "services": [], "pod": _img_pod(owner_uid="u1"), "skip_pyref": True,
+    "expect": {"n1": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 1000010, "total": 1000478},
+               "n2": {"ba": 87, "la": 81, "ip": 0, "na": 0, "pts": 100, "tt": 100, "sm": 0, "ex": 23, "total": 491}},
+    "winner": "n1",
+}

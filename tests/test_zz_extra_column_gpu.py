@@ -1,0 +1,28 @@
+"""ImageLocality / NodePreferAvoidPods ("extra" column, simon_podset.extra_score) on the GPU engine.
+
+Added after the round's GPU minutes were spent (no earlier test input had a non-empty extra column), so this is the first
+GPU run of that gather; the file sorts last so that it cannot mask the rest of the suite under `pytest -x`.
+Expected numbers: hand-derived in tests/golden/kat_plugins.py.
+"""
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["image_locality", "prefer_avoid_pods"])
+def test_engine_extra_column_kats(name):
+    from simon_b200.engine import Engine
+    from test_golden import _kat_cluster, _kat_expected, _plugin_kats
+    kat = _plugin_kats()[name]
+    p, c, n_in = _kat_cluster(kat)
+    assert c.pods_dims["n_extra_rows"] > 0
+    winners, scores = _kat_expected(kat, n_in)
+    with Engine(c, device=0, record_scores=True) as eng:
+        out, score, _, _ = eng.schedule()
+    assert [c.node_names[n] if n >= 0 else None for n in out[-n_in:]] == winners
+    assert [int(x) for x in score[-n_in:]] == scores
