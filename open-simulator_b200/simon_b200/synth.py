@@ -244,7 +244,7 @@ def make_c4(n_nodes: int = 2000, n_workloads: int = 50, replicas: int = 100, fil
     return cluster, [app], specs
 
 
-def make_mix(seed_no: int = 100, n_nodes: int = 40, n_workloads: int = 30, max_replicas: int = 6):
+def make_mix(seed_no: int = 100, n_nodes: int = 40, n_workloads: int = 30, max_replicas: int = 6, with_images: bool = False):
     """Small clusters that exercise EVERY predicate / score input the path knows, in random combinations: unschedulable
     nodes, NoSchedule / NoExecute / PreferNoSchedule taints and all toleration shapes, nodeSelector, required and
     preferred node affinity with In / NotIn / Exists / DoesNotExist / Gt / Lt and matchFields, host ports (with and
@@ -294,6 +294,14 @@ def make_mix(seed_no: int = 100, n_nodes: int = 40, n_workloads: int = 30, max_r
                 n["status"][sect]["alibabacloud.com/gpu-count"] = str(cnt)
                 n["status"][sect]["alibabacloud.com/gpu-mem"] = mem
         cluster.Nodes.append(n)
+    if with_images:
+        # node images for ImageLocality: a few workload images of different sizes, each on a random subset of the nodes
+        irng = SplitMix64(SEED_BASE + 0x2000 + seed_no)
+        pool = [(f"registry.local/wl-{w:03d}:v1", (50 + irng.below(900)) * 1024 * 1024) for w in range(min(8, n_workloads))]
+        for n in cluster.Nodes:
+            imgs = [{"names": [nm, nm.replace("registry.local/", "mirror.local/")], "sizeBytes": sz} for (nm, sz) in pool if irng.chance(35)]
+            if imgs:
+                n["status"]["images"] = imgs
     # pre-bound pods (some carry labels that later selectors match, some hold host ports)
     for i in range(n_nodes):
         if not rng.chance(30):

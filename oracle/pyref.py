@@ -19,7 +19,7 @@ It reuses the product's Quantity / go_log restatements (simon_b200.quantity, sim
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 from simon_b200.gomath import go_log
 from simon_b200.quantity import Quantity
@@ -343,9 +343,24 @@ def _gpu_allocate(ns: NodeState, mem, num):
 class PyRef:
     """Schedules pods one at a time over dict objects. nodes must already be in snapshot (nodeTree.list) order."""
 
-    def __init__(self, nodes: List[dict], services=None, replicasets=None, statefulsets=None):
+    def __init__(self, nodes: List[dict], services=None, replicasets=None, statefulsets=None, creation_order=None):
         self.nodes = [NodeState(n) for n in nodes]
         self.by_name = {n.name: n for n in self.nodes}
+        # ImageLocality: the scheduler cache summarises a node's images when the node is ADDED (cache.go:673-697), in
+        # node creation order (creation_order[i] = original index of snapshot node i), and never refreshes the summary
+        order = sorted(range(len(nodes)), key=(lambda i: creation_order[i]) if creation_order is not None else (lambda i: i))
+        seen: Dict[str, set] = {}
+        size_of: Dict[str, int] = {}
+        self.image_states: List[Dict[str, Tuple[int, int]]] = [dict() for _ in nodes]
+        for i in order:
+            for im in ((nodes[i].get("status") or {}).get("images") or []):
+                for nm in im.get("names") or []:
+                    if nm not in seen:
+                        seen[nm] = set()
+                        size_of[nm] = int(im.get("sizeBytes") or 0)
+                    seen[nm].add(i)
+                    if nm not in self.image_states[i]:
+                        self.image_states[i][nm] = (size_of[nm], len(seen[nm]))
         self.services = services or []
         self.replicasets = replicasets or []
         self.statefulsets = statefulsets or []
@@ -661,12 +676,52 @@ class PyRef:
                 pts = 100
             else:
                 pts = (100 * (pts_max + pts_min - r["pts"])) // pts_max
-            total = ba + la + ip + na + 2 * pts + tt + 2 * sm + 100 * 10000
+            ex = self.image_locality(pod, i) + 10000 * self.prefer_avoid(pod, n)
+            total = ba + la + ip + na + 2 * pts + tt + 2 * sm + ex
             if detail is not None:
-                detail[i] = dict(ba=ba, la=la, ip=ip, na=na, pts=pts, tt=tt, sm=sm, total=total)
+                detail[i] = dict(ba=ba, la=la, ip=ip, na=na, pts=pts, tt=tt, sm=sm, ex=ex, total=total)
             if best is None or total > best:
                 best, best_i = total, i
         return best_i, best, {}
+
+    # -- ImageLocality (PL/imagelocality/image_locality.go:53-118)
+    def image_locality(self, pod, i: int) -> int:
+        mb = 1024 * 1024
+        containers = (pod.get("spec") or {}).get("containers") or []
+        total_nodes = len(self.nodes)
+        s = 0
+        for ct in containers:
+            name = ct.get("image") or ""
+            if name.rfind(":") <= name.rfind("/"):          # normalizedImageName: no tag -> ":latest"
+                name += ":latest"
+            st = self.image_states[i].get(name)
+            if st is not None:
+                s += int(float(st[0]) * (float(st[1]) / float(total_nodes)))
+        lo, hi = 23 * mb, 1000 * mb * len(containers)
+        s = min(max(s, lo), hi)
+        return (100 * (s - lo)) // (hi - lo)
+
+    # -- NodePreferAvoidPods (PL/nodepreferavoidpods/node_prefer_avoid_pods.go:47-82)
+    def prefer_avoid(self, pod, n) -> int:
+        ref = None
+        for r in (pod["metadata"].get("ownerReferences") or []):
+            if r.get("controller"):
+                ref = r
+        if ref is None or ref.get("kind") not in ("ReplicationController", "ReplicaSet"):
+            return 100
+        ann = ((n.node.get("metadata") or {}).get("annotations") or {}).get("scheduler.alpha.kubernetes.io/preferAvoidPods")
+        if not ann:
+            return 100
+        try:
+            import json as _json
+            entries = _json.loads(ann).get("preferAvoidPods") or []
+        except Exception:
+            return 100
+        for e in entries:
+            pc = ((e.get("podSignature") or {}).get("podController") or {})
+            if pc.get("kind") == ref.get("kind") and pc.get("uid") == ref.get("uid"):
+                return 0
+        return 100
 
     def run(self, pods: List[dict], fixed: Optional[List[str]] = None):
         """pods: pod dicts in order. fixed[i]: preset spec.nodeName or ''. -> list of node indices (-1 failed)."""

@@ -177,10 +177,9 @@ def test_oracle_reproduces_hand_derived_plugin_kats(name):
     got_w = [c.node_names[n] if n >= 0 else None for n in out[-n_in:]]
     assert got_w == winners
     assert [int(x) for x in score[-n_in:]] == scores
-    if kat.get("skip_pyref"):          # the object-level restatement does not model ImageLocality / NodePreferAvoidPods
-        return
     # the independent object-level restatement picks the same nodes
-    ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets)
+    ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets,
+                creation_order=c.node_orig_index)
     py = ref.run([x.tmpl.pod for x in p.pods], [x.node_name for x in p.pods])
     assert [c.node_names[n] if n >= 0 else None for n in py[-n_in:]] == winners
 

@@ -34,6 +34,16 @@ def test_c_oracle_matches_pyref_mixed_features(seed):
     assert fc.sum() > 0
 
 
+@pytest.mark.parametrize("seed", [500, 503, 511])
+def test_c_oracle_matches_pyref_with_node_images(seed):
+    """ImageLocality: the compiler's per-(class, node) table (read by the C oracle and the engine) against the object-level
+    restatement that applies image_locality.go and the scheduler cache's add-time image summaries directly."""
+    p, c = make_case("mix", seed_no=seed, n_nodes=20 + (seed % 5) * 20, n_workloads=20 + (seed % 7) * 8, with_images=True)
+    assert c.pods_dims["n_extra_rows"] > 0
+    (out, _, _, _), _ = run_oracle(c)
+    np.testing.assert_array_equal(out, run_pyref(p, c))
+
+
 def test_threaded_oracle_is_thread_count_invariant():
     """The CPU port may share its per-node loops between host threads (bench.py's reference arm): same placements,
     scores, failure histograms and final state for any thread count."""

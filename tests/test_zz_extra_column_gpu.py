@@ -26,3 +26,19 @@ def test_engine_extra_column_kats(name):
         out, score, _, _ = eng.schedule()
     assert [c.node_names[n] if n >= 0 else None for n in out[-n_in:]] == winners
     assert [int(x) for x in score[-n_in:]] == scores
+
+
+@pytest.mark.parametrize("seed", [500, 503, 511, 520])
+def test_engine_matches_oracle_with_node_images(seed):
+    import numpy as np
+    from simon_b200.engine import Engine
+    from util import make_case, run_oracle
+    p, c = make_case("mix", seed_no=seed, n_nodes=20 + (seed % 5) * 20, n_workloads=20 + (seed % 7) * 8, with_images=True)
+    assert c.pods_dims["n_extra_rows"] > 0
+    (ref, rscore, rfc, _), _ = run_oracle(c)
+    with Engine(c, device=0, record_scores=True) as eng:
+        out, score, fc, _ = eng.schedule()
+    np.testing.assert_array_equal(out, ref)
+    sched = ref >= 0
+    np.testing.assert_array_equal(score[sched & (rscore > 0)], rscore[sched & (rscore > 0)])
+    np.testing.assert_array_equal(fc, rfc)

@@ -23,5 +23,6 @@ def run_oracle(c):
 
 def run_pyref(p, c):
     from oracle.pyref import PyRef
-    ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets)
+    ref = PyRef(c.node_objs, services=p.ctx.services, replicasets=p.ctx.replicasets, statefulsets=p.ctx.statefulsets,
+                creation_order=c.node_orig_index)
     return np.array(ref.run([x.tmpl.pod for x in p.pods], [x.node_name for x in p.pods]), dtype=np.int32)
