@@ -125,6 +125,7 @@ int alloc_state(simon_ctx *ctx, ScenState &s, uint32_t max_fail, bool scores) {
     CU(s.ocache.alloc((size_t)ctx->n_classes * N));
     CU(cudaMemsetAsync(s.ocache.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * N), ctx->stream));
     CU(cudaMemsetAsync(s.csum.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * SK_CSUM_W), ctx->stream));
+    CU(cudaMemsetAsync(s.fbits.p, 0, std::max<size_t>(1, (size_t)ctx->n_classes * N), ctx->stream));
     CU(s.out_node.alloc(ctx->n_pods));
     if (scores) CU(s.out_score.alloc(ctx->n_pods));
     CU(s.fail_counts.alloc((size_t)max_fail * SIMON_N_FAIL_CODES)); CU(s.fail_pod.alloc(max_fail)); CU(s.counters.alloc(2));
@@ -143,6 +144,10 @@ int reset_state(simon_ctx *ctx, ScenState &s) {
     CU(cudaMemsetAsync(s.cnt_total.p, 0, 4ull * (ctx->n_counters ? ctx->n_counters : 1), st));
     // the own-score cache is keyed by the node's pod count, which restarts with the state
     if (s.ocache.p) CU(cudaMemsetAsync(s.ocache.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * N), st));
+    // the stored feasible-set summaries (and the feasibility bits they are exact for) describe the node set and order of
+    // the run that wrote them: a state that restarts from empty - possibly with another scenario's node list - must not
+    // inherit them (the kernel validates a summary only against flips of nodes it currently owns)
+    if (s.csum.p) CU(cudaMemsetAsync(s.csum.p, 0, 8ull * std::max<size_t>(1, (size_t)ctx->n_classes * SK_CSUM_W), st));
     return SIMON_OK;
 }
 
@@ -367,7 +372,7 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
         if (p->simon_raw[q] < 0 || p->simon_raw[q] >= (1ll << 31)) { ctx->simon32 = 0; break; }
     CU(ctx->d_extra.upload(p->extra_score, (size_t)std::max(1u, p->n_extra_rows) * std::max(1u, ctx->N), st));
     CU(cudaStreamSynchronize(st));
-    ctx->max_fail = std::min<uint32_t>(std::max(1u, p->n_pods), 1u << 16);
+    ctx->max_fail = std::max(1u, p->n_pods);      // every pod of the list may fail: one histogram row each (96 B)
     int rc = alloc_state(ctx, ctx->st, ctx->max_fail, (ctx->opt_flags & SIMON_OPT_RECORD_SCORES) != 0);
     if (rc) return rc;
     rc = reset_state(ctx, ctx->st);

@@ -444,13 +444,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                                 atomicAdd(&SC.cnt[P.cnt_off[k] + d], 1);
                                 atomicAdd(&SC.cnt_total[k], 1);
                             }
-                            if (cw2[SCW_GPU_MEM] > 0) {
-                                // a pre-bound GPU-share pod reserves device memory like a scheduled one (same allocation rule)
-                                int slots[64];
-                                int ns = gpu_allocate(P, SC, cw2[SCW_GPU_MEM], cw2[SCW_GPU_COUNT], (uint32_t)f2, slots);
-                                #pragma unroll 1
-                                for (int z = 0; z < ns && z < 64; z++) SC.gpu_used[(uint64_t)slots[z] * N + (uint32_t)f2] += cw2[SCW_GPU_MEM];
-                            }
+                            // no GPU-share reservation here: the plugin's cache is filled by Reserve alone
+                            // (open-gpu-share.go:147-188) and pre-bound pods never reach the scheduler (simulator.go:326-329)
                         }
                     }
                 }

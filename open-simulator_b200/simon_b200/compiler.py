@@ -327,6 +327,19 @@ def _parse_class(cid: int, tmpl: PodTemplate) -> ClassInfo:
             pass
     if GPU_INDEX_NAME in ann and ci.gpu_mem > 0:
         raise CompileError("pods with a preset alibabacloud.com/gpu-index annotation are not supported")
+    # Open-Local (pkg/simulator/plugin/open-local.go:51-138) is out of scope: pods that REQUEST local
+    # storage would be filtered / scored / reserved by it, so they are refused instead of being placed as if it did not
+    # exist.  A StatefulSet without open-local volumeClaimTemplates carries the annotation with an empty list
+    # (pkg/utils/utils.go:249-292) and is unaffected: GetPodLocalPVCs returns nothing and the plugin is inert.
+    if O.ANNO_POD_LOCAL_STORAGE in ann:
+        import json as _json
+        try:
+            vols = (_json.loads(ann[O.ANNO_POD_LOCAL_STORAGE]) or {}).get("volumes") or []
+        except ValueError:
+            vols = []
+        if any((v or {}).get("kind") in ("LVM", "HDD", "SSD") for v in vols):
+            raise CompileError(f"pod {ci.namespace}/{O.name_of(pod)} requests open-local storage "
+                               f"({len(vols)} volume(s)): the Open-Local plugin is not implemented by this engine")
 
     try:
         aff = spec.get("affinity") or {}

@@ -113,7 +113,7 @@ class Engine:
         """Place pods [first, first+count). Returns (out_node, out_score, fail_counts, fail_pod)."""
         P = self.c.pods_dims["n_pods"]
         count = P - first if count is None else count
-        max_fail = min(count, 1 << 16) if max_fail is None else max_fail
+        max_fail = count if max_fail is None else max_fail
         n_fail = C.c_uint32(0)
         if not download:
             self._check(lib().simon_schedule(self.h, first, count, None, None, None, None, 0, C.byref(n_fail)))

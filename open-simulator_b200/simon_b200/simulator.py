@@ -193,6 +193,14 @@ def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> 
     if options.extraRegistry:
         raise NotImplementedError("WithExtraRegistry: out-of-tree Go plugins cannot run on the device "
                                   "(SURVEY.md §8b plugin surface); refusing to ignore them silently")
+    if options.schedulerConfig:
+        # the reference merges a user KubeSchedulerConfiguration over its defaults (pkg/simulator/utils.go:304-381); the
+        # engine implements exactly the default plugin set and weights, so a custom file cannot be honoured
+        raise NotImplementedError("WithSchedulerConfig: custom scheduler configurations are not supported by the engine "
+                                  "(default plugin set and weights only); refusing to ignore the file silently")
+    if options.kubeconfig:
+        raise NotImplementedError("WithKubeConfig: importing a live cluster needs an API server; pass the cluster as "
+                                  "ResourceTypes (objects.create_cluster_resource_from_cluster_config)")
     from .engine import Engine     # raises if libsimon_gpu.so / CUDA is unavailable: no CPU fallback
     p = plan(cluster, apps)
     compiled = compile_cluster(p.nodes, p.pods, p.ctx)

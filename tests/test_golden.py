@@ -144,8 +144,13 @@ def _kat_cluster(kat):
     app = AppResource("kat", ResourceTypes())
     pods = kat["pod"] if isinstance(kat["pod"], list) else [kat["pod"]]
     app.Resource.Pods.extend(pods)
-    p = simulator.plan(cluster, [app])
-    return p, compile_cluster(p.nodes, p.pods, p.ctx), len(pods)
+    apps = [app]
+    if kat.get("pod2"):                      # a second app: placed after the first one (pkg/simulator/core.go:105-116)
+        app2 = AppResource("kat2", ResourceTypes())
+        app2.Resource.Pods.extend(kat["pod2"])
+        apps.append(app2)
+    p = simulator.plan(cluster, apps)
+    return p, compile_cluster(p.nodes, p.pods, p.ctx), len(pods) + len(kat.get("pod2") or [])
 
 
 def _kat_expected(kat, n_in):
