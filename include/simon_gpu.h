@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define SIMON_ABI_VERSION 1
+#define SIMON_ABI_VERSION 2
 
 #define SIMON_MAX_SCALARS 8     /* extended/scalar resource columns (K) */
 #define SIMON_MAX_GPU_DEV 8     /* GPU-share devices per node */
@@ -286,6 +286,23 @@ int simon_state_download(simon_ctx *ctx, int64_t *req_mcpu, int64_t *req_mem, in
  * inactive node are skipped (they do not exist in that scenario). */
 int simon_scenarios_run(simon_ctx *ctx, const simon_scenario *scen, uint32_t n,
                         simon_scenario_result *out, int32_t *out_node);
+
+/* GPU-share Reserve results of the last simon_schedule (pkg/simulator/plugin/open-gpu-share.go:147-188: the device ids that
+ * Reserve writes into the pod annotation alibabacloud.com/gpu-index): out_slots[i] holds 4 bits per device d (bits 4d..4d+3)
+ * = the number of the pod's GPU slots AllocateGpuId (cache/gpunodeinfo.go:232-290) put on device d; 0 for pods without a
+ * GPU request, unschedulable pods and pre-bound pods (which never reach Reserve). */
+int simon_gpu_slots_download(simon_ctx *ctx, uint32_t first, uint32_t count, uint32_t *out_slots);
+
+/* The rest of the dynamic per-node state: NodeInfo.Requested.ScalarResources [K][N] and the GPU-share device memory in use
+ * [SIMON_MAX_GPU_DEV][N] (what Reserve exports into the node annotation simon/node-gpu-share). Either pointer may be NULL. */
+int simon_state_download_ext(simon_ctx *ctx, int64_t *req_scalar, int64_t *gpu_used);
+
+/* Debug / parity instrumentation: record, for ONE pod of the next simon_schedule call that covers it, the total weighted
+ * score of every feasible node (klog V(10) of prioritizeNodes, generic_scheduler.go:558-562; -1 for nodes that were not
+ * scored) and the filter verdict of every node (0 = feasible, else a bitmask of simon_fail_code); pod = 0xffffffff: off.
+ * No placement depends on it. */
+int simon_debug_set_dump_pod(simon_ctx *ctx, uint32_t pod);
+int simon_debug_dump_read(simon_ctx *ctx, int64_t *out_total, int32_t *out_code);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ struct ScenState {
     DevBuf<uint8_t> hard_reg;
     DevBuf<int32_t> out_node;
     DevBuf<int64_t> out_score;
+    DevBuf<uint32_t> out_gpu;
     DevBuf<uint32_t> fail_counts, fail_pod, counters;   // counters: [0]=n_fail [1]=n_sched
     DevBuf<unsigned long long> clk;
     DevBuf<uint32_t> order;
@@ -60,6 +61,47 @@ struct ScenState {
 };
 
 }  // namespace
+
+struct ScenBatch {
+    DevBuf<int64_t> req_mcpu, req_mem, req_eph, nz_mcpu, nz_mem, req_scalar, gpu_used;
+    DevBuf<int32_t> num_pods, cnt, cnt_total, tp, fcount, size, out_node, rank_of;
+    DevBuf<long long> csum;
+    DevBuf<uint8_t> fbits, hard_reg;
+    DevBuf<unsigned long long> ocache, clk;
+    DevBuf<uint32_t> counters, order;
+    DevBuf<simon_scenario_result> results;
+    std::vector<uint32_t> h_order;
+    std::vector<int32_t> h_rank;
+};
+
+// satisfyResourceSetting's sums (pkg/apply/apply.go:747-757) per scenario over its active nodes, plus the scenario's counters
+__global__ void simon_scen_reduce(const SkScenario *scen, const int64_t *alloc_mcpu, const int64_t *alloc_mem, simon_scenario_result *out) {
+    const SkScenario &sc = scen[blockIdx.x];
+    long long v[4] = {0, 0, 0, 0};
+    for (uint32_t r = threadIdx.x; r < sc.n_active; r += blockDim.x) {
+        const uint32_t g = sc.order ? sc.order[r] : r;
+        v[0] += sc.req_mcpu[g]; v[1] += alloc_mcpu[g]; v[2] += sc.req_mem[g]; v[3] += alloc_mem[g];
+    }
+    __shared__ long long part[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) part[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        simon_scenario_result o;
+        long long t[4] = {0, 0, 0, 0};
+        for (int q = 0; q < 4; q++)
+            for (unsigned w = 0; w < (blockDim.x + 31) / 32; w++) t[q] += part[q][w];
+        o.n_unscheduled = *sc.n_fail; o.n_scheduled = *sc.n_sched;
+        o.req_mcpu = t[0]; o.alloc_mcpu = t[1]; o.req_mem = t[2]; o.alloc_mem = t[3];
+        o.elapsed_ms = sc.clk ? (float)((double)(sc.clk[1] - sc.clk[0]) * 1e-6) : 0.f;
+        o.reserved = 0;
+        out[blockIdx.x] = o;
+    }
+}
 
 struct simon_ctx {
     int device = 0;
@@ -85,6 +127,13 @@ struct simon_ctx {
     DevBuf<uint64_t> d_class_off, d_cnt_off;
     DevBuf<int64_t> d_class_blob, d_simon_raw;
     DevBuf<int32_t> d_pod_class, d_pod_fixed, d_pod_guard, d_extra;
+    DevBuf<ulonglong2> d_pod_meta;
+    DevBuf<uint32_t> d_cls_aux;
+    // debug dump of one pod's per-node totals / filter verdicts (simon_debug_*)
+    uint32_t dump_pod = 0xffffffffu;
+    DevBuf<long long> d_dump_total;
+    DevBuf<int32_t> d_dump_code;
+    uint32_t fast = 3;
     // single-scenario state
     ScenState st;
     uint32_t max_fail = 0;
@@ -93,6 +142,7 @@ struct simon_ctx {
     uint32_t n_sigs = 1, use_scache = 0, simon32 = 0;
     // multi-scenario state
     std::vector<ScenState *> scen_states;
+    ScenBatch *batch = nullptr;
 };
 
 namespace {
@@ -128,6 +178,7 @@ int alloc_state(simon_ctx *ctx, ScenState &s, uint32_t max_fail, bool scores) {
     CU(cudaMemsetAsync(s.fbits.p, 0, std::max<size_t>(1, (size_t)ctx->n_classes * N), ctx->stream));
     CU(s.out_node.alloc(ctx->n_pods));
     if (scores) CU(s.out_score.alloc(ctx->n_pods));
+    CU(s.out_gpu.alloc(ctx->n_pods));
     CU(s.fail_counts.alloc((size_t)max_fail * SIMON_N_FAIL_CODES)); CU(s.fail_pod.alloc(max_fail)); CU(s.counters.alloc(2));
     CU(s.clk.alloc(2));
     return SIMON_OK;
@@ -159,7 +210,7 @@ void fill_scen(simon_ctx *ctx, ScenState &s, SkScenario &o, uint32_t n_active, b
     o.req_mcpu = s.req_mcpu.p; o.req_mem = s.req_mem.p; o.req_eph = s.req_eph.p; o.nz_mcpu = s.nz_mcpu.p; o.nz_mem = s.nz_mem.p;
     o.req_scalar = s.req_scalar.p; o.gpu_used = s.gpu_used.p; o.num_pods = s.num_pods.p; o.cnt = s.cnt.p; o.cnt_total = s.cnt_total.p;
     o.tp = s.tp.p; o.fcount = s.fcount.p; o.size = s.size.p; o.hard_reg = s.hard_reg.p; o.csum = s.csum.p; o.fbits = s.fbits.p; o.ocache = s.ocache.p;
-    o.out_node = s.out_node.p; o.out_score = s.out_score.p;
+    o.out_node = s.out_node.p; o.out_score = s.out_score.p; o.out_gpu = s.out_gpu.p;
     o.fail_counts = s.fail_counts.p; o.fail_pod = s.fail_pod.p; o.n_fail = s.counters.p; o.n_sched = s.counters.p + 1;
     o.clk = s.clk.p;
     (void)ctx;
@@ -180,6 +231,9 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.emax = ctx->emax;
     P.stats = ctx->d_stats.p;
     P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p;
+    P.pod_meta = ctx->d_pod_meta.p; P.cls_aux = ctx->d_cls_aux.p;
+    P.fast = ctx->fast;
+    P.dump_pod = 0xffffffffu; P.dump_total = nullptr; P.dump_code = nullptr;
 }
 
 #define SIMON_MAX_TPB 320u       // largest compiled variant: 168 registers/thread, no spills (640 threads = 96 registers spilled and measured slower)
@@ -287,6 +341,7 @@ void simon_ctx_destroy(simon_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (auto *s : ctx->scen_states) delete s;
+    delete ctx->batch;
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -371,6 +426,63 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     for (size_t q = 0; q < (size_t)p->n_static_rows * ctx->NC; q++)
         if (p->simon_raw[q] < 0 || p->simon_raw[q] >= (1ll << 31)) { ctx->simon32 = 0; break; }
     CU(ctx->d_extra.upload(p->extra_score, (size_t)std::max(1u, p->n_extra_rows) * std::max(1u, ctx->N), st));
+    // per-class commit tables (what warp 0 of every CTA used to derive at each class switch) and the per-pod queue
+    // records the kernel reads two pods ahead (class-context prefetch)
+    if (blob_words >= (1ull << 32)) return fail(ctx, SIMON_ERR_LIMIT, "class records exceed 2^32 words");
+    std::vector<uint32_t> aux((size_t)std::max(1u, p->n_classes) * SK_AUX_W, 0u);
+    for (uint32_t c = 0; c < p->n_classes; c++) {
+        const int64_t *cw = p->class_blob + p->class_off[c];
+        const int64_t *et = cw + cw[SCW_OFF_ENT];
+        const uint32_t E = (uint32_t)(cw[SCW_N_PORTS] + cw[SCW_N_PTS_HARD] + cw[SCW_N_PTS_SOFT] + cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] +
+                                      cw[SCW_N_IPA_EXIST] + cw[SCW_N_IPA_SCORE]);
+        if ((uint64_t)cw[SCW_OFF_ENT] + 8ull * E > p->class_off[c + 1] - p->class_off[c] || (uint32_t)cw[SCW_N_ENT] != E)
+            return fail(ctx, SIMON_ERR_INVALID, "class %u: entry table does not match the list sizes", c);
+        uint32_t *ax = aux.data() + (size_t)c * SK_AUX_W;
+        uint32_t recs[SK_MAX_ENT];
+        bool node_lvl[SK_MAX_ENT], incs[SK_MAX_ENT];
+        uint32_t n_dom = 0, n_all = 0, n_aff_node = 0;
+        for (uint32_t e = 0; e < E; e++) {
+            const int64_t *r = et + 8ull * e;
+            const int32_t kind = (int32_t)r[ER_KIND];
+            const bool host = kind == EK_SOFT && r[ER_B] != 0;
+            incs[e] = r[ER_INC] != 0;
+            // entry | topology row << 8 | flags << 16 (bit 16: domain-level soft constraint, bit 17: required affinity term)
+            recs[e] = e | ((host ? 0u : (uint32_t)r[ER_T]) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) | (kind == EK_AFF ? 1u << 17 : 0u);
+            // entries on topology row 0 (the node itself) can only match the winner's own node: they go to the end of the
+            // list and are applied by the owning thread alone; every thread walks the others
+            node_lvl[e] = incs[e] && ((recs[e] >> 8) & 0xff) == 0;
+            if (incs[e]) { n_all++; if (!node_lvl[e]) n_dom++; else if (recs[e] & (1u << 17)) n_aff_node++; }
+        }
+        uint32_t kd = 0, kn = n_dom;
+        for (uint32_t e = 0; e < E; e++) {
+            if (!incs[e]) continue;
+            if (node_lvl[e]) ax[kn++] = recs[e]; else ax[kd++] = recs[e];
+        }
+        ax[SK_MAX_ENT] = n_dom | (n_all << 8) | (n_aff_node << 16);
+        const int64_t *inc = cw + cw[SCW_OFF_INC];
+        for (uint32_t u = 0; u < 32 && (int64_t)u < cw[SCW_N_INC]; u++) {
+            if (inc[3 * u] < 0 || (uint64_t)inc[3 * u] >= p->n_counters) return fail(ctx, SIMON_ERR_INVALID, "class %u: bad counter in the commit list", c);
+            ax[SK_AUX_INCB + u] = (uint32_t)cnt_off[inc[3 * u]];
+        }
+    }
+    std::vector<ulonglong2> meta((size_t)std::max(1u, p->n_pods) * 2);
+    for (uint32_t i = 0; i < p->n_pods; i++) {
+        const uint32_t c = (uint32_t)p->pod_class[i];
+        const int64_t *cw = p->class_blob + p->class_off[c];
+        const uint64_t words = p->class_off[c + 1] - p->class_off[c];
+        ulonglong2 a, b;
+        a.x = (uint64_t)c | ((uint64_t)(uint32_t)p->pod_fixed_node[i] << 32);
+        a.y = (uint64_t)(uint32_t)guard[i] | (words << 32);
+        b.x = (uint64_t)(uint32_t)p->class_off[c] | ((uint64_t)(uint32_t)(int32_t)cw[SCW_EXTRA_ROW] << 32);
+        b.y = (uint64_t)(uint32_t)(int32_t)cw[SCW_STATIC_SIG] | ((uint64_t)(uint32_t)(int32_t)cw[SCW_STATIC_ROW] << 32);
+        meta[2ull * i] = a; meta[2ull * i + 1] = b;
+    }
+    CU(ctx->d_cls_aux.upload(aux.data(), aux.size(), st));
+    CU(ctx->d_pod_meta.upload(meta.data(), meta.size(), st));
+    {
+        const char *fv = getenv("SIMON_FAST");      // diagnostic switch: bit 0 merged arg-max, bit 1 class-context prefetch
+        ctx->fast = fv ? (uint32_t)strtoul(fv, nullptr, 0) : 3u;
+    }
     CU(cudaStreamSynchronize(st));
     ctx->max_fail = std::max(1u, p->n_pods);      // every pod of the list may fail: one histogram row each (96 B)
     int rc = alloc_state(ctx, ctx->st, ctx->max_fail, (ctx->opt_flags & SIMON_OPT_RECORD_SCORES) != 0);
@@ -386,6 +498,8 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
         CU(ctx->d_scache.alloc(words));
         CU(cudaMemsetAsync(ctx->d_scache.p, 0, 8ull * words, st));
     }
+    CU(ctx->d_dump_total.alloc(std::max(1u, ctx->N))); CU(ctx->d_dump_code.alloc(std::max(1u, ctx->N)));
+    ctx->dump_pod = 0xffffffffu;
     CU(ctx->d_stats.alloc(32));
     CU(cudaMemsetAsync(ctx->d_stats.p, 0, 256, st));
     CU(cudaStreamSynchronize(st));
@@ -433,6 +547,11 @@ int simon_schedule(simon_ctx *ctx, uint32_t first, uint32_t count, int32_t *out_
     SkParams P;
     fill_params(ctx, P);
     P.first = first; P.count = count; P.max_fail = ctx->max_fail; P.npt = NPT; P.scen = ctx->d_scen.p;
+    if (ctx->dump_pod >= first && ctx->dump_pod < first + count) {
+        P.dump_pod = ctx->dump_pod; P.dump_total = ctx->d_dump_total.p; P.dump_code = ctx->d_dump_code.p;
+        CU(cudaMemsetAsync(ctx->d_dump_total.p, 0xff, 8ull * std::max(1u, ctx->N), st));     // -1: node not scored (infeasible)
+        CU(cudaMemsetAsync(ctx->d_dump_code.p, 0, 4ull * std::max(1u, ctx->N), st));
+    }
     rc = launch(ctx, P, 1, CS, TPB, smem);
     if (rc) return rc;
     cudaError_t e = cudaStreamSynchronize(st);
@@ -511,71 +630,119 @@ int simon_scenarios_run(simon_ctx *ctx, const simon_scenario *scen, uint32_t n, 
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (n == 0) return SIMON_OK;
-    while (ctx->scen_states.size() < n) {
-        ScenState *s = new (std::nothrow) ScenState();
-        if (!s) return SIMON_ERR_NOMEM;
-        ctx->scen_states.push_back(s);
-        int rc = alloc_state(ctx, *s, 1, false);
-        if (rc) return rc;
-        CU(s->order.alloc(ctx->N)); CU(s->rank_of.alloc(ctx->N));
-    }
+    const uint32_t N = ctx->N, N1 = std::max(1u, N), K1 = ctx->K ? ctx->K : 1, P = ctx->n_pods, P1 = std::max(1u, P);
+    const size_t cntw = std::max<uint64_t>(1, ctx->cnt_words), nct = std::max(1u, ctx->n_counters), ncl = std::max(1u, ctx->n_classes);
+    if (!ctx->batch) { ctx->batch = new (std::nothrow) ScenBatch(); if (!ctx->batch) return SIMON_ERR_NOMEM; }
+    ScenBatch &B = *ctx->batch;
+    // ---- node lists: validated on the host, uploaded in ONE copy each (scenario order and its inverse) ----
     uint32_t max_active = 0;
-    std::vector<SkScenario> h(n);
-    std::vector<int32_t> rank(ctx->N);
+    B.h_order.assign((size_t)n * N1, 0u);
+    B.h_rank.assign((size_t)n * N1, -1);
+    std::vector<uint8_t> ident(n, 0);
     for (uint32_t i = 0; i < n; i++) {
-        ScenState &s = *ctx->scen_states[i];
-        if (scen[i].n_nodes > ctx->N) return fail(ctx, SIMON_ERR_INVALID, "scenario %u: too many nodes", i);
-        std::fill(rank.begin(), rank.end(), -1);
+        if (scen[i].n_nodes > N) return fail(ctx, SIMON_ERR_INVALID, "scenario %u: too many nodes", i);
+        uint32_t *ord = B.h_order.data() + (size_t)i * N1;
+        int32_t *rank = B.h_rank.data() + (size_t)i * N1;
+        bool id = scen[i].n_nodes == N;
         for (uint32_t r = 0; r < scen[i].n_nodes; r++) {
             uint32_t g = scen[i].nodes[r];
-            if (g >= ctx->N || rank[g] != -1) return fail(ctx, SIMON_ERR_INVALID, "scenario %u: bad node list", i);
+            if (g >= N || rank[g] != -1) return fail(ctx, SIMON_ERR_INVALID, "scenario %u: bad node list", i);
             rank[g] = (int32_t)r;
+            ord[r] = g;
+            if (g != r) id = false;
         }
-        CU(cudaMemcpyAsync(s.order.p, scen[i].nodes, 4ull * scen[i].n_nodes, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s.rank_of.p, rank.data(), 4ull * ctx->N, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));
-        int rc = reset_state(ctx, s);
-        if (rc) return rc;
-        CU(cudaMemsetAsync(s.counters.p, 0, 8, st));
-        CU(cudaMemsetAsync(s.clk.p, 0, 16, st));
-        fill_scen(ctx, s, h[i], scen[i].n_nodes, false);
-        h[i].fail_counts = nullptr;
+        ident[i] = id ? 1 : 0;
         max_active = std::max(max_active, scen[i].n_nodes);
+    }
+    // ---- pooled state of all scenarios: one allocation and one memset per column ----
+    CU(B.req_mcpu.alloc((size_t)n * N1)); CU(B.req_mem.alloc((size_t)n * N1)); CU(B.req_eph.alloc((size_t)n * N1));
+    CU(B.nz_mcpu.alloc((size_t)n * N1)); CU(B.nz_mem.alloc((size_t)n * N1)); CU(B.req_scalar.alloc((size_t)n * K1 * N1));
+    CU(B.gpu_used.alloc((size_t)n * SIMON_MAX_GPU_DEV * N1)); CU(B.num_pods.alloc((size_t)n * N1));
+    CU(B.cnt.alloc((size_t)n * cntw)); CU(B.cnt_total.alloc((size_t)n * nct));
+    const size_t tabw = (size_t)SK_MAX_SOFT * ctx->max_dom;
+    CU(B.tp.alloc((size_t)n * tabw)); CU(B.fcount.alloc((size_t)n * tabw)); CU(B.size.alloc((size_t)n * SK_MAX_SOFT));
+    CU(B.hard_reg.alloc((size_t)n * SK_MAX_HARD * ctx->max_dom));
+    CU(B.csum.alloc((size_t)n * ncl * SK_CSUM_W)); CU(B.fbits.alloc((size_t)n * ncl * N1)); CU(B.ocache.alloc((size_t)n * ncl * N1));
+    CU(B.out_node.alloc((size_t)n * P1)); CU(B.counters.alloc((size_t)n * 2)); CU(B.clk.alloc((size_t)n * 2));
+    CU(B.order.alloc((size_t)n * N1)); CU(B.rank_of.alloc((size_t)n * N1)); CU(B.results.alloc(n));
+    CU(cudaMemcpyAsync(B.order.p, B.h_order.data(), 4ull * n * N1, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B.rank_of.p, B.h_rank.data(), 4ull * n * N1, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(B.req_mcpu.p, 0, 8ull * n * N1, st)); CU(cudaMemsetAsync(B.req_mem.p, 0, 8ull * n * N1, st));
+    CU(cudaMemsetAsync(B.req_eph.p, 0, 8ull * n * N1, st)); CU(cudaMemsetAsync(B.nz_mcpu.p, 0, 8ull * n * N1, st));
+    CU(cudaMemsetAsync(B.nz_mem.p, 0, 8ull * n * N1, st)); CU(cudaMemsetAsync(B.req_scalar.p, 0, 8ull * n * K1 * N1, st));
+    CU(cudaMemsetAsync(B.gpu_used.p, 0, 8ull * n * SIMON_MAX_GPU_DEV * N1, st)); CU(cudaMemsetAsync(B.num_pods.p, 0, 4ull * n * N1, st));
+    CU(cudaMemsetAsync(B.cnt.p, 0, 4ull * n * cntw, st)); CU(cudaMemsetAsync(B.cnt_total.p, 0, 4ull * n * nct, st));
+    // each scenario starts from an empty state: no stored class summary / own-score cache may survive from an earlier
+    // call (another node list!); fbits are only read under a valid summary record
+    CU(cudaMemsetAsync(B.csum.p, 0, 8ull * n * ncl * SK_CSUM_W, st)); CU(cudaMemsetAsync(B.ocache.p, 0, 8ull * n * ncl * N1, st));
+    CU(cudaMemsetAsync(B.counters.p, 0, 8ull * n, st)); CU(cudaMemsetAsync(B.clk.p, 0, 16ull * n, st));
+    std::vector<SkScenario> h(n);
+    for (uint32_t i = 0; i < n; i++) {
+        SkScenario &o = h[i];
+        memset(&o, 0, sizeof(o));
+        o.order = ident[i] ? nullptr : B.order.p + (size_t)i * N1;
+        o.rank_of = ident[i] ? nullptr : B.rank_of.p + (size_t)i * N1;
+        o.n_active = scen[i].n_nodes;
+        o.req_mcpu = B.req_mcpu.p + (size_t)i * N1; o.req_mem = B.req_mem.p + (size_t)i * N1; o.req_eph = B.req_eph.p + (size_t)i * N1;
+        o.nz_mcpu = B.nz_mcpu.p + (size_t)i * N1; o.nz_mem = B.nz_mem.p + (size_t)i * N1;
+        o.req_scalar = B.req_scalar.p + (size_t)i * K1 * N1; o.gpu_used = B.gpu_used.p + (size_t)i * SIMON_MAX_GPU_DEV * N1;
+        o.num_pods = B.num_pods.p + (size_t)i * N1; o.cnt = B.cnt.p + (size_t)i * cntw; o.cnt_total = B.cnt_total.p + (size_t)i * nct;
+        o.tp = B.tp.p + (size_t)i * tabw; o.fcount = B.fcount.p + (size_t)i * tabw; o.size = B.size.p + (size_t)i * SK_MAX_SOFT;
+        o.hard_reg = B.hard_reg.p + (size_t)i * SK_MAX_HARD * ctx->max_dom;
+        o.csum = B.csum.p + (size_t)i * ncl * SK_CSUM_W; o.fbits = B.fbits.p + (size_t)i * ncl * N1; o.ocache = B.ocache.p + (size_t)i * ncl * N1;
+        o.out_node = B.out_node.p + (size_t)i * P1; o.out_score = nullptr; o.out_gpu = nullptr;
+        o.fail_counts = nullptr; o.fail_pod = nullptr; o.n_fail = B.counters.p + 2ull * i; o.n_sched = B.counters.p + 2ull * i + 1;
+        o.clk = B.clk.p + 2ull * i;
     }
     CU(ctx->d_scen.upload(h.data(), n, st));
     uint32_t CS, TPB, NPT;
     size_t smem;
     int rc = choose_geometry(ctx, max_active, CS, TPB, NPT, smem);
     if (rc) return rc;
-    SkParams P;
-    fill_params(ctx, P);
-    P.first = 0; P.count = ctx->n_pods; P.max_fail = 0; P.npt = NPT; P.scen = ctx->d_scen.p;
-    rc = launch(ctx, P, n, CS, TPB, smem);
+    SkParams Pm;
+    fill_params(ctx, Pm);
+    Pm.first = 0; Pm.count = ctx->n_pods; Pm.max_fail = 0; Pm.npt = NPT; Pm.scen = ctx->d_scen.p;
+    rc = launch(ctx, Pm, n, CS, TPB, smem);
     if (rc) return rc;
+    // per-scenario sums over the active nodes on the device; ONE copy of the result structs comes back
+    simon_scen_reduce<<<n, 256, 0, st>>>(ctx->d_scen.p, ctx->d_alloc_mcpu.p, ctx->d_alloc_mem.p, B.results.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, B.results.p, sizeof(simon_scenario_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (out_node) CU(cudaMemcpyAsync(out_node, B.out_node.p, 4ull * n * P, cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
     CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-    std::vector<int64_t> rq(ctx->N), rm(ctx->N);
-    for (uint32_t i = 0; i < n; i++) {
-        ScenState &s = *ctx->scen_states[i];
-        uint32_t counters[2];
-        unsigned long long clk[2];
-        CU(cudaMemcpy(counters, s.counters.p, 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(clk, s.clk.p, 16, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(rq.data(), s.req_mcpu.p, 8ull * ctx->N, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(rm.data(), s.req_mem.p, 8ull * ctx->N, cudaMemcpyDeviceToHost));
-        simon_scenario_result &o = out[i];
-        memset(&o, 0, sizeof(o));
-        o.n_unscheduled = counters[0];
-        o.n_scheduled = counters[1];
-        for (uint32_t r = 0; r < scen[i].n_nodes; r++) {
-            uint32_t g = scen[i].nodes[r];
-            o.req_mcpu += rq[g]; o.req_mem += rm[g];
-            o.alloc_mcpu += ctx->h_alloc_mcpu[g]; o.alloc_mem += ctx->h_alloc_mem[g];
-        }
-        o.elapsed_ms = (float)((double)(clk[1] - clk[0]) * 1e-6);
-        if (out_node) CU(cudaMemcpy(out_node + (size_t)i * ctx->n_pods, s.out_node.p, 4ull * ctx->n_pods, cudaMemcpyDeviceToHost));
-    }
+    return SIMON_OK;
+}
+
+int simon_debug_set_dump_pod(simon_ctx *ctx, uint32_t pod) {
+    if (!ctx) return SIMON_ERR_INVALID;
+    ctx->dump_pod = pod;
+    return SIMON_OK;
+}
+
+int simon_debug_dump_read(simon_ctx *ctx, int64_t *out_total, int32_t *out_code) {
+    if (!ctx || !ctx->have_pods) return SIMON_ERR_STATE;
+    CU(cudaSetDevice(ctx->device));
+    if (out_total) CU(cudaMemcpy(out_total, ctx->d_dump_total.p, 8ull * ctx->N, cudaMemcpyDeviceToHost));
+    if (out_code) CU(cudaMemcpy(out_code, ctx->d_dump_code.p, 4ull * ctx->N, cudaMemcpyDeviceToHost));
+    return SIMON_OK;
+}
+
+int simon_gpu_slots_download(simon_ctx *ctx, uint32_t first, uint32_t count, uint32_t *out_slots) {
+    if (!ctx || !ctx->have_pods || !out_slots) return SIMON_ERR_STATE;
+    if ((uint64_t)first + count > ctx->n_pods) return fail(ctx, SIMON_ERR_INVALID, "range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(out_slots, ctx->st.out_gpu.p + first, 4ull * count, cudaMemcpyDeviceToHost));
+    return SIMON_OK;
+}
+
+int simon_state_download_ext(simon_ctx *ctx, int64_t *req_scalar, int64_t *gpu_used) {
+    if (!ctx || !ctx->have_pods) return SIMON_ERR_STATE;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t N = ctx->N;
+    if (req_scalar && ctx->K) CU(cudaMemcpy(req_scalar, ctx->st.req_scalar.p, 8ull * ctx->K * N, cudaMemcpyDeviceToHost));
+    if (gpu_used) CU(cudaMemcpy(gpu_used, ctx->st.gpu_used.p, 8ull * SIMON_MAX_GPU_DEV * N, cudaMemcpyDeviceToHost));
     return SIMON_OK;
 }
 

@@ -462,6 +462,10 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
                 alloc_eph[i] += q.int_value()
             elif name in scalar_names:
                 alloc_scalar[scalar_names.index(name), i] += q.int_value()
+        # leastRequestedScore computes (capacity - requested) * 100 in int64 (least_allocated.go:108-117): a capacity of
+        # 2^63 / 100 or more overflows in the reference too; refuse rather than reproduce the wrap-around
+        if max(int(alloc_mcpu[i]), int(alloc_mem[i])) >= (1 << 63) // 100:
+            raise CompileError(f"node {O.name_of(n)}: allocatable cpu/memory of 2^63/100 or more")
         if (n.get("spec") or {}).get("unschedulable"):
             node_flags[i] |= NODE_UNSCHEDULABLE
         if len(node_labels[i]) > 0:
@@ -547,6 +551,10 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
                 if t is None:
                     raise CompileError("invalid preferred node affinity term")   # NewPreferredSchedulingTerms errors out
                 prefs.append((w, t))
+        # the engine keeps raw NodeAffinity scores as int32 (the reference sums int64, node_affinity.go:77-107): API-valid
+        # weights are 1..100, so the sum fits unless the input is not a valid PodSpec - refuse instead of narrowing silently
+        if sum(abs(w) for w, _t in prefs) >= (1 << 31):
+            raise CompileError("preferred node affinity weights sum to 2^31 or more")
         class_sel.append((ns_reqs, has_required, terms, prefs))
     n_atoms = len(atoms.items)
     WL = max(1, (n_atoms + 63) // 64)
@@ -924,6 +932,10 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
         put(SCW_OFF_IPA_SCORE)
         sc = sorted((k, v) for k, v in L["score"].items())
         w[SCW_N_IPA_SCORE] = len(sc)
+        # raw InterPodAffinity scores (sum of weight x matching pods, scoring.go:224-243) are kept as int32 on the device:
+        # bound them by the number of pods of the list
+        if sum(abs(v) for _k, v in sc) * max(1, len(pods)) >= (1 << 31):
+            raise CompileError(f"class {c.cid}: inter-pod affinity weights x pod count can exceed 2^31")
         for (kid, t), wt in sc:
             body.extend((kid, t, wt))
         put(SCW_OFF_INC)

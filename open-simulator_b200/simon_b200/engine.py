@@ -19,7 +19,8 @@ _LIB = None
 
 EXPORTS = ["simon_gpu_version", "simon_ctx_create", "simon_ctx_destroy", "simon_last_error", "simon_snapshot_upload",
            "simon_pods_upload", "simon_state_reset", "simon_schedule", "simon_results_download", "simon_last_kernel_ms",
-           "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay", "simon_stats"]
+           "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay", "simon_stats",
+           "simon_gpu_slots_download", "simon_state_download_ext", "simon_debug_set_dump_pod", "simon_debug_dump_read"]
 
 
 class EngineUnavailable(RuntimeError):
@@ -62,6 +63,14 @@ def lib():
     L.simon_state_download.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.simon_scenarios_run.restype = C.c_int
     L.simon_scenarios_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.simon_gpu_slots_download.restype = C.c_int
+    L.simon_gpu_slots_download.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.simon_state_download_ext.restype = C.c_int
+    L.simon_state_download_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simon_debug_set_dump_pod.restype = C.c_int
+    L.simon_debug_set_dump_pod.argtypes = [C.c_void_p, C.c_uint32]
+    L.simon_debug_dump_read.restype = C.c_int
+    L.simon_debug_dump_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _LIB = L
     return L
 
@@ -145,6 +154,7 @@ class Engine:
         a = np.zeros(32, np.uint64)
         self._check(lib().simon_stats(self.h, a.ctypes.data))
         return dict(decisions=int(a[0]), class_switches=int(a[1]), summary_rebuilds=int(a[2]), redone=int(a[3]), static_evals=int(a[4]), single_flip_fast=int(a[6]),
+                    merged_decisions=int(a[7] & 0xffffffff), merged_redone=int(a[7] >> 32),
                     cycles=dict(zip(['loop', 'fixed', 'class_change_tail', 'r1', 'p1', 'reduce_steady', 'reduce_summary', 'p3', 'argmax', 'commit',
                                      'cc_pre', 'cc_sync', 'cc_blob', 'cc_entry', 'cc_static', 'pts_pass_steady'],
                                     [int(x) for x in a[8:24]])),
@@ -163,6 +173,36 @@ class Engine:
         arrs = [np.zeros(N, np.int64) for _ in range(5)] + [np.zeros(N, np.int32)]
         self._check(lib().simon_state_download(self.h, *[a.ctypes.data for a in arrs]))
         return dict(zip(["req_mcpu", "req_mem", "req_eph", "nz_mcpu", "nz_mem", "num_pods"], arrs))
+
+    def gpu_slots(self, first: int = 0, count: Optional[int] = None):
+        """GPU-share Reserve results: per pod a list of device ids (one per GPU slot, ascending), [] if none."""
+        P = self.c.pods_dims["n_pods"]
+        count = P - first if count is None else count
+        a = np.zeros(max(count, 1), np.uint32)
+        self._check(lib().simon_gpu_slots_download(self.h, first, count, a.ctypes.data))
+        out = []
+        for v in a[:count]:
+            v = int(v)
+            out.append([d for d in range(8) for _ in range((v >> (4 * d)) & 15)])
+        return out
+
+    def state_ext(self):
+        N, K = self.c.n_nodes, int(self.c.snap_dims["n_scalars"])
+        rs = np.zeros((max(K, 1), max(N, 1)), np.int64)
+        gu = np.zeros((8, max(N, 1)), np.int64)
+        self._check(lib().simon_state_download_ext(self.h, rs.ctypes.data, gu.ctypes.data))
+        return dict(req_scalar=rs[:K, :N], gpu_used=gu[:, :N])
+
+    def dump_pod(self, pod: int):
+        """Schedule up to and including `pod`; return (out_node of the range, per-node totals, per-node filter verdicts)."""
+        self._check(lib().simon_debug_set_dump_pod(self.h, pod))
+        out = self.schedule(0, pod + 1)[0]
+        self._check(lib().simon_debug_set_dump_pod(self.h, 0xffffffff))
+        N = self.c.n_nodes
+        tot = np.zeros(max(N, 1), np.int64)
+        code = np.zeros(max(N, 1), np.int32)
+        self._check(lib().simon_debug_dump_read(self.h, tot.ctypes.data, code.ctypes.data))
+        return out, tot[:N], code[:N]
 
     def run_scenarios(self, scenarios: List[np.ndarray], want_nodes: bool = False):
         """scenarios: list of uint32 arrays (active node indices in scenario order)."""

@@ -87,7 +87,7 @@ def test_abi_library_exports():
     for name in declared:
         assert hasattr(L, name), name
     assert set(engine.EXPORTS) == declared
-    assert L.simon_gpu_version() == 1
+    assert L.simon_gpu_version() == 2
 
 
 def test_open_local_pods_are_refused_at_compile_time():
@@ -151,3 +151,38 @@ def test_unsupported_simulate_options_are_refused():
                 simulator.WithExtraRegistry({"x": object()})):
         with pytest.raises(NotImplementedError):
             simulator.Simulate(ResourceTypes(), [], opt)
+
+
+def test_numeric_ranges_are_proven_at_compile_time():
+    """The device keeps some raw scores in 32 bits and divides (capacity - requested) * 100 exactly below 2^63: inputs that
+    could leave those ranges are refused by the snapshot compiler, never narrowed silently."""
+    from simon_b200 import simulator
+    from simon_b200.compiler import CompileError, compile_cluster
+    from simon_b200.objects import AppResource, ResourceTypes
+
+    def cluster(mem="8Gi"):
+        cl = ResourceTypes()
+        cl.Nodes.append({"kind": "Node", "metadata": {"name": "n1", "labels": {"kubernetes.io/hostname": "n1", "disk": "ssd"}}, "spec": {},
+                         "status": {"allocatable": {"cpu": "4", "memory": mem, "pods": "110"}}})
+        return cl
+
+    def one(spec_extra=None, mem="8Gi"):
+        app = AppResource("a", ResourceTypes())
+        spec = {"containers": [{"name": "c", "image": "x"}]}
+        spec.update(spec_extra or {})
+        app.Resource.Pods.append({"kind": "Pod", "metadata": {"name": "p", "namespace": "default", "labels": {"app": "x"}}, "spec": spec})
+        p = simulator.plan(cluster(mem), [app])
+        return compile_cluster(p.nodes, p.pods, p.ctx)
+
+    one()
+    with pytest.raises(CompileError, match="2\\^63/100"):
+        one(mem=str((1 << 63) // 100))
+    big = {"affinity": {"nodeAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+        {"weight": 1 << 30, "preference": {"matchExpressions": [{"key": "disk", "operator": "In", "values": ["ssd"]}]}},
+        {"weight": 1 << 30, "preference": {"matchExpressions": [{"key": "disk", "operator": "Exists"}]}}]}}}
+    with pytest.raises(CompileError, match="2\\^31"):
+        one(big)
+    ipa = {"affinity": {"podAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+        {"weight": 1 << 31, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "x"}}, "topologyKey": "kubernetes.io/hostname"}}]}}}
+    with pytest.raises(CompileError, match="2\\^31"):
+        one(ipa)

@@ -41,6 +41,19 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
         }
         else if (mode == 12) { uint32_t v[6] = {(uint32_t)acc, (uint32_t)acc + 1, (uint32_t)acc + 2, (uint32_t)acc + 3, (uint32_t)acc & 1, 1u}; const int op[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM}; sk_allreduce_w<6>(R, v, op); acc += v[1] + v[5]; }
         else if (mode == 13) { uint32_t v[22]; for (int q = 0; q < 22; q++) v[q] = (uint32_t)acc + q; const int op[22] = {0,0,2,2,2,1,1,2,1,2,3,3,3,3,3,3,3,3,3,3,3,3}; sk_allreduce_w<22>(R, v, op); acc += v[2] + v[0]; }
+        else if (mode == 14) {  // merged arg-max: key + payload + 7 words in ONE exchange
+            uint32_t who; uint32_t xw[7] = {(uint32_t)acc, (uint32_t)acc + 1, (uint32_t)acc + 2, (uint32_t)acc + 3, (uint32_t)acc & 1, 1u, 0u};
+            const int xop[7] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM, W_SUM};
+            const uint32_t ct = cluster.num_blocks() * blockDim.x;
+            sk_argmaxx_send<7>(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), ct, blockDim.x, xw, xop);
+            unsigned long long k = sk_argmaxx_wait<7>(R, who, xw, xop); acc += k + sk_wpay(S, who, 0) + xw[1] + xw[5];
+        }
+        else if (mode == 15) {  // what the merged form replaces: allreduce_w<7> followed by the plain arg-max
+            uint32_t who; uint32_t xw[7] = {(uint32_t)acc, (uint32_t)acc + 1, (uint32_t)acc + 2, (uint32_t)acc + 3, (uint32_t)acc & 1, 1u, 0u};
+            const int xop[7] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM, W_SUM};
+            sk_allreduce_w<7>(R, xw, xop);
+            unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, who); acc += k + sk_wpay(S, who, 0) + xw[1] + xw[5];
+        }
         else if (mode == 11) {  // CTA-level combine: per-warp slots + __syncthreads + every warp folds
             unsigned *a = (unsigned *)S.wpart + (i & 1) * 32;
             unsigned x = __reduce_max_sync(0xffffffffu, (unsigned)acc + threadIdx.x);
@@ -54,8 +67,8 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
 
 int main() {
     long long *d; cudaMalloc(&d, 64);
-    const char *names[14] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "10x redux.max.u32 (dependent)", "10x warp_maxu64 (dependent)", "st.async self + mbar wait", "st.async next CTA + mbar wait", "redux+smem atomicMax+bar", "redux+slots+bar+fold", "allreduce_w<6> (32-bit words)", "allreduce_w<22> (32-bit words)"};
-    for (int cs : {1, 4, 16}) for (int tpb : {128, 256}) for (int mode = 0; mode < 14; mode++) {
+    const char *names[16] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "10x redux.max.u32 (dependent)", "10x warp_maxu64 (dependent)", "st.async self + mbar wait", "st.async next CTA + mbar wait", "redux+smem atomicMax+bar", "redux+slots+bar+fold", "allreduce_w<6> (32-bit words)", "allreduce_w<22> (32-bit words)", "merged arg-max + 7 words (1 exchange)", "allreduce_w<7> + arg-max (2 exchanges)"};
+    for (int cs : {1, 2, 4, 8, 16}) for (int tpb : {256, 320}) for (int mode = 0; mode < 16; mode++) {
         size_t smem = sk_smem_bytes(tpb, 2, 4, 64, cs);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
