@@ -304,6 +304,40 @@ int simon_state_download_ext(simon_ctx *ctx, int64_t *req_scalar, int64_t *gpu_u
 int simon_debug_set_dump_pod(simon_ctx *ctx, uint32_t pod);
 int simon_debug_dump_read(simon_ctx *ctx, int64_t *out_total, int32_t *out_code);
 
+/* ---- candidate-move scoring for defragmentation / rebalancing (BASELINE config 5) ----------------------------------
+ * The reference names the use case (README.md:16) and provides the primitive, NodeInfo.RemovePod
+ * (K8S/framework/types.go:539-585); it has no implementation of the scoring itself, so the definition is this library's:
+ * a move (pod, target) is evaluated on the live state left by simon_schedule, with the pod taken off its current node
+ * (RemovePod: requests, non-zero requests, pod count, its own increments of its class's counters):
+ *   code = 0 if every filter of this path passes on the target, else the failing filter's reasons as a bitmask of
+ *          (1 << simon_fail_code), or one of SIMON_MOVE_*;
+ *   gain = (LeastAllocated + BalancedAllocation of the target for the pod) - (the same of its current node, pod removed first).
+ * simon_moves_upload copies a move list to the device (move_base = global index of moves[0] when the list is one GPU's
+ * contiguous shard); simon_moves_run scores it and returns, each optional: per-move gain / code, per pod the best feasible
+ * move as key = (gain + 1000) << 32 | (0xffffffff - global move index) (0: none), and the top-k moves by (gain descending,
+ * global move index ascending).  simon_moves_replay repeats the scoring `steps` times, results left on the device
+ * (device time by CUDA events). */
+#define SIMON_MOVE_NOOP (1u << 24)         /* target is the pod's current node */
+#define SIMON_MOVE_NOT_PLACED (1u << 25)   /* the pod is not running on a node of the snapshot */
+#define SIMON_MOVE_NOT_MOVABLE (1u << 26)  /* class with DoNotSchedule spread constraints or a GPU-share request */
+#define SIMON_MOVE_BAD_INDEX (1u << 27)
+#define SIMON_MOVE_GAIN_BIAS 1000
+
+typedef struct simon_move { uint32_t pod, target; } simon_move;
+typedef struct simon_move_rank { uint32_t move; int32_t gain; } simon_move_rank;
+typedef struct simon_moves_result {
+    uint64_t best_key;       /* best feasible move of the list, same key format as per pod; 0 if none */
+    uint32_t n_feasible;
+    uint32_t n_topk;         /* entries written to out_topk (min(k, n_feasible)) */
+    float kernel_ms;         /* device time of the pack + scoring kernels */
+    uint32_t reserved;
+} simon_moves_result;
+
+int simon_moves_upload(simon_ctx *ctx, const simon_move *moves, uint32_t n_moves, uint32_t move_base);
+int simon_moves_run(simon_ctx *ctx, uint32_t k, int32_t *out_gain, uint32_t *out_code, uint64_t *out_best_per_pod,
+                    simon_move_rank *out_topk, simon_moves_result *out);
+int simon_moves_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 #include "simon_kernel.cuh"
 
 #include "simon_kernel.cu"   // single translation unit: kernel + host API
+#include "simon_moves.cu"    // candidate-move scoring kernels (config 5)
 
 namespace {
 
@@ -134,6 +135,14 @@ struct simon_ctx {
     DevBuf<long long> d_dump_total;
     DevBuf<int32_t> d_dump_code;
     uint32_t fast = 3;
+    // candidate-move scoring (simon_moves_*)
+    DevBuf<uint2> d_moves;
+    DevBuf<int32_t> d_mv_gain;
+    DevBuf<uint32_t> d_mv_code, d_mv_hist, d_mv_topn;
+    DevBuf<unsigned long long> d_mv_best_pod, d_mv_best;
+    DevBuf<uint2> d_mv_topk;
+    DevBuf<SmvNode> d_mv_nodes;
+    uint32_t mv_n = 0, mv_base = 0;
     // single-scenario state
     ScenState st;
     uint32_t max_fail = 0;
@@ -743,6 +752,119 @@ int simon_state_download_ext(simon_ctx *ctx, int64_t *req_scalar, int64_t *gpu_u
     const uint32_t N = ctx->N;
     if (req_scalar && ctx->K) CU(cudaMemcpy(req_scalar, ctx->st.req_scalar.p, 8ull * ctx->K * N, cudaMemcpyDeviceToHost));
     if (gpu_used) CU(cudaMemcpy(gpu_used, ctx->st.gpu_used.p, 8ull * SIMON_MAX_GPU_DEV * N, cudaMemcpyDeviceToHost));
+    return SIMON_OK;
+}
+
+// ---- candidate-move scoring (config 5) ------------------------------------------------------------------------------
+static int moves_launch(simon_ctx *ctx, bool record) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t N = ctx->N, n = ctx->mv_n;
+    CU(cudaMemsetAsync(ctx->d_mv_best_pod.p, 0, 8ull * std::max(1u, ctx->n_pods), st));
+    CU(cudaMemsetAsync(ctx->d_mv_best.p, 0, 8, st));
+    CU(cudaMemsetAsync(ctx->d_mv_hist.p, 0, 4ull * SMV_NBINS, st));
+    if (record) CU(cudaEventRecord(ctx->ev0, st));
+    if (N) simon_moves_pack<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->T, ctx->d_alloc_mcpu.p, ctx->d_alloc_mem.p, ctx->d_alloc_eph.p, ctx->d_alloc_pods.p,
+                                                            ctx->d_topo_dom.p, ctx->st.req_mcpu.p, ctx->st.req_mem.p, ctx->st.req_eph.p,
+                                                            ctx->st.nz_mcpu.p, ctx->st.nz_mem.p, ctx->st.num_pods.p, ctx->d_mv_nodes.p);
+    SmvParams P;
+    memset(&P, 0, sizeof(P));
+    P.N = N; P.K = ctx->K; P.WT = ctx->WT; P.T = ctx->T; P.n_pods = ctx->n_pods; P.n_moves = n; P.use_scache = ctx->use_scache;
+    P.nodes = ctx->d_mv_nodes.p; P.alloc_scalar = ctx->d_alloc_scalar.p; P.req_scalar = ctx->st.req_scalar.p; P.node_flags = ctx->d_node_flags.p;
+    P.label_bits = ctx->d_label_bits.p; P.taint_hard = ctx->d_taint_hard.p; P.topo_dom = ctx->d_topo_dom.p;
+    P.class_off = ctx->d_class_off.p; P.class_blob = ctx->d_class_blob.p; P.pod_class = ctx->d_pod_class.p; P.placement = ctx->st.out_node.p;
+    P.cnt = ctx->st.cnt.p; P.cnt_total = ctx->st.cnt_total.p; P.scache = ctx->d_scache.p; P.moves = ctx->d_moves.p;
+    P.out_gain = ctx->d_mv_gain.p; P.out_code = ctx->d_mv_code.p; P.best_per_pod = ctx->d_mv_best_pod.p; P.best_global = ctx->d_mv_best.p;
+    P.hist = ctx->d_mv_hist.p; P.move_base = ctx->mv_base;
+    if (n) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const uint32_t grid = std::min<uint32_t>((n + 255) / 256, (uint32_t)sms * 8);      // 8 resident CTAs of 256 threads per SM
+        simon_moves_kernel<<<grid, 256, 0, st>>>(P);
+        ctx->launches++;
+    }
+    if (record) CU(cudaEventRecord(ctx->ev1, st));
+    CU(cudaGetLastError());
+    return SIMON_OK;
+}
+
+int simon_moves_upload(simon_ctx *ctx, const simon_move *moves, uint32_t n_moves, uint32_t move_base) {
+    if (!ctx || (!moves && n_moves)) return SIMON_ERR_INVALID;
+    if (!ctx->have_pods) return fail(ctx, SIMON_ERR_STATE, "simon_moves_upload before uploads");
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(simon_move) == sizeof(uint2), "simon_move layout");
+    CU(ctx->d_moves.upload(reinterpret_cast<const uint2 *>(moves), n_moves, ctx->stream));
+    CU(ctx->d_mv_gain.alloc(n_moves)); CU(ctx->d_mv_code.alloc(n_moves)); CU(ctx->d_mv_hist.alloc(SMV_NBINS)); CU(ctx->d_mv_topn.alloc(2));
+    CU(ctx->d_mv_best_pod.alloc(std::max(1u, ctx->n_pods))); CU(ctx->d_mv_best.alloc(1)); CU(ctx->d_mv_nodes.alloc(std::max(1u, ctx->N)));
+    ctx->mv_n = n_moves; ctx->mv_base = move_base;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SIMON_OK;
+}
+
+int simon_moves_run(simon_ctx *ctx, uint32_t k, int32_t *out_gain, uint32_t *out_code, uint64_t *out_best_per_pod,
+                    simon_move_rank *out_topk, simon_moves_result *out) {
+    if (!ctx || !out) return SIMON_ERR_INVALID;
+    if (!ctx->have_pods || !ctx->d_moves.p) return fail(ctx, SIMON_ERR_STATE, "simon_moves_run before simon_moves_upload");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = ctx->mv_n;
+    int rc = moves_launch(ctx, true);
+    if (rc) return rc;
+    uint32_t hist[SMV_NBINS];
+    unsigned long long best = 0;
+    CU(cudaMemcpyAsync(hist, ctx->d_mv_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&best, ctx->d_mv_best.p, 8, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "move kernel failed: %s", cudaGetErrorString(e));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    uint64_t feas = 0;
+    for (int b = 0; b < SMV_NBINS; b++) feas += hist[b];
+    memset(out, 0, sizeof(*out));
+    out->best_key = best; out->n_feasible = (uint32_t)std::min<uint64_t>(feas, 0xffffffffu); out->kernel_ms = ctx->last_ms;
+    // top-k by (gain descending, move index ascending): threshold gain from the histogram, then one ordered collection pass
+    uint32_t kk = (uint32_t)std::min<uint64_t>(k, feas);
+    if (kk && out_topk) {
+        uint64_t cum = 0;
+        int thr = -201;
+        uint32_t n_gt = 0, need_eq = 0;
+        for (int b = SMV_NBINS - 1; b >= 0; b--) {
+            if (cum + hist[b] >= kk) { thr = b - 200; n_gt = (uint32_t)cum; need_eq = kk - (uint32_t)cum; break; }
+            cum += hist[b];
+        }
+        CU(ctx->d_mv_topk.alloc(2ull * kk));
+        simon_moves_collect<<<1, 1024, 0, st>>>(n, ctx->d_mv_gain.p, ctx->d_mv_code.p, thr, need_eq, kk, ctx->mv_base, ctx->d_mv_topk.p, ctx->d_mv_topn.p);
+        CU(cudaGetLastError());
+        std::vector<uint2> tk(2ull * kk);
+        CU(cudaMemcpyAsync(tk.data(), ctx->d_mv_topk.p, 16ull * kk, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<simon_move_rank> r;
+        for (uint32_t q = 0; q < n_gt; q++) r.push_back({tk[q].x, (int32_t)tk[q].y});
+        for (uint32_t q = 0; q < need_eq; q++) r.push_back({tk[kk + q].x, (int32_t)tk[kk + q].y});
+        std::sort(r.begin(), r.end(), [](const simon_move_rank &x, const simon_move_rank &y) { return x.gain != y.gain ? x.gain > y.gain : x.move < y.move; });
+        for (uint32_t q = 0; q < kk; q++) out_topk[q] = r[q];
+        out->n_topk = kk;
+    }
+    if (out_gain && n) CU(cudaMemcpyAsync(out_gain, ctx->d_mv_gain.p, 4ull * n, cudaMemcpyDeviceToHost, st));
+    if (out_code && n) CU(cudaMemcpyAsync(out_code, ctx->d_mv_code.p, 4ull * n, cudaMemcpyDeviceToHost, st));
+    if (out_best_per_pod && ctx->n_pods) CU(cudaMemcpyAsync(out_best_per_pod, ctx->d_mv_best_pod.p, 8ull * ctx->n_pods, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIMON_OK;
+}
+
+int simon_moves_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total) {
+    if (!ctx) return SIMON_ERR_INVALID;
+    if (!ctx->have_pods || !ctx->d_moves.p) return fail(ctx, SIMON_ERR_STATE, "simon_moves_replay before simon_moves_upload");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, st));
+    for (uint32_t s = 0; s < steps; s++) {
+        int rc = moves_launch(ctx, false);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev1, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "move kernel failed: %s", cudaGetErrorString(e));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (out_ms_total) *out_ms_total = ctx->last_ms;
     return SIMON_OK;
 }
 

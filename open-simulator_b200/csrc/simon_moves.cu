@@ -1,0 +1,264 @@
+// simon_moves.cu — candidate-move scoring for defragmentation / rebalancing (BASELINE config 5).
+//
+// The reference has no implementation of this path (README.md:16 names the use case only); what it offers is the
+// primitive a rebalancer needs, NodeInfo.RemovePod (vendor/k8s.io/kubernetes/pkg/scheduler/framework/types.go:539-585),
+// and the scheduling path restated by this engine.  The definition below is therefore this repository's (DESIGN.md
+// section 5) and parity is against oracle/simon_oracle.c:simon_oracle_moves_score.
+//
+// A move m = (pod p, target node b) is evaluated on the LIVE state the context holds after simon_schedule, with p taken
+// off its current node a = placement[p] (RemovePod: requests, non-zero requests, pod count and p's own increments of the
+// class's counters at a's domains):
+//   code  = first failing filter of this path for p's class on b, in the path's order: static verdict (NodeUnschedulable,
+//           NodeName, TaintToleration, NodeAffinity), NodePorts, NodeResourcesFit, InterPodAffinity (required affinity,
+//           required anti-affinity, existing pods' anti-affinity), or SMV_* for moves that are not candidates;
+//   gain  = [LeastAllocated + BalancedAllocation of b for p]  -  [the same of a for p, with p removed first]
+//           i.e. how much better the scheduler's own node-local score likes p on b than where it sits.
+// Every move is independent: one thread per move over a read-only snapshot.  Node columns are packed per launch into one
+// 96-byte record per node (three 32-byte sectors) so that the two random gathers per move (target, source) cost six
+// sectors instead of two dozen; the move list itself streams through coalesced 8-byte loads.
+#pragma once
+
+struct __align__(32) SmvNode {          // 96 bytes
+    int64_t alloc_mcpu, alloc_mem, alloc_eph, req_mcpu;
+    int64_t req_mem, req_eph, nz_mcpu, nz_mem;
+    int32_t alloc_pods, num_pods;
+    int32_t dom[6];                     // domains of topologies 1..6 (topology 0 is the node itself)
+};
+static_assert(sizeof(SmvNode) == 96, "SmvNode layout");
+
+#define SMV_OK 0u
+#define SMV_NOOP (1u << 24)            // target == current node
+#define SMV_NOT_PLACED (1u << 25)      // the pod is not running anywhere (unscheduled / absent / bound outside the cluster)
+#define SMV_NOT_MOVABLE (1u << 26)     // class with DoNotSchedule spread constraints or a GPU-share request: not a candidate
+#define SMV_BAD_INDEX (1u << 27)
+#define SMV_GAIN_BIAS 1000
+#define SMV_NBINS 401                  // gains lie in [-200, 200]
+
+struct SmvParams {
+    uint32_t N, K, WT, T, n_pods, n_moves, use_scache, pad;
+    const SmvNode *nodes;
+    const int64_t *alloc_scalar, *req_scalar;
+    const uint32_t *node_flags;
+    const uint64_t *label_bits, *taint_hard;
+    const int32_t *topo_dom;
+    const uint64_t *class_off;
+    const int64_t *class_blob;
+    const int32_t *pod_class, *placement;
+    const int32_t *cnt, *cnt_total;
+    unsigned long long *scache;
+    const uint2 *moves;                 // (pod, target)
+    int32_t *out_gain;
+    uint32_t *out_code;
+    unsigned long long *best_per_pod;   // [n_pods] max over the pod's feasible moves of (gain + bias) << 32 | ~move index; 0 = none
+    unsigned long long *best_global;    // [1]
+    uint32_t *hist;                     // [SMV_NBINS] feasible moves per gain
+    uint32_t move_base, pad2;           // global index of moves[0] (multi-GPU shards)
+};
+
+__global__ void simon_moves_pack(uint32_t N, uint32_t T, const int64_t *alloc_mcpu, const int64_t *alloc_mem, const int64_t *alloc_eph,
+                                 const int32_t *alloc_pods, const int32_t *topo_dom, const int64_t *req_mcpu, const int64_t *req_mem,
+                                 const int64_t *req_eph, const int64_t *nz_mcpu, const int64_t *nz_mem, const int32_t *num_pods, SmvNode *out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    SmvNode r;
+    r.alloc_mcpu = alloc_mcpu[g]; r.alloc_mem = alloc_mem[g]; r.alloc_eph = alloc_eph[g];
+    r.req_mcpu = req_mcpu[g]; r.req_mem = req_mem[g]; r.req_eph = req_eph[g]; r.nz_mcpu = nz_mcpu[g]; r.nz_mem = nz_mem[g];
+    r.alloc_pods = alloc_pods[g]; r.num_pods = num_pods[g];
+#pragma unroll
+    for (int t = 0; t < 6; t++) r.dom[t] = (uint32_t)(t + 1) < T ? topo_dom[(uint64_t)(t + 1) * N + g] : -1;
+    out[g] = r;
+}
+
+__device__ __forceinline__ SmvNode smv_load(const SmvNode *p) {
+    SmvNode r;
+    const int4 *q = reinterpret_cast<const int4 *>(p);
+    int4 *d = reinterpret_cast<int4 *>(&r);
+#pragma unroll
+    for (int i = 0; i < 6; i++) d[i] = __ldg(q + i);
+    return r;
+}
+
+// LeastAllocated + BalancedAllocation for a pod with scoring request (sc, sm) on a node whose NonZeroRequested is (nzc, nzm)
+// (least_allocated.go:93-117, balanced_allocation.go:82-119); same arithmetic as the placement kernel's own_core
+__device__ __forceinline__ int32_t smv_own(int64_t capc, int64_t capm, int64_t nzc, int64_t nzm, int64_t sc, int64_t sm) {
+    const int64_t rqc = nzc + sc, rqm = nzm + sm;
+    const int64_t s1 = (capc == 0 || rqc > capc) ? 0 : ((capc - rqc) * 100) / capc;
+    const int64_t s2 = (capm == 0 || rqm > capm) ? 0 : ((capm - rqm) * 100) / capm;
+    const int64_t la = (s1 + s2) / 2;
+    const double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
+    const double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
+    int64_t ba = 0;
+    if (!(cf >= 1.0 || mf >= 1.0)) ba = f2i((1.0 - fabs(cf - mf)) * 100.0);
+    return (int32_t)(la + ba);
+}
+
+// domain of node g on topology t: topology 0 is the node itself, 1..6 travel in the packed record, 7 (rare) is gathered
+__device__ __forceinline__ int32_t smv_dom(const SmvParams &P, const SmvNode &n, uint32_t g, int64_t t) {
+    if (t == 0) return (int32_t)g;
+    if (t <= 6) {
+        int32_t d = n.dom[0];
+#pragma unroll
+        for (int q = 1; q < 6; q++) d = (t == q + 1) ? n.dom[q] : d;
+        return d;
+    }
+    return __ldg(P.topo_dom + (uint64_t)t * P.N + g);
+}
+
+__global__ void __launch_bounds__(256) simon_moves_kernel(const __grid_constant__ SmvParams P) {
+    __shared__ uint32_t s_hist[SMV_NBINS];
+    for (uint32_t q = threadIdx.x; q < SMV_NBINS; q += blockDim.x) s_hist[q] = 0;
+    __syncthreads();
+    const ReqCtx RC{P.label_bits, P.N};
+    unsigned long long my_best = 0;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < P.n_moves; m += gridDim.x * blockDim.x) {
+        const uint2 mv = __ldg(P.moves + m);
+        const uint32_t pod = mv.x, b = mv.y;
+        uint32_t code = SMV_OK;
+        int32_t gain = 0;
+        int32_t a = -1;
+        if (pod >= P.n_pods || b >= P.N) code = SMV_BAD_INDEX;
+        else {
+            a = __ldg(P.placement + pod);
+            if (a < 0 || (uint32_t)a >= P.N) code = SMV_NOT_PLACED;
+            else if ((uint32_t)a == b) code = SMV_NOOP;
+        }
+        if (code == SMV_OK) {
+            const int32_t cls = __ldg(P.pod_class + pod);
+            const int64_t *cw = P.class_blob + __ldg(P.class_off + cls);
+            if (__ldg(cw + SCW_N_PTS_HARD) > 0 || __ldg(cw + SCW_GPU_MEM) > 0) code = SMV_NOT_MOVABLE;
+            else {
+                const SmvNode nb = smv_load(P.nodes + b), na = smv_load(P.nodes + a);
+                const uint32_t cflags = (uint32_t)__ldg(cw + SCW_FLAGS);
+                // ---- static verdict of (class, b): cached per (static signature, node) by the placement kernel, or computed here
+                const int64_t sig = __ldg(cw + SCW_STATIC_SIG);
+                unsigned long long rec = P.use_scache ? __ldcg(P.scache + (uint64_t)sig * P.N + b) : 0ull;
+                uint32_t st_code;
+                if (rec & (1ull << 24)) st_code = (uint32_t)(rec & 0xff);
+                else {
+                    const bool ok = selection_ok(cw, RC, b);
+                    const int64_t *tol = cw + cw[SCW_OFF_TOL];
+                    st_code = 0;
+                    if ((P.node_flags[b] & SIMON_NODE_UNSCHEDULABLE) && !(cflags & SIMON_CLS_TOL_UNSCHED)) st_code = 1;
+                    if (!st_code && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)b) st_code = 2;
+                    if (!st_code)
+                        for (uint32_t w = 0; w < P.WT; w++)
+                            if (P.taint_hard[(uint64_t)w * P.N + b] & ~(uint64_t)tol[w]) st_code = 3;
+                    if (!st_code && !ok) st_code = 4;
+                }
+                if (st_code) code = 1u << SFC_STATIC;
+                const int64_t *et = cw + cw[SCW_OFF_ENT];
+                const uint32_t n_ports = (uint32_t)cw[SCW_N_PORTS], n_soft = (uint32_t)cw[SCW_N_PTS_SOFT], n_aff = (uint32_t)cw[SCW_N_IPA_AFF];
+                const uint32_t n_anti = (uint32_t)cw[SCW_N_IPA_ANTI], n_exist = (uint32_t)cw[SCW_N_IPA_EXIST];
+                // counter value of entry e at b's domain with p's own contribution (made from node a) removed
+                auto val_at = [&](uint32_t e, int32_t d) -> int32_t {
+                    const int64_t *r = et + 8ull * e;
+                    int32_t v = __ldg(P.cnt + (uint32_t)r[ER_BASE] + (uint32_t)d);
+                    if (r[ER_INC] && smv_dom(P, na, (uint32_t)a, r[ER_T]) == d) v -= 1;
+                    return v;
+                };
+                // ---- NodePorts
+                if (code == SMV_OK)
+                    for (uint32_t e = 0; e < n_ports; e++)
+                        if (val_at(e, (int32_t)b) > 0) { code = 1u << SFC_PORTS; break; }
+                // ---- NodeResourcesFit on b (p is not on b)
+                if (code == SMV_OK) {
+                    uint32_t rs = 0;
+                    if (nb.num_pods + 1 > nb.alloc_pods) rs |= 1u << SFC_TOO_MANY_PODS;
+                    if (cflags & SIMON_CLS_HAS_REQUEST) {
+                        if (nb.alloc_mcpu < cw[SCW_REQ_MCPU] + nb.req_mcpu) rs |= 1u << SFC_CPU;
+                        if (nb.alloc_mem < cw[SCW_REQ_MEM] + nb.req_mem) rs |= 1u << SFC_MEM;
+                        if (nb.alloc_eph < cw[SCW_REQ_EPH] + nb.req_eph) rs |= 1u << SFC_EPH;
+                        const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
+                        for (uint32_t k = 0; k < P.K; k++)
+                            if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * P.N + b] < sc_req[k] + P.req_scalar[(uint64_t)k * P.N + b]) rs |= 1u << (SFC_SCALAR0 + k);
+                    }
+                    code = rs;
+                }
+                // ---- InterPodAffinity (filtering.go:317-401) on the counters, p's own increments taken out
+                const uint32_t e_aff = n_ports + n_soft, e_anti = e_aff + n_aff, e_exist = e_anti + n_anti, e_end = e_exist + n_exist;
+                if (code == SMV_OK && n_aff) {
+                    bool pods_exist = true, missing = false;
+                    long long aff_total = 0;
+                    for (uint32_t e = e_aff; e < e_anti; e++) {
+                        const int64_t *r = et + 8ull * e;
+                        aff_total += __ldg(P.cnt_total + r[ER_K]);
+                        if (r[ER_INC] && smv_dom(P, na, (uint32_t)a, r[ER_T]) >= 0) aff_total -= 1;
+                        const int32_t d = smv_dom(P, nb, b, r[ER_T]);
+                        if (d < 0) { missing = true; continue; }
+                        if (val_at(e, d) <= 0) pods_exist = false;
+                    }
+                    bool ok = true;
+                    if (missing) ok = false;
+                    else if (!pods_exist) ok = aff_total == 0 && (cflags & SIMON_CLS_IPA_SELF_MATCH);
+                    if (!ok) code = 1u << SFC_IPA_AFF;
+                }
+                if (code == SMV_OK)
+                    for (uint32_t e = e_anti; e < e_exist; e++) {
+                        const int32_t d = smv_dom(P, nb, b, (et + 8ull * e)[ER_T]);
+                        if (d >= 0 && val_at(e, d) > 0) { code = 1u << SFC_IPA_ANTI; break; }
+                    }
+                if (code == SMV_OK)
+                    for (uint32_t e = e_exist; e < e_end; e++) {
+                        const int32_t d = smv_dom(P, nb, b, (et + 8ull * e)[ER_T]);
+                        if (d >= 0 && val_at(e, d) > 0) { code = 1u << SFC_IPA_EXIST; break; }
+                    }
+                if (code == SMV_OK) {
+                    const int32_t on_b = smv_own(nb.alloc_mcpu, nb.alloc_mem, nb.nz_mcpu, nb.nz_mem, cw[SCW_SCORE_MCPU], cw[SCW_SCORE_MEM]);
+                    const int32_t on_a = smv_own(na.alloc_mcpu, na.alloc_mem, na.nz_mcpu - cw[SCW_NZ_MCPU], na.nz_mem - cw[SCW_NZ_MEM],
+                                                 cw[SCW_SCORE_MCPU], cw[SCW_SCORE_MEM]);
+                    gain = on_b - on_a;
+                }
+            }
+        }
+        P.out_gain[m] = gain;
+        P.out_code[m] = code;
+        if (code == SMV_OK) {
+            const uint32_t gm = P.move_base + m;
+            const unsigned long long key = ((unsigned long long)(uint32_t)(gain + SMV_GAIN_BIAS) << 32) | (unsigned long long)(0xffffffffu - gm);
+            atomicMax(P.best_per_pod + pod, key);
+            my_best = key > my_best ? key : my_best;
+            int bin = gain + 200;
+            bin = bin < 0 ? 0 : (bin > SMV_NBINS - 1 ? SMV_NBINS - 1 : bin);
+            atomicAdd(&s_hist[bin], 1u);
+        }
+    }
+    my_best = warp_maxu64(my_best);
+    if ((threadIdx.x & 31) == 0 && my_best) atomicMax(P.best_global, my_best);
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < SMV_NBINS; q += blockDim.x)
+        if (s_hist[q]) atomicAdd(P.hist + q, s_hist[q]);
+}
+
+// Top-k by (gain descending, move index ascending): one block scans the move list in index order and keeps every feasible
+// move above the threshold gain plus the first `need_eq` moves exactly at it (the threshold comes from the histogram).
+__global__ void __launch_bounds__(1024) simon_moves_collect(uint32_t n_moves, const int32_t *gain, const uint32_t *code, int32_t thr,
+                                                            uint32_t need_eq, uint32_t k, uint32_t move_base, uint2 *out, uint32_t *out_n) {
+    __shared__ uint32_t s_gt[32], s_eq[32];
+    __shared__ uint32_t base_gt, base_eq;
+    if (threadIdx.x == 0) { base_gt = 0; base_eq = 0; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t m0 = 0; m0 < n_moves; m0 += blockDim.x) {
+        const uint32_t m = m0 + threadIdx.x;
+        bool gt = false, eq = false;
+        int32_t g = 0;
+        if (m < n_moves && code[m] == SMV_OK) { g = gain[m]; gt = g > thr; eq = g == thr; }
+        const uint32_t bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) { s_gt[warp] = __popc(bg); s_eq[warp] = __popc(be); }
+        __syncthreads();
+        uint32_t og = 0, oe = 0;
+        for (uint32_t w = 0; w < warp; w++) { og += s_gt[w]; oe += s_eq[w]; }
+        const uint32_t rg = base_gt + og + __popc(bg & ((1u << lane) - 1u));
+        const uint32_t re = base_eq + oe + __popc(be & ((1u << lane) - 1u));
+        if (gt && rg < k) out[rg] = make_uint2(move_base + m, (uint32_t)g);
+        if (eq && re < need_eq) out[k + re] = make_uint2(move_base + m, (uint32_t)g);       // ties are stored after the k "greater" slots
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tg = 0, te = 0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) { tg += s_gt[w]; te += s_eq[w]; }
+            base_gt += tg; base_eq += te;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out_n[0] = base_gt < k ? base_gt : k; out_n[1] = base_eq < need_eq ? base_eq : need_eq; }
+}

@@ -47,6 +47,15 @@ class SimonScenarioResult(C.Structure):
                 ("elapsed_ms", C.c_float), ("reserved", C.c_uint32)]
 
 
+class SimonMovesResult(C.Structure):
+    _fields_ = [("best_key", C.c_uint64), ("n_feasible", C.c_uint32), ("n_topk", C.c_uint32),
+                ("kernel_ms", C.c_float), ("reserved", C.c_uint32)]
+
+
+MOVE_NOOP, MOVE_NOT_PLACED, MOVE_NOT_MOVABLE, MOVE_BAD_INDEX = 1 << 24, 1 << 25, 1 << 26, 1 << 27
+MOVE_GAIN_BIAS = 1000
+
+
 _SNAP_DTYPES = {
     "topo_ndom": np.uint32, "alloc_mcpu": np.int64, "alloc_mem": np.int64, "alloc_eph": np.int64,
     "alloc_scalar": np.int64, "alloc_pods": np.int32, "node_flags": np.uint32, "label_bits": np.uint64,

@@ -14,13 +14,14 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimon_gpu.so")
+LIB_PATH = os.environ.get("SIMON_GPU_LIB") or os.path.join(_HERE, "libsimon_gpu.so")    # the override is for kernel experiments
 _LIB = None
 
 EXPORTS = ["simon_gpu_version", "simon_ctx_create", "simon_ctx_destroy", "simon_last_error", "simon_snapshot_upload",
            "simon_pods_upload", "simon_state_reset", "simon_schedule", "simon_results_download", "simon_last_kernel_ms",
            "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay", "simon_stats",
-           "simon_gpu_slots_download", "simon_state_download_ext", "simon_debug_set_dump_pod", "simon_debug_dump_read"]
+           "simon_gpu_slots_download", "simon_state_download_ext", "simon_debug_set_dump_pod", "simon_debug_dump_read",
+           "simon_moves_upload", "simon_moves_run", "simon_moves_replay"]
 
 
 class EngineUnavailable(RuntimeError):
@@ -71,6 +72,12 @@ def lib():
     L.simon_debug_set_dump_pod.argtypes = [C.c_void_p, C.c_uint32]
     L.simon_debug_dump_read.restype = C.c_int
     L.simon_debug_dump_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simon_moves_upload.restype = C.c_int
+    L.simon_moves_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.simon_moves_run.restype = C.c_int
+    L.simon_moves_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simon_moves_replay.restype = C.c_int
+    L.simon_moves_replay.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -203,6 +210,33 @@ class Engine:
         code = np.zeros(max(N, 1), np.int32)
         self._check(lib().simon_debug_dump_read(self.h, tot.ctypes.data, code.ctypes.data))
         return out, tot[:N], code[:N]
+
+    # ---- candidate-move scoring (config 5) ----
+    def moves_upload(self, moves: np.ndarray, move_base: int = 0):
+        """moves: uint32 array [n, 2] of (pod index, target node)."""
+        a = np.ascontiguousarray(moves, dtype=np.uint32).reshape(-1, 2)
+        self._moves_keep = a
+        self._check(lib().simon_moves_upload(self.h, a.ctypes.data, len(a), move_base))
+        return len(a)
+
+    def moves_run(self, k: int = 0, want_arrays: bool = True, want_per_pod: bool = False):
+        """-> dict(best_key, n_feasible, kernel_ms, gain, code, best_per_pod, topk=[(move, gain)...])."""
+        n = len(self._moves_keep)
+        gain = np.zeros(max(n, 1), np.int32) if want_arrays else None
+        code = np.zeros(max(n, 1), np.uint32) if want_arrays else None
+        bpp = np.zeros(max(self.c.pods_dims["n_pods"], 1), np.uint64) if want_per_pod else None
+        topk = np.zeros((max(k, 1), 2), np.int32)
+        res = abi.SimonMovesResult()
+        self._check(lib().simon_moves_run(self.h, k, gain.ctypes.data if want_arrays else None, code.ctypes.data if want_arrays else None,
+                                          bpp.ctypes.data if want_per_pod else None, topk.ctypes.data if k else None, C.byref(res)))
+        return dict(best_key=int(res.best_key), n_feasible=int(res.n_feasible), kernel_ms=float(res.kernel_ms),
+                    gain=None if gain is None else gain[:n], code=None if code is None else code[:n],
+                    best_per_pod=bpp, topk=[(int(topk[q, 0]) & 0xffffffff, int(topk[q, 1])) for q in range(res.n_topk)])
+
+    def moves_replay(self, steps: int = 1) -> float:
+        ms = C.c_float(0)
+        self._check(lib().simon_moves_replay(self.h, steps, C.byref(ms)))
+        return float(ms.value)
 
     def run_scenarios(self, scenarios: List[np.ndarray], want_nodes: bool = False):
         """scenarios: list of uint32 arrays (active node indices in scenario order)."""

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Tuple
 
+import numpy as np
+
 from .objects import AppResource, ResourceTypes
 
 MASK = (1 << 64) - 1
@@ -458,3 +460,46 @@ def make_mix(seed_no: int = 100, n_nodes: int = 40, n_workloads: int = 30, max_r
                                                                                    "resources": {"requests": {"cpu": "100m", "memory": "128Mi"}}}],
                                                                    "nodeSelector": {label_keys[0]: "v0"}}}}})
     return cluster, [app]
+
+
+class LiveSnapshot:
+    """A compiled cluster whose pod list is a set of RUNNING pods (spec.nodeName set): what importing a live cluster yields.
+    Same arrays as compiler.Compiled as far as Engine / Oracle are concerned."""
+
+    def __init__(self, base, pod_class, pod_fixed):
+        self.snap, self.snap_dims = base.snap, dict(base.snap_dims)
+        self.pods = dict(base.pods)
+        self.pods["pod_class"] = np.ascontiguousarray(pod_class, dtype=np.int32)
+        self.pods["pod_fixed_node"] = np.ascontiguousarray(pod_fixed, dtype=np.int32)
+        self.pods_dims = dict(base.pods_dims)
+        self.pods_dims["n_pods"] = len(pod_class)
+        self.n_nodes = base.n_nodes
+        self.node_names = base.node_names
+
+
+def make_c5(compiled, n_running: int = 300000, seed_no: int = 5) -> LiveSnapshot:
+    """C5: a live snapshot with ~n_running pods already bound.  The pods are instances of the classes of
+    `compiled` (a C3-shaped cluster), each bound to a uniformly drawn node that still has room for it (CPU, memory, pod
+    count); pods for which 8 draws find no room are dropped.  Pre-bound pods bypass the filters (simulator.go:326-329), so the
+    snapshot may violate soft rules - as live clusters do."""
+    rng = np.random.RandomState(0x5151 + seed_no)
+    blob, off = compiled.pods["class_blob"], compiled.pods["class_off"]
+    C = int(compiled.pods_dims["n_classes"])
+    N = compiled.n_nodes
+    hdr = np.array([[int(blob[int(off[k]) + w]) for w in (0, 1, 7, 10, 13)] for k in range(C)], dtype=np.int64)   # mcpu, mem, gpu, nodeName, guard
+    usable = np.nonzero((hdr[:, 2] == 0) & (hdr[:, 3] == -1) & (hdr[:, 4] == -1))[0]      # no GPU share, not pinned, not a DaemonSet pod
+    cap_c, cap_m, cap_p = compiled.snap["alloc_mcpu"].astype(np.int64), compiled.snap["alloc_mem"].astype(np.int64), compiled.snap["alloc_pods"].astype(np.int64)
+    use_c, use_m, use_p = np.zeros(N, np.int64), np.zeros(N, np.int64), np.zeros(N, np.int64)
+    cls_draw = usable[rng.randint(0, len(usable), n_running)]
+    node_draw = rng.randint(0, max(N, 1), (n_running, 8))
+    pc, pf = [], []
+    for i in range(n_running):
+        k = int(cls_draw[i])
+        rc, rm = int(hdr[k, 0]), int(hdr[k, 1])
+        for g in node_draw[i]:
+            g = int(g)
+            if use_p[g] + 1 <= cap_p[g] and use_c[g] + rc <= cap_c[g] and use_m[g] + rm <= cap_m[g]:
+                use_p[g] += 1; use_c[g] += rc; use_m[g] += rm
+                pc.append(k); pf.append(g)
+                break
+    return LiveSnapshot(compiled, np.array(pc, np.int32), np.array(pf, np.int32))

@@ -37,6 +37,8 @@ def lib():
         _LIB.simon_oracle_schedule.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _LIB.simon_oracle_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        _LIB.simon_oracle_moves_score.restype = C.c_int
+        _LIB.simon_oracle_moves_score.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.simon_oracle_set_threads.restype = C.c_int
         _LIB.simon_oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
     return _LIB
@@ -104,6 +106,17 @@ class Oracle:
         sc = np.zeros((N, 10), np.int64)
         lib().simon_oracle_last_detail(self.h, code.ctypes.data, sc.ctypes.data)
         return code, sc
+
+    def moves_score(self, moves, placement):
+        """Candidate moves [(pod, target)] on the oracle's CURRENT state; placement[pod] = node the pod runs on (or < 0)."""
+        a = np.ascontiguousarray(moves, dtype=np.uint32).reshape(-1, 2)
+        pl = np.ascontiguousarray(placement, dtype=np.int32)
+        gain = np.zeros(max(len(a), 1), np.int32)
+        code = np.zeros(max(len(a), 1), np.uint32)
+        rc = lib().simon_oracle_moves_score(self.h, len(a), a.ctypes.data, pl.ctypes.data, gain.ctypes.data, code.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"simon_oracle_moves_score rc={rc}")
+        return gain[:len(a)], code[:len(a)]
 
     def state(self):
         N = self.c.n_nodes

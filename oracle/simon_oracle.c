@@ -825,3 +825,127 @@ void simon_oracle_state(simon_oracle *o, int64_t *req_mcpu, int64_t *req_mem, in
     if (nz_mem) memcpy(nz_mem, o->nz_mem, 8ull * N);
     if (num_pods) memcpy(num_pods, o->num_pods, 4ull * N);
 }
+
+/* does a pod of the class with commit list `inc` (n entries of {counter, topology, sig}), sitting on node a, contribute
+ * one count to counter k (keyed on topology t) at domain d?  (what commit() added for it and RemovePod takes back) */
+static int32_t own_inc(const simon_oracle *o, const int64_t *inc, int64_t n, int64_t k, int64_t t, uint32_t a, int32_t d) {
+    for (int64_t i = 0; i < n; i++)
+        if (inc[3 * i] == k && inc[3 * i + 1] == t && inc[3 * i + 2] < 0)
+            return dom_of(o, t, a) == d ? 1 : 0;
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Candidate-move scoring (BASELINE config 5).  The reference has no implementation of this path (README.md:16 names the
+ * use case; NodeInfo.RemovePod, K8S/framework/types.go:539-585, is the primitive it would use), so the definition is this
+ * repository's and this function is the checker of open-simulator_b200/csrc/simon_moves.cu:
+ * a move (pod p, target b) is evaluated on the oracle's current state with p taken off its node a = placement[p]
+ * (requests, non-zero requests, pod count, p's own counter increments at a's domains); code = reasons of the first failing
+ * filter of this path on b (static verdict, NodePorts, NodeResourcesFit, InterPodAffinity) or a SMV_* marker;
+ * gain = (LeastAllocated + BalancedAllocation of b for p) - (the same of a for p with p removed first). */
+#define SMV_NOOP (1u << 24)
+#define SMV_NOT_PLACED (1u << 25)
+#define SMV_NOT_MOVABLE (1u << 26)
+#define SMV_BAD_INDEX (1u << 27)
+
+static int64_t own_score(int64_t capc, int64_t capm, int64_t nzc, int64_t nzm, int64_t sc, int64_t sm) {
+    int64_t rqc = nzc + sc, rqm = nzm + sm;
+    int64_t s1 = (capc == 0 || rqc > capc) ? 0 : ((capc - rqc) * 100) / capc;
+    int64_t s2 = (capm == 0 || rqm > capm) ? 0 : ((capm - rqm) * 100) / capm;
+    int64_t la = (s1 + s2) / 2, ba = 0;
+    double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
+    double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
+    if (!(cf >= 1.0 || mf >= 1.0)) ba = f2i((1.0 - fabs(cf - mf)) * 100.0);
+    return la + ba;
+}
+
+int simon_oracle_moves_score(simon_oracle *o, uint32_t n_moves, const uint32_t *moves, const int32_t *placement,
+                             int32_t *out_gain, uint32_t *out_code) {
+    const uint32_t N = o->N;
+    for (uint32_t m = 0; m < n_moves; m++) {
+        uint32_t pod = moves[2 * m], b = moves[2 * m + 1];
+        uint32_t code = 0;
+        int32_t gain = 0;
+        int32_t a = -1;
+        if (pod >= o->p.n_pods || b >= N) code = SMV_BAD_INDEX;
+        else {
+            a = placement[pod];
+            if (a < 0 || (uint32_t)a >= N) code = SMV_NOT_PLACED;
+            else if ((uint32_t)a == b) code = SMV_NOOP;
+        }
+        if (!code) {
+            const int64_t *cw = CW(o, o->p.pod_class[pod]);
+            if (cw[SCW_N_PTS_HARD] > 0 || cw[SCW_GPU_MEM] > 0) code = SMV_NOT_MOVABLE;
+            else {
+                uint32_t flags = (uint32_t)cw[SCW_FLAGS];
+                const int64_t *tol = cw + cw[SCW_OFF_TOL];
+                int st = 0;
+                if ((o->s.node_flags[b] & SIMON_NODE_UNSCHEDULABLE) && !(flags & SIMON_CLS_TOL_UNSCHED)) st = 1;
+                if (!st && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)b) st = 2;
+                if (!st)
+                    for (uint32_t w = 0; w < o->s.n_taint_words; w++)
+                        if (o->s.taint_hard[(uint64_t)w * N + b] & ~(uint64_t)tol[w]) st = 3;
+                if (!st && !node_selection_ok(o, cw, b)) st = 4;
+                if (st) code = 1u << SFC_STATIC;
+                /* p's own contribution to counter k on topology t: made at a's domain, if the class increments (k, t) */
+                const int64_t *inc = cw + cw[SCW_OFF_INC];
+#define OWN_AT(k, t, d) (own_inc(o, inc, cw[SCW_N_INC], (k), (t), (uint32_t)a, (d)))
+                const int64_t *ports = cw + cw[SCW_OFF_PORTS];
+                if (!code)
+                    for (int64_t j = 0; j < cw[SCW_N_PORTS]; j++)
+                        if (cnt_at(o, ports[j], (int32_t)b) - own_inc(o, inc, cw[SCW_N_INC], ports[j], 0, (uint32_t)a, (int32_t)b) > 0) { code = 1u << SFC_PORTS; break; }
+                if (!code) {
+                    uint32_t rs = 0;
+                    if (o->num_pods[b] + 1 > o->s.alloc_pods[b]) rs |= 1u << SFC_TOO_MANY_PODS;
+                    if (flags & SIMON_CLS_HAS_REQUEST) {
+                        if (o->s.alloc_mcpu[b] < cw[SCW_REQ_MCPU] + o->req_mcpu[b]) rs |= 1u << SFC_CPU;
+                        if (o->s.alloc_mem[b] < cw[SCW_REQ_MEM] + o->req_mem[b]) rs |= 1u << SFC_MEM;
+                        if (o->s.alloc_eph[b] < cw[SCW_REQ_EPH] + o->req_eph[b]) rs |= 1u << SFC_EPH;
+                        const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
+                        for (uint32_t k = 0; k < o->s.n_scalars; k++)
+                            if (sc_req[k] != 0 && o->s.alloc_scalar[(uint64_t)k * N + b] < sc_req[k] + o->req_scalar[(uint64_t)k * N + b]) rs |= 1u << (SFC_SCALAR0 + k);
+                    }
+                    code = rs;
+                }
+                const int64_t *aff = cw + cw[SCW_OFF_IPA_AFF], *anti = cw + cw[SCW_OFF_IPA_ANTI], *exist = cw + cw[SCW_OFF_IPA_EXIST];
+                if (!code && cw[SCW_N_IPA_AFF] > 0) {
+                    int pods_exist = 1, missing = 0;
+                    int64_t aff_total = 0;
+                    for (int64_t j = 0; j < cw[SCW_N_IPA_AFF]; j++) {
+                        int64_t k = aff[2 * j], t = aff[2 * j + 1];
+                        aff_total += o->cnt_total[k];
+                        int32_t da = dom_of(o, t, (uint32_t)a);
+                        if (da >= 0) aff_total -= own_inc(o, inc, cw[SCW_N_INC], k, t, (uint32_t)a, da);
+                        int32_t d = dom_of(o, t, b);
+                        if (d < 0) { missing = 1; continue; }
+                        if (cnt_at(o, k, d) - OWN_AT(k, t, d) <= 0) pods_exist = 0;
+                    }
+                    int ok = 1;
+                    if (missing) ok = 0;
+                    else if (!pods_exist) ok = (aff_total == 0 && (flags & SIMON_CLS_IPA_SELF_MATCH)) ? 1 : 0;
+                    if (!ok) code = 1u << SFC_IPA_AFF;
+                }
+                if (!code)
+                    for (int64_t j = 0; j < cw[SCW_N_IPA_ANTI]; j++) {
+                        int32_t d = dom_of(o, anti[2 * j + 1], b);
+                        if (d >= 0 && cnt_at(o, anti[2 * j], d) - OWN_AT(anti[2 * j], anti[2 * j + 1], d) > 0) { code = 1u << SFC_IPA_ANTI; break; }
+                    }
+                if (!code)
+                    for (int64_t j = 0; j < cw[SCW_N_IPA_EXIST]; j++) {
+                        int32_t d = dom_of(o, exist[2 * j + 1], b);
+                        if (d >= 0 && cnt_at(o, exist[2 * j], d) - OWN_AT(exist[2 * j], exist[2 * j + 1], d) > 0) { code = 1u << SFC_IPA_EXIST; break; }
+                    }
+#undef OWN_AT
+                if (!code) {
+                    int64_t on_b = own_score(o->s.alloc_mcpu[b], o->s.alloc_mem[b], o->nz_mcpu[b], o->nz_mem[b], cw[SCW_SCORE_MCPU], cw[SCW_SCORE_MEM]);
+                    int64_t on_a = own_score(o->s.alloc_mcpu[a], o->s.alloc_mem[a], o->nz_mcpu[a] - cw[SCW_NZ_MCPU], o->nz_mem[a] - cw[SCW_NZ_MEM],
+                                             cw[SCW_SCORE_MCPU], cw[SCW_SCORE_MEM]);
+                    gain = (int32_t)(on_b - on_a);
+                }
+            }
+        }
+        out_gain[m] = gain;
+        out_code[m] = code;
+    }
+    return SIMON_OK;
+}

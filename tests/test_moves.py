@@ -1,0 +1,139 @@
+"""Candidate-move scoring (BASELINE config 5): the oracle's restatement, the sharding + collectives of the multi-GPU search
+(gloo, world size 2, on CPU), and GPU parity of the CUDA kernel against the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from util import make_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _state(kind="mix", **kw):
+    from oracle.binding import Oracle
+    p, c = make_case(kind, **kw)
+    o = Oracle(c)
+    out, _, _, _ = o.schedule()
+    return p, c, o, out
+
+
+def oracle_runner(o, placement):
+    """Test-side runner: the CPU restatement scoring a shard; same result dictionary as the GPU runner."""
+    from simon_b200 import moves as M
+
+    def run(shard, move_base, k):
+        gain, code = o.moves_score(shard, placement)
+        feas = np.nonzero(code == 0)[0]
+        keys = [M.pack_key(int(gain[m]), move_base + int(m)) for m in feas]
+        top = sorted(((move_base + int(m), int(gain[m])) for m in feas), key=lambda mg: (-mg[1], mg[0]))[:k]
+        return dict(best_key=max(keys) if keys else 0, n_feasible=len(feas), topk=top, gain=gain, code=code)
+    return run
+
+
+def test_move_scores_agree_with_replaying_the_move():
+    """A move is feasible exactly when the pod, taken off its node (RemovePod) and run through this path's filters on the
+    target, passes: replay every sampled move of a small cluster on a fresh oracle whose pod list has that pod re-pinned."""
+    from oracle.binding import Oracle
+    from simon_b200 import moves as M
+    p, c, o, out = _state("c3", n_nodes=40, n_workloads=12, replicas=5, n_apps=1, seed_no=7)
+    mv = M.sample_moves(len(out), c.n_nodes, 400, seed=3, placement=out)
+    gain, code = o.moves_score(mv, out)
+    assert (code == 0).sum() > 20 and (code != 0).sum() > 20
+    # NOOP and index handling
+    g2, c2 = o.moves_score(np.array([[0, int(out[0])], [len(out) + 5, 0], [0, c.n_nodes + 1]], np.uint32), out)
+    from simon_b200 import abi
+    assert int(c2[0]) == abi.MOVE_NOOP if out[0] >= 0 else abi.MOVE_NOT_PLACED
+    assert int(c2[1]) == abi.MOVE_BAD_INDEX and int(c2[2]) == abi.MOVE_BAD_INDEX
+    # gain of a feasible move = own score on the target - own score at home: bounded by the plugin ranges
+    assert gain[code == 0].min() >= -200 and gain[code == 0].max() <= 200
+    # resource reasons are consistent with the aggregates: a move flagged "Insufficient cpu" really does not fit
+    st = o.state()
+    blob, off = c.pods["class_blob"], c.pods["class_off"]
+    for m in np.nonzero(code & (1 << 3))[0][:50]:
+        pod, b = int(mv[m, 0]), int(mv[m, 1])
+        req = int(blob[int(off[c.pods["pod_class"][pod]])])
+        assert int(c.snap["alloc_mcpu"][b]) < req + int(st["req_mcpu"][b])
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "open-simulator_b200"))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from simon_b200 import moves as M
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p, c, o, out = _state("mix", seed_no=103, n_nodes=95, n_workloads=40, max_replicas=7)
+    mv = M.sample_moves(len(out), c.n_nodes, 5000, seed=9, placement=out)
+    arm, agk = M.torch_collectives("cpu")
+    best, topk, _ = M.search(mv, oracle_runner(o, out), k=8, rank=rank, world=world, all_reduce_max=arm, all_gather_topk=agk)
+    q.put((rank, best, topk))
+    dist.destroy_process_group()
+
+
+def test_move_search_two_ranks_gloo_matches_single_process():
+    import torch.multiprocessing as mp
+    from simon_b200 import moves as M
+    p, c, o, out = _state("mix", seed_no=103, n_nodes=95, n_workloads=40, max_replicas=7)
+    mv = M.sample_moves(len(out), c.n_nodes, 5000, seed=9, placement=out)
+    best1, top1, _ = M.search(mv, oracle_runner(o, out), k=8)
+    assert best1 is not None and len(top1) == 8
+    assert top1[0] == (best1["move"], best1["gain"])
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = [q.get(timeout=180) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+    for rank, best, topk in got:
+        assert best == best1, (rank, best, best1)
+        assert topk == top1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,kw,n", [
+    ("mix", dict(seed_no=103, n_nodes=95, n_workloads=40, max_replicas=7), 30000),
+    ("mix", dict(seed_no=215, n_nodes=45, n_workloads=30, max_replicas=9), 20000),
+    ("c3", dict(n_nodes=1500, n_workloads=200, replicas=20, n_apps=4, seed_no=5), 200000),
+    ("c2", dict(n_nodes=300, n_workloads=30, replicas=30, seed_no=2), 50000),
+])
+def test_moves_gpu_matches_oracle(kind, kw, n):
+    from simon_b200 import moves as M
+    from simon_b200.engine import Engine
+    p, c, o, out = _state(kind, **kw)
+    mv = M.sample_moves(len(out), c.n_nodes, n, seed=11, placement=out)
+    mv[:50, 0] = np.arange(50) % max(len(out), 1)           # some arbitrary pods too (unscheduled / pre-bound ones among them)
+    gain, code = o.moves_score(mv, out)
+    with Engine(c, device=0) as eng:
+        got_out = eng.schedule()[0]
+        np.testing.assert_array_equal(got_out, out)
+        eng.moves_upload(mv, 0)
+        r = eng.moves_run(k=32, want_arrays=True, want_per_pod=True)
+        # a shard with a base offset reports global move indices
+        half = len(mv) // 2
+        eng.moves_upload(mv[half:], half)
+        r2 = eng.moves_run(k=8, want_arrays=False)
+    bad = np.nonzero(r["code"] != code)[0]
+    assert len(bad) == 0, f"codes differ at moves {bad[:5]}: gpu {r['code'][bad[:5]]} oracle {code[bad[:5]]}"
+    np.testing.assert_array_equal(r["gain"], gain)
+    ref = oracle_runner(o, out)(mv, 0, 32)
+    assert r["best_key"] == ref["best_key"] and r["n_feasible"] == ref["n_feasible"]
+    assert r["topk"] == ref["topk"]
+    ref2 = oracle_runner(o, out)(mv[half:], half, 8)
+    assert r2["best_key"] == ref2["best_key"] and r2["topk"] == ref2["topk"]
+    # best move per pod
+    want = np.zeros(len(out), np.uint64)
+    for m in np.nonzero(code == 0)[0]:
+        k = M.pack_key(int(gain[m]), int(m))
+        if k > int(want[mv[m, 0]]):
+            want[mv[m, 0]] = k
+    np.testing.assert_array_equal(r["best_per_pod"][:len(out)], want)

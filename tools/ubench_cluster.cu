@@ -10,6 +10,7 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
     sk_carve(S, smem_raw, blockDim.x, 2, 4, 64, cluster.num_blocks());
     for (uint32_t q = threadIdx.x; q < (B_N32 + 2 + 4) * blockDim.x; q += blockDim.x) S.a32[q] = (int32_t)q;
     for (uint32_t q = threadIdx.x; q < C_N8 * blockDim.x; q += blockDim.x) S.a8[q] = (uint8_t)q;
+    if (threadIdx.x < 2) ((uint32_t *)(S.wpart + 200))[threadIdx.x] = 0;
     SkRed R{&S, &cluster, cluster.block_rank(), cluster.num_blocks(), 0, nullptr};
     sk_red_init(R);
     long long t0 = clock64();
@@ -54,6 +55,41 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
             sk_allreduce_w<7>(R, xw, xop);
             unsigned long long k = sk_argmax(R, ((acc & 0xffff) << 24) | (0xFFFFFFu - (cluster.block_rank() * blockDim.x + threadIdx.x)), cluster.num_blocks() * blockDim.x, blockDim.x, who); acc += k + sk_wpay(S, who, 0) + xw[1] + xw[5];
         }
+        else if (mode == 16) {  // allreduce of 6 words with plain DSMEM stores + release/acquire flag polling (no mbarrier / async proxy)
+            const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const uint32_t CS = cluster.num_blocks(), buf = i & 1;
+            uint32_t w[6] = {(uint32_t)acc, (uint32_t)acc + 1, (uint32_t)acc + 2, (uint32_t)acc + 3, (uint32_t)acc & 1, 1u};
+            const int op[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
+            for (int q = 0; q < 6; q++) w[q] = warp_w(w[q], op[q]);
+            uint32_t *wp = (uint32_t *)S.wpart;
+            if (lane == 0) for (int q = 0; q < 6; q++) wp[q * SK_MAX_WARPS + warp] = w[q];
+            __syncthreads();
+            uint32_t *flag = (uint32_t *)(S.wpart + 200);        // two counters, untouched by the partials
+            if (warp == 0) {
+                uint32_t c[6];
+                for (int q = 0; q < 6; q++) c[q] = warp_w(lane < NW ? wp[q * SK_MAX_WARPS + lane] : w_ident(op[q]), op[q]);
+                if (lane < CS) {
+                    const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * CS + cluster.block_rank()), lane);
+                    for (int m2 = 0; m2 < 3; m2++) {
+                        unsigned long long v = ((unsigned long long)c[2 * m2 + 1] << 32) | c[2 * m2];
+                        asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(rbox + 8u * m2 * CS), "l"(v) : "memory");
+                    }
+                    const uint32_t rflag = sk_mapa(sk_saddr(&flag[buf]), lane);
+                    asm volatile("red.release.cluster.shared::cluster.add.u32 [%0], 1;" ::"r"(rflag) : "memory");
+                }
+            }
+            const uint32_t target = ((uint32_t)(i >> 1) + 1u) * CS;
+            uint32_t seen;
+            do { asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(sk_saddr(&flag[buf])) : "memory"); } while ((int32_t)(seen - target) < 0);
+            const unsigned long long *bx = S.box + (size_t)buf * SK_NV * CS;
+            for (int m2 = 0; m2 < 3; m2++) {
+                const bool in = lane < CS;
+                const unsigned long long x = in ? bx[m2 * CS + lane] : 0ull;
+                w[2 * m2] = warp_w(in ? (uint32_t)x : w_ident(op[2 * m2]), op[2 * m2]);
+                w[2 * m2 + 1] = warp_w(in ? (uint32_t)(x >> 32) : w_ident(op[2 * m2 + 1]), op[2 * m2 + 1]);
+            }
+            acc += w[1] + w[5];
+        }
         else if (mode == 11) {  // CTA-level combine: per-warp slots + __syncthreads + every warp folds
             unsigned *a = (unsigned *)S.wpart + (i & 1) * 32;
             unsigned x = __reduce_max_sync(0xffffffffu, (unsigned)acc + threadIdx.x);
@@ -67,8 +103,8 @@ extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
 
 int main() {
     long long *d; cudaMalloc(&d, 64);
-    const char *names[16] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "10x redux.max.u32 (dependent)", "10x warp_maxu64 (dependent)", "st.async self + mbar wait", "st.async next CTA + mbar wait", "redux+smem atomicMax+bar", "redux+slots+bar+fold", "allreduce_w<6> (32-bit words)", "allreduce_w<22> (32-bit words)", "merged arg-max + 7 words (1 exchange)", "allreduce_w<7> + arg-max (2 exchanges)"};
-    for (int cs : {1, 2, 4, 8, 16}) for (int tpb : {256, 320}) for (int mode = 0; mode < 16; mode++) {
+    const char *names[17] = {"cluster.sync", "allreduce<5>", "allreduce<16>", "argmax", "__syncthreads", "threadfence+cluster.sync", "10x redux.max.u32 (dependent)", "10x warp_maxu64 (dependent)", "st.async self + mbar wait", "st.async next CTA + mbar wait", "redux+smem atomicMax+bar", "redux+slots+bar+fold", "allreduce_w<6> (32-bit words)", "allreduce_w<22> (32-bit words)", "merged arg-max + 7 words (1 exchange)", "allreduce_w<7> + arg-max (2 exchanges)", "allreduce 6 words, st.shared::cluster + flag polling"};
+    for (int cs : {1, 2, 4, 8, 16}) for (int tpb : {256, 320}) for (int mode = 0; mode < 17; mode++) {
         size_t smem = sk_smem_bytes(tpb, 2, 4, 64, cs);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_sync, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
