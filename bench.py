@@ -11,12 +11,20 @@ A "step" is one pass of the hot path over one batch: the whole ordered pod list 
            simon_snapshot_upload + simon_pods_upload + simon_schedule(out_node -> host), wall clock
   N > 1  : a single scenario does not shard (each placement depends on the previous one) -> N independent
            replicas (distinct seeds), one per GPU, no data-path collective; scaling = weak.
+Beside the headline the line carries the other BASELINE configurations as blocks:
+  c2               1k nodes x 10k pods, Fit-only predicates (config 2)
+  batch            concurrent what-if replicas of C3 on one GPU at the best residency (aggregate decisions/s)
+  capacity_search  config 4: 2,000-node base, 5,000 pending pods, 8 specs x 32 node counts = 256 scenarios sharded over the
+                   ranks, ONE all_reduce(MIN) inside the timed region
+  move_scoring     config 5: 1,000,000 candidate moves on a 10k-node live snapshot (~300k running pods), moves partitioned
+                   contiguously over the ranks, one all_reduce(MAX) + one all_gather of the per-rank top-k
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -31,6 +39,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "pod-placement decisions/sec on 10k-node synthetic cluster"
 ALGO_BYTES_PER_NODE_DECISION = 180      # SURVEY.md section 8(d), C3 full predicate set
+ALGO_BYTES_PER_NODE_DECISION_C2 = 80    # SURVEY.md section 8(d), C2 Fit + default scores
+ALGO_BYTES_PER_MOVE = 280               # move 8 + pod 8 + class 56 + target 96 + source 96 + verdict 8 + out 8
 
 
 def peaks():
@@ -41,6 +51,17 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def go_probe() -> str:
+    """BASELINE.md section 3 / SURVEY 8c step 4: the reference itself can only be timed where a Go >= 1.18 toolchain exists."""
+    exe = shutil.which("go")
+    if not exe:
+        return "go: not found on this box (the reference's Go path cannot be built or timed here)"
+    try:
+        return subprocess.run([exe, "version"], capture_output=True, text=True, timeout=20).stdout.strip()
+    except Exception as e:       # noqa: BLE001
+        return f"go: probe failed ({e})"
 
 
 def build_workload(args, seed_no):
@@ -102,10 +123,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_threads(args, c=None, first_sched=0) -> int:
+def host_cores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_threads(args, c=None, first_sched=0, cap=64) -> int:
     """Host threads for the CPU port: --cpu-threads, or the count that is fastest on a short sample of this workload
     (the per-node loops of one cycle are short, so more threads than that only add fork/join cost)."""
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ncpu = host_cores()
     if args.cpu_threads > 0:
         return max(1, min(64, args.cpu_threads))
     if c is None or ncpu <= 1:
@@ -114,7 +139,7 @@ def cpu_threads(args, c=None, first_sched=0) -> int:
     best_t, best_v = 1, 0.0
     n = min(1500, c.pods_dims["n_pods"] - first_sched)
     for t in (1, 2, 4, 8, 16, 32, 64):
-        if t > ncpu:
+        if t > ncpu or t > cap:
             break
         o = Oracle(c, threads=t)
         o.schedule(0, first_sched)
@@ -128,34 +153,51 @@ def cpu_threads(args, c=None, first_sched=0) -> int:
 
 
 def run_reference(args):
-    """The reference's CPU path, restated (oracle/simon_oracle.c) — there is no Go toolchain to build the original."""
+    """The reference's CPU path, restated (oracle/simon_oracle.c) — there is no Go toolchain to build the original.
+    Like the GPU arm, a job at N "GPUs" is N independent replicas (distinct seeds): rank 0 runs them CONCURRENTLY on the box's
+    host cores (one oracle per replica, each with the thread count that is fastest for it, capped so that the N replicas
+    share the cores), the other ranks exit at once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle.binding import Oracle
-    p, c, _ = build_workload(args, 3)
-    P = c.pods_dims["n_pods"]
-    first_sched = int(np.argmax(c.pods["pod_fixed_node"] == -1))
-    sample = min(args.cpu_sample, P - first_sched)
-    o = Oracle(c, threads=cpu_threads(args, c, first_sched))
+    n_rep = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+    ncpu = host_cores()
+    reps = []
+    for r in range(n_rep):
+        p, c, _ = build_workload(args, 3 + r)
+        reps.append(c)
+    c0 = reps[0]
+    P = c0.pods_dims["n_pods"]
+    first0 = int(np.argmax(c0.pods["pod_fixed_node"] == -1))
+    per = cpu_threads(args, c0, first0, cap=max(1, ncpu // n_rep))
+    sample = min(args.cpu_sample, min(int(c.pods_dims["n_pods"]) - int(np.argmax(c.pods["pod_fixed_node"] == -1)) for c in reps))
+    oracles = [Oracle(c, threads=per) for c in reps]
+    firsts = [int(np.argmax(c.pods["pod_fixed_node"] == -1)) for c in reps]
     times = []
     for step in range(args.warmup + args.steps):
-        o.reset()
-        o.schedule(0, first_sched)                 # pre-bound pods: accounting only, not timed
+        for o, f in zip(oracles, firsts):
+            o.reset()
+            o.schedule(0, f)                       # pre-bound pods: accounting only, not timed
+        ths = [threading.Thread(target=o.schedule, args=(f, sample)) for o, f in zip(oracles, firsts)]
         t0 = time.perf_counter()
-        o.schedule(first_sched, sample)
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(dt)
     tot = sum(times)
-    value = sample * len(times) / tot
-    cb = {"value": value, "unit": "decisions/s", "cores": o.threads, "kind": "port",
-          "sample": f"first {sample} scheduled pods of the {P}-pod list per step (oracle/simon_oracle.c, per-node loops shared "
-                    f"between {o.threads} host threads, the fastest count on this box)"}
+    value = n_rep * sample * len(times) / tot
+    cb = {"value": value, "unit": "decisions/s", "cores": per * n_rep, "kind": "port",
+          "sample": f"first {sample} scheduled pods of each of {n_rep} replica pod list(s) ({P} pods) per step, {n_rep} concurrent "
+                    f"oracle instance(s) x {per} host threads (oracle/simon_oracle.c; {ncpu} cores visible)",
+          "go": go_probe()}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-            "config": workload_config(args, c), "cpu_baseline": cb,
+            "config": workload_config(args, c0), "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -167,6 +209,170 @@ def workload_config(args, c):
             "parallelism": "1 scenario per GPU (replicas)", "l2": "flushed between timed steps (256 MiB write)"}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# blocks beside the headline
+# ---------------------------------------------------------------------------------------------------------------------
+def block_c2(args, local, flush, torch):
+    """BASELINE config 2: 1k nodes x 10k pods, NodeResourcesFit-only predicates (the default score set stays active)."""
+    from simon_b200 import simulator, synth
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.engine import Engine
+    from oracle.binding import Oracle
+    cluster, apps = synth.make_c2(n_nodes=1000, n_workloads=100, replicas=100, seed_no=2)
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    D = int((c.pods["pod_fixed_node"] == -1).sum())
+    with Engine(c, device=local) as eng:
+        for _ in range(3):
+            eng.replay(1)
+        ms = 0.0
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms += eng.replay(1)
+        out = eng.schedule()[0]
+    o = Oracle(c)
+    t0 = time.perf_counter()
+    ref = o.schedule()[0]
+    cpu = D / (time.perf_counter() - t0)
+    v = D * 5 / (ms * 1e-3)
+    peak, _ = peaks()
+    return {"workload": "C2: 1000 nodes x 10000 pods (100 deployments x 100), NodeResourcesFit-only predicates", "value": v, "unit": "decisions/s",
+            "ms_per_step": ms / 5, "placements_identical_to_oracle": bool(np.array_equal(out, ref)), "cpu_port_1_thread": cpu,
+            "roofline_frac": v * ALGO_BYTES_PER_NODE_DECISION_C2 * 1000 / 1e9 / peak}
+
+
+def block_batch(args, c, D, P, placed, local, flush, torch):
+    """Concurrent what-if replicas of the C3 workload on one GPU: one thread-block cluster each; report the best residency."""
+    from simon_b200.engine import Engine
+    best = None
+    tried = []
+    act = np.arange(int(c.n_nodes), dtype=np.uint32)
+    for cs, tpb, nb in ((16, 320, 7), (8, 320, 16), (8, 320, 18)):
+        try:
+            with Engine(c, device=local, cluster_ctas=cs, threads_per_cta=tpb) as eng:
+                eng.run_scenarios([act] * nb)                                   # warm-up
+                flush.zero_()
+                torch.cuda.synchronize()
+                res, _ = eng.run_scenarios([act] * nb)
+                ms = eng.last_kernel_ms()
+        except Exception as e:       # noqa: BLE001
+            tried.append({"cluster_ctas": cs, "threads": tpb, "scenarios": nb, "error": str(e)[:120]})
+            continue
+        same = all(r["n_scheduled"] == placed - (P - D) or r["n_scheduled"] == placed for r in res)
+        rec = {"cluster_ctas": cs, "threads": tpb, "scenarios": nb, "value": nb * D / (ms * 1e-3), "ms": ms, "identical_counts": bool(same)}
+        tried.append(rec)
+        if same and (best is None or rec["value"] > best["value"]):
+            best = rec
+    if best is None:
+        return {"tried": tried}
+    peak, _ = peaks()
+    return dict(best, unit="decisions/s", tried=tried,
+                roofline_frac_nominal=best["value"] * ALGO_BYTES_PER_NODE_DECISION * args.nodes / 1e9 / peak,
+                note="simon_scenarios_run: independent replicas of the same workload placed concurrently on one GPU (the capacity-planning "
+                     "batch shape); aggregate, not the headline value.  The snapshot of every scenario is resident in its cluster's shared "
+                     "memory, so the nominal roofline fraction counts algorithmic bytes that never touch DRAM")
+
+
+def block_capacity(args, rank, world, local, dist, torch):
+    """BASELINE config 4: the add-node search (pkg/apply/apply.go:203-259) as 256 what-if scenarios sharded over the ranks."""
+    from simon_b200 import capacity, synth
+    from simon_b200.engine import Engine
+    t0 = time.perf_counter()
+    cluster, apps, specs = synth.make_c4(n_nodes=2000, n_workloads=50, replicas=100)
+    ss = capacity.build_scenarios(cluster, apps, specs, list(range(1, 33)))
+    t_build = time.perf_counter() - t0
+    reduce_fn = capacity.torch_all_reduce_min(f"cuda:{local}") if world > 1 else None
+    eng = Engine(ss.compiled, device=local)
+    runner = capacity.gpu_runner(local, engine=eng)
+    capacity.search(ss, runner, rank=rank, world=world, all_reduce_min=reduce_fn)       # warm-up: buffers + communicator
+    times = []
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t1 = time.perf_counter()
+        best, _local = capacity.search(ss, runner, rank=rank, world=world, all_reduce_min=reduce_fn)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t1)
+    kernel_ms = eng.last_kernel_ms()
+    eng.close()
+    dt = min(times)
+    tt = torch.tensor([dt, kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt, kernel_ms = float(tt[0].item()), float(tt[1].item())
+    dec = capacity.decode_key(best)
+    pods_per_scen = int((ss.compiled.pods["pod_fixed_node"] == -1).sum())
+    return {"workload": "C4: 2000-node base ~85 % full, 5000 pending pods, 8 node specs x k = 1..32 -> 256 scenarios",
+            "scenarios": len(ss.scenarios), "n_gpus": world, "search_s": dt, "kernel_ms_max_rank": kernel_ms, "host_build_s": t_build,
+            "best": dec, "best_spec": (ss.scenarios[dec["scenario"]].spec if dec else None),
+            "decisions_per_s": len(ss.scenarios) * pods_per_scen / dt, "scheduled_pods_per_scenario": pods_per_scen,
+            "collective": "one all_reduce(MIN) of an int64 key (k << 32 | scenario) over NCCL, inside search_s" if world > 1 else "none (single process)",
+            "timing": "best of 3 searches, wall clock per rank (includes the scenario-list uploads, the launch, the result download "
+                      "and the collective), max over ranks"}
+
+
+def block_moves(args, rank, world, local, dist, torch):
+    """BASELINE config 5: 1,000,000 candidate moves scored on a 10k-node live snapshot."""
+    from simon_b200 import moves as M, simulator, synth
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.engine import Engine
+    cluster, apps = synth.make_c3(n_nodes=args.nodes, n_workloads=max(10, args.nodes // 10), replicas=10, n_apps=10, seed_no=3)
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    live = synth.make_c5(c, args.running)
+    n_moves = args.moves
+    with Engine(live, device=local) as eng:
+        out = eng.schedule()[0]                                     # import of the running pods (accounting only)
+        mv = M.sample_moves(len(out), live.n_nodes, n_moves, seed=11, placement=out)
+        lo, hi = M.shard_bounds(n_moves, rank, world)
+        eng.moves_upload(mv[lo:hi], lo)
+        eng.moves_replay(3)
+        steps = 20
+        ms = eng.moves_replay(steps) / steps                        # device-resident: pack + score kernels, CUDA events
+        arm, agk = M.torch_collectives(f"cuda:{local}") if world > 1 else (None, None)
+        runner = M.gpu_runner(eng)
+        M.search(mv, runner, k=16, rank=rank, world=world, all_reduce_max=arm, all_gather_topk=agk)     # warm-up
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        best, topk, res = M.search(mv, runner, k=16, rank=rank, world=world, all_reduce_max=arm, all_gather_topk=agk)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        check = None
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle.binding import Oracle
+            o = Oracle(live)
+            o.schedule()
+            nchk = min(200000, hi - lo)
+            eng.moves_upload(mv[lo:lo + nchk], lo)
+            r = eng.moves_run(k=0, want_arrays=True)
+            t1 = time.perf_counter()
+            g, cd = o.moves_score(mv[lo:lo + nchk], out)
+            cpu = nchk / (time.perf_counter() - t1)
+            check = {"moves_compared_with_oracle": nchk, "identical": bool(np.array_equal(g, r["gain"]) and np.array_equal(cd, r["code"])),
+                     "cpu_port_moves_per_s_1_thread": cpu}
+    tt = torch.tensor([ms, dt], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, dt = float(tt[0].item()), float(tt[1].item())
+    peak, _ = peaks()
+    v = n_moves / (ms * 1e-3)
+    return {"workload": f"C5: {live.n_nodes} nodes, {live.pods_dims['n_pods']} running pods, {n_moves} candidate moves sampled uniformly",
+            "n_gpus": world, "value": v, "unit": "moves/s", "us_per_pass_max_rank": ms * 1e3,
+            "roofline": {"bound": "hbm", "achieved": v / world * ALGO_BYTES_PER_MOVE / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": v / world * ALGO_BYTES_PER_MOVE / 1e9 / peak,
+                         "note": f"algorithmic bytes = {ALGO_BYTES_PER_MOVE} B/move (move 8, pod 8, class 56, target + source node records 96 each, "
+                                 "static verdict 8, outputs 8); per GPU; the node table (~1 MB) is L2-resident, so DRAM traffic is the move list "
+                                 "and the outputs"},
+            "e2e": {"value": n_moves / dt, "unit": "moves/s", "h2d_bytes": int(8 * (hi - lo)), "path": "simon_moves_upload + simon_moves_run(top-16) "
+                    "+ all_reduce(MAX) + all_gather(top-k), wall clock, max over ranks"},
+            "best": best, "topk": topk[:4], "check": check}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,12 +382,15 @@ def main():
     ap.add_argument("--nodes", type=int, default=10000)
     ap.add_argument("--workloads", type=int, default=1000)
     ap.add_argument("--replicas", type=int, default=100)
-    ap.add_argument("--cpu-sample", type=int, default=30000)
+    ap.add_argument("--running", type=int, default=300000, help="running pods of the C5 live snapshot")
+    ap.add_argument("--moves", type=int, default=1000000, help="candidate moves of C5")
+    ap.add_argument("--cpu-sample", type=int, default=30000, help="decisions per step of the --impl reference arm")
     ap.add_argument("--cluster-ctas", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU port (0 = all cores, capped at 64)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU port (0 = fastest count on this box, capped at 64)")
     ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--no-blocks", action="store_true", help="headline only: skip the c2 / batch / capacity_search / move_scoring blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gpu" else args.warmup
 
@@ -237,7 +446,6 @@ def main():
     value = world * D * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: host buffers -> C ABI -> host results ----
-    from simon_b200 import abi
     import ctypes as C
     from simon_b200.engine import lib
     L = lib()
@@ -260,62 +468,70 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * D * len(e2e_times) / float(te.item())
     placed = int((out_node >= 0).sum())
+    stats = eng.stats()
+    eng.close()
 
-    # ---- batch of independent what-if replicas on ONE GPU: one 16-CTA cluster each.  A cluster lives inside one GPC; on this
-    # part 7 such clusters are co-resident (tools/batch_scale.py: 1..7 scenarios take the same time, the 8th starts a second wave) ----
-    batch = None
-    if not args.no_batch and world == 1:
-        nb = 7
-        act = np.arange(int(c.n_nodes), dtype=np.uint32)
-        eng.run_scenarios([act] * nb)                                   # warm-up
-        flush.zero_()
-        torch.cuda.synchronize()
-        res, _ = eng.run_scenarios([act] * nb)
-        bms = eng.last_kernel_ms()
-        same = all(r["n_scheduled"] == placed - (P - D) or r["n_scheduled"] == placed for r in res)
-        batch = {"scenarios": nb, "value": nb * D / (bms * 1e-3), "unit": "decisions/s", "ms": bms, "identical_counts": bool(same),
-                 "note": "simon_scenarios_run: 7 independent replicas of the same workload placed concurrently on one GPU "
-                         "(the capacity-planning batch shape); aggregate, not the headline value"}
+    # ---- the other BASELINE configurations ----
+    blocks = {}
+    if not args.no_blocks:
+        def guarded(name, fn, *a):
+            try:
+                blocks[name] = fn(*a)
+            except Exception as e:       # noqa: BLE001  (a block must never take the headline down with it)
+                blocks[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1:
+            guarded("c2", block_c2, args, local, flush, torch)
+            if not args.no_batch:
+                guarded("batch", block_batch, args, c, D, P, placed, local, flush, torch)
+        guarded("capacity_search", block_capacity, args, rank, world, local, dist, torch)
+        guarded("move_scoring", block_moves, args, rank, world, local, dist, torch)
 
     if rank == 0:
         peak, peak_src = peaks()
         per_gpu_dps = D * args.steps / (ms_total * 1e-3)
         achieved = per_gpu_dps * ALGO_BYTES_PER_NODE_DECISION * args.nodes / 1e9
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
-            traffic = prof["dram_bytes_per_launch"]      # dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture
-        except Exception:
-            pass
+        traffic, traffic_src = None, None
+        for name in ("r02_ncu_full_summary.json", "r01_ncu_full_summary.json"):
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                traffic = prof["dram_bytes_per_launch"]      # dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture
+                traffic_src = f"profiles/{name} (one ncu --set full capture of the same launch shape; not measured in this run)"
+                break
+            except Exception:
+                continue
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NODE_DECISION * args.nodes * D,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NODE_DECISION * args.nodes * D,
                 "note": f"algorithmic bytes = {ALGO_BYTES_PER_NODE_DECISION} B/node-decision x {args.nodes} nodes x {D} decisions per launch; "
-                        "the snapshot is cluster-resident in shared memory, so DRAM traffic << algorithmic bytes"}
+                        "the snapshot is cluster-resident in shared memory, so DRAM traffic << algorithmic bytes and the kernel is bound by the "
+                        "latency of its per-decision reductions, not by HBM"}
         cb = None
         if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N = 1 only
             from oracle.binding import Oracle
             first_sched = int(np.argmax(c.pods["pod_fixed_node"] == -1))
             o = Oracle(c, threads=cpu_threads(args, c, first_sched))
-            sample = min(args.cpu_sample, P - first_sched)
             o.schedule(0, first_sched)
             t0 = time.perf_counter()
-            ref_nodes, _, _, _ = o.schedule(first_sched, sample)
+            ref_nodes, _, _, _ = o.schedule(first_sched, P - first_sched)        # EVERY decision of the timed pod list
             dt = time.perf_counter() - t0
-            agree = bool(np.array_equal(ref_nodes, out_node[first_sched:first_sched + sample]))
-            cb = {"value": sample / dt, "unit": "decisions/s", "cores": o.threads, "kind": "port",
-                  "sample": f"first {sample} scheduled pods of the same pod list (oracle/simon_oracle.c, per-node loops shared "
-                            f"between {o.threads} host threads, the fastest count on this box)",
-                  "placements_identical_on_sample": agree}
+            agree = bool(np.array_equal(ref_nodes, out_node[first_sched:]))
+            n_dec = int((c.pods["pod_fixed_node"][first_sched:] == -1).sum())
+            cb = {"value": n_dec / dt, "unit": "decisions/s", "cores": o.threads, "kind": "port",
+                  "sample": f"all {n_dec} decisions of the same pod list (oracle/simon_oracle.c, per-node loops shared "
+                            f"between {o.threads} host threads, the fastest count on this box; {host_cores()} cores visible)",
+                  "placements_identical": agree, "decisions_compared": n_dec, "go": go_probe()}
         line = {"metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args, c),
-                "roofline": roof, "cpu_baseline": cb, "batch": batch,
+                "roofline": roof, "cpu_baseline": cb,
                 "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * P + 8),
-                        "path": "simon_snapshot_upload + simon_pods_upload + simon_schedule(host out_node), wall clock"},
-                "gpu_launches": int(launches), "clocks": clocks, "decisions_per_step": D, "prebound_pods_per_step": P - D, "placed": placed, "unschedulable": int((out_node == -1).sum()),
-                "wall_s_timed_region": wall, "host_compile_s": host_s}
+                        "path": "simon_snapshot_upload + simon_pods_upload + simon_schedule(host out_node), wall clock; the host-side snapshot "
+                                "compile (host_compile_s) happens once per cluster and is reported separately"},
+                "gpu_launches": int(launches), "clocks": clocks, "decisions_per_step": D, "prebound_pods_per_step": P - D, "placed": placed,
+                "unschedulable": int((out_node == -1).sum()), "wall_s_timed_region": wall, "host_compile_s": host_s,
+                "kernel_stats": {k: stats[k] for k in ("class_switches", "summary_rebuilds", "redone", "single_flip_fast", "merged_decisions", "merged_redone")}}
+        line.update(blocks)
         print(json.dumps(line), flush=True)
-    eng.close()
     if dist is not None:
         dist.destroy_process_group()
 

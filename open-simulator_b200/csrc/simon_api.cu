@@ -134,7 +134,7 @@ struct simon_ctx {
     uint32_t dump_pod = 0xffffffffu;
     DevBuf<long long> d_dump_total;
     DevBuf<int32_t> d_dump_code;
-    uint32_t fast = 3;
+    uint32_t fast = 2;
     // candidate-move scoring (simon_moves_*)
     DevBuf<uint2> d_moves;
     DevBuf<int32_t> d_mv_gain;
@@ -142,7 +142,9 @@ struct simon_ctx {
     DevBuf<unsigned long long> d_mv_best_pod, d_mv_best;
     DevBuf<uint2> d_mv_topk;
     DevBuf<SmvNode> d_mv_nodes;
+    DevBuf<SmvClass> d_mv_classes;
     uint32_t mv_n = 0, mv_base = 0;
+    std::vector<uint8_t> bypass;        // per pod: never reaches the scheduler in a single-scenario run (pre-bound or absent)
     // single-scenario state
     ScenState st;
     uint32_t max_fail = 0;
@@ -316,6 +318,30 @@ int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t T
     return SIMON_OK;
 }
 
+// Place pods [first, first + count) of the single scenario: a long leading run of pods that bypass the scheduler is
+// accounted by the parallel import kernel, the rest by the persistent placement kernel.
+int launch_range(simon_ctx *ctx, SkParams &P, uint32_t CS, uint32_t TPB, size_t smem, uint32_t first, uint32_t count, bool record) {
+    uint32_t n_pre = 0;
+    while (n_pre < count && ctx->bypass[first + n_pre]) n_pre++;
+    if (n_pre < 256) n_pre = 0;
+    if (record) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (n_pre) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const uint32_t grid = std::min<uint32_t>((n_pre + 255) / 256, (uint32_t)sms * 4);
+        simon_import_kernel<<<grid, 256, 0, ctx->stream>>>(P, first, n_pre);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (count > n_pre) {
+        P.first = first + n_pre; P.count = count - n_pre;
+        int rc = launch(ctx, P, 1, CS, TPB, smem, false);
+        if (rc) return rc;
+    }
+    if (record) CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    return SIMON_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -469,6 +495,8 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
         }
         ax[SK_MAX_ENT] = n_dom | (n_all << 8) | (n_aff_node << 16);
         const int64_t *inc = cw + cw[SCW_OFF_INC];
+        for (uint32_t e = 0; e < E; e++)
+            for (uint32_t r = 0; r < ER_ROWS; r++) ax[SK_AUX_ENT + r * SK_MAX_ENT + e] = (uint32_t)(int32_t)et[8ull * e + r];
         for (uint32_t u = 0; u < 32 && (int64_t)u < cw[SCW_N_INC]; u++) {
             if (inc[3 * u] < 0 || (uint64_t)inc[3 * u] >= p->n_counters) return fail(ctx, SIMON_ERR_INVALID, "class %u: bad counter in the commit list", c);
             ax[SK_AUX_INCB + u] = (uint32_t)cnt_off[inc[3 * u]];
@@ -481,16 +509,48 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
         const uint64_t words = p->class_off[c + 1] - p->class_off[c];
         ulonglong2 a, b;
         a.x = (uint64_t)c | ((uint64_t)(uint32_t)p->pod_fixed_node[i] << 32);
-        a.y = (uint64_t)(uint32_t)guard[i] | (words << 32);
+        const uint64_t n_ent = (uint64_t)(cw[SCW_N_PORTS] + cw[SCW_N_PTS_HARD] + cw[SCW_N_PTS_SOFT] + cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] +
+                                          cw[SCW_N_IPA_EXIST] + cw[SCW_N_IPA_SCORE]);
+        a.y = (uint64_t)(uint32_t)guard[i] | (words << 32) | (n_ent << 56);       // words <= 16384, entries <= 32
         b.x = (uint64_t)(uint32_t)p->class_off[c] | ((uint64_t)(uint32_t)(int32_t)cw[SCW_EXTRA_ROW] << 32);
         b.y = (uint64_t)(uint32_t)(int32_t)cw[SCW_STATIC_SIG] | ((uint64_t)(uint32_t)(int32_t)cw[SCW_STATIC_ROW] << 32);
         meta[2ull * i] = a; meta[2ull * i + 1] = b;
     }
+    {
+        // compact per-class header of the move kernel (simon_moves.cu): scoring + Fit inputs and a few counts in 64 bytes
+        std::vector<SmvClass> mc(std::max(1u, p->n_classes));
+        for (uint32_t c = 0; c < p->n_classes; c++) {
+            const int64_t *cw = p->class_blob + p->class_off[c];
+            SmvClass &k = mc[c];
+            memset(&k, 0, sizeof(k));
+            k.score_mcpu = cw[SCW_SCORE_MCPU]; k.score_mem = cw[SCW_SCORE_MEM]; k.nz_mcpu = cw[SCW_NZ_MCPU]; k.nz_mem = cw[SCW_NZ_MEM];
+            k.req_mcpu = cw[SCW_REQ_MCPU]; k.req_mem = cw[SCW_REQ_MEM]; k.req_eph = cw[SCW_REQ_EPH];
+            k.sig = (uint32_t)cw[SCW_STATIC_SIG];
+            uint32_t bits = (uint32_t)cw[SCW_FLAGS] & 0xffu;
+            if (cw[SCW_N_PTS_HARD] > 0 || cw[SCW_GPU_MEM] > 0) bits |= SMC_NOT_MOVABLE;
+            const int64_t *sc = cw + cw[SCW_OFF_SCALARS];
+            for (uint32_t q = 0; q < ctx->K; q++) if (sc[q] != 0) bits |= SMC_HAS_SCALAR;
+            const uint32_t n_filt = (uint32_t)(cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] + cw[SCW_N_IPA_EXIST]);
+            bits |= ((uint32_t)cw[SCW_N_PORTS] & 31u) << 10;
+            bits |= (n_filt & 63u) << 15;
+            const int64_t *et = cw + cw[SCW_OFF_ENT];
+            const uint32_t E = (uint32_t)cw[SCW_N_ENT];
+            for (uint32_t e = 0; e < E; e++) if (et[8ull * e + ER_INC]) bits |= SMC_OWN_INC;
+            k.bits = bits;
+        }
+        CU(ctx->d_mv_classes.upload(mc.data(), mc.size(), st));
+        CU(cudaStreamSynchronize(st));       // `mc` leaves scope
+    }
+    ctx->bypass.assign(std::max(1u, p->n_pods), 0);
+    for (uint32_t i = 0; i < p->n_pods; i++) ctx->bypass[i] = (guard[i] == -2 || p->pod_fixed_node[i] != -1) ? 1 : 0;
     CU(ctx->d_cls_aux.upload(aux.data(), aux.size(), st));
     CU(ctx->d_pod_meta.upload(meta.data(), meta.size(), st));
     {
         const char *fv = getenv("SIMON_FAST");      // diagnostic switch: bit 0 merged arg-max, bit 1 class-context prefetch
-        ctx->fast = fv ? (uint32_t)strtoul(fv, nullptr, 0) : 3u;
+        // default: prefetch on, merged arg-max off - on C3 a third of the decisions see a feasibility flip (the winner of a
+        // class with required anti-affinity always leaves the feasible set), those are redone, and the larger merged message
+        // costs more than the exchange it saves (profiles/r02_ubench_cluster.txt, r02_kernel_variants.txt)
+        ctx->fast = fv ? (uint32_t)strtoul(fv, nullptr, 0) : 2u;
     }
     CU(cudaStreamSynchronize(st));
     ctx->max_fail = std::max(1u, p->n_pods);      // every pod of the list may fail: one histogram row each (96 B)
@@ -561,7 +621,7 @@ int simon_schedule(simon_ctx *ctx, uint32_t first, uint32_t count, int32_t *out_
         CU(cudaMemsetAsync(ctx->d_dump_total.p, 0xff, 8ull * std::max(1u, ctx->N), st));     // -1: node not scored (infeasible)
         CU(cudaMemsetAsync(ctx->d_dump_code.p, 0, 4ull * std::max(1u, ctx->N), st));
     }
-    rc = launch(ctx, P, 1, CS, TPB, smem);
+    rc = launch_range(ctx, P, CS, TPB, smem, first, count, true);
     if (rc) return rc;
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(ctx, SIMON_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
@@ -598,7 +658,7 @@ int simon_replay(simon_ctx *ctx, uint32_t steps, float *out_ms_total) {
         if (rc) return rc;
         CU(cudaMemsetAsync(ctx->st.fail_counts.p, 0, 4ull * ctx->max_fail * SIMON_N_FAIL_CODES, st));
         CU(cudaMemsetAsync(ctx->st.counters.p, 0, 8, st));
-        rc = launch(ctx, P, 1, CS, TPB, smem, false);
+        rc = launch_range(ctx, P, CS, TPB, smem, 0, ctx->n_pods, false);
         if (rc) return rc;
     }
     CU(cudaEventRecord(ctx->ev1, st));
@@ -771,15 +831,19 @@ static int moves_launch(simon_ctx *ctx, bool record) {
     P.N = N; P.K = ctx->K; P.WT = ctx->WT; P.T = ctx->T; P.n_pods = ctx->n_pods; P.n_moves = n; P.use_scache = ctx->use_scache;
     P.nodes = ctx->d_mv_nodes.p; P.alloc_scalar = ctx->d_alloc_scalar.p; P.req_scalar = ctx->st.req_scalar.p; P.node_flags = ctx->d_node_flags.p;
     P.label_bits = ctx->d_label_bits.p; P.taint_hard = ctx->d_taint_hard.p; P.topo_dom = ctx->d_topo_dom.p;
-    P.class_off = ctx->d_class_off.p; P.class_blob = ctx->d_class_blob.p; P.pod_class = ctx->d_pod_class.p; P.placement = ctx->st.out_node.p;
+    P.class_off = ctx->d_class_off.p; P.class_blob = ctx->d_class_blob.p; P.classes = ctx->d_mv_classes.p; P.pod_class = ctx->d_pod_class.p; P.placement = ctx->st.out_node.p;
     P.cnt = ctx->st.cnt.p; P.cnt_total = ctx->st.cnt_total.p; P.scache = ctx->d_scache.p; P.moves = ctx->d_moves.p;
     P.out_gain = ctx->d_mv_gain.p; P.out_code = ctx->d_mv_code.p; P.best_per_pod = ctx->d_mv_best_pod.p; P.best_global = ctx->d_mv_best.p;
     P.hist = ctx->d_mv_hist.p; P.move_base = ctx->mv_base;
     if (n) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        const uint32_t grid = std::min<uint32_t>((n + 255) / 256, (uint32_t)sms * 8);      // 8 resident CTAs of 256 threads per SM
-        simon_moves_kernel<<<grid, 256, 0, st>>>(P);
+        // occupancy variant: 4 resident CTAs per SM (64 registers, a few spills) by default; SIMON_MOVES_OCC=2 selects the
+        // 2-CTA variant without spills (diagnostic switch)
+        static const int occ = getenv("SIMON_MOVES_OCC") ? atoi(getenv("SIMON_MOVES_OCC")) : 4;
+        const uint32_t grid = std::min<uint32_t>((n + 255) / 256, (uint32_t)sms * (occ == 2 ? 2u : 4u) * 2u);
+        if (occ == 2) simon_moves_kernel<2><<<grid, 256, 0, st>>>(P);
+        else simon_moves_kernel<4><<<grid, 256, 0, st>>>(P);
         ctx->launches++;
     }
     if (record) CU(cudaEventRecord(ctx->ev1, st));

@@ -27,8 +27,10 @@ namespace cg = cooperative_groups;
 #define SK_PLW 5            // payload: 10 int32 packed in 5 u64 (T domains + flags)
 #define SK_MAX_WARPS 16     // threads per CTA <= 512 (the shipped variants use <= 320)
 #define SK_CSUM_W 30          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains, score ranges (4) + their valid flag
-#define SK_AUX_W 68           // per-class commit tables built at upload: [0..32] compact commit list (+ count word), [33..64] counter bases, pad
+#define SK_AUX_W 324          // per-class tables built at upload: [0..32] compact commit list (+ count word), [33..64] counter bases, pad,
+                              //   [68..323] the entry table transposed to int32 rows: [ER_ROWS][SK_MAX_ENT]
 #define SK_AUX_INCB 33
+#define SK_AUX_ENT 68
 #define SK_XROW (1 + SK_PLW)  // first inbox row of the extra words of the merged arg-max (rows 0..SK_PLW: key + payload)
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };

@@ -18,13 +18,27 @@
 // sectors instead of two dozen; the move list itself streams through coalesced 8-byte loads.
 #pragma once
 
-struct __align__(32) SmvNode {          // 96 bytes
-    int64_t alloc_mcpu, alloc_mem, alloc_eph, req_mcpu;
-    int64_t req_mem, req_eph, nz_mcpu, nz_mem;
-    int32_t alloc_pods, num_pods;
-    int32_t dom[6];                     // domains of topologies 1..6 (topology 0 is the node itself)
+struct __align__(32) SmvNode {          // 96 bytes = three 32-byte sectors, ordered by who needs them:
+    int64_t alloc_mcpu, alloc_mem, nz_mcpu, nz_mem;      // sector 0: scoring inputs (target AND source node of a move)
+    int64_t alloc_eph, req_mcpu, req_mem, req_eph;       // sector 1: NodeResourcesFit inputs (target only)
+    int32_t alloc_pods, num_pods;                        // sector 2: pod count + domains (target; source only for classes that
+    int32_t dom[6];                                      //           increment counters), topologies 1..6 (0 is the node itself)
 };
 static_assert(sizeof(SmvNode) == 96, "SmvNode layout");
+
+// per-class header of the move kernel (64 bytes = two sectors), built at upload from the class record
+struct __align__(32) SmvClass {
+    int64_t score_mcpu, score_mem, nz_mcpu, nz_mem;      // sector 0: scoring
+    int64_t req_mcpu, req_mem, req_eph;                  // sector 1: Fit
+    uint32_t sig;                                        //           static signature
+    uint32_t bits;                                       //           flags:8 | not movable:1 | has scalar request:1 | n_ports:5 | n_filter entries (aff+anti+exist):6 | own increments:1
+};
+static_assert(sizeof(SmvClass) == 64, "SmvClass layout");
+#define SMC_NOT_MOVABLE (1u << 8)
+#define SMC_HAS_SCALAR (1u << 9)
+#define SMC_NPORTS(b) (((b) >> 10) & 31u)
+#define SMC_NFILT(b) (((b) >> 15) & 63u)
+#define SMC_OWN_INC (1u << 21)
 
 #define SMV_OK 0u
 #define SMV_NOOP (1u << 24)            // target == current node
@@ -43,6 +57,7 @@ struct SmvParams {
     const int32_t *topo_dom;
     const uint64_t *class_off;
     const int64_t *class_blob;
+    const SmvClass *classes;
     const int32_t *pod_class, *placement;
     const int32_t *cnt, *cnt_total;
     unsigned long long *scache;
@@ -69,13 +84,20 @@ __global__ void simon_moves_pack(uint32_t N, uint32_t T, const int64_t *alloc_mc
     out[g] = r;
 }
 
+// sector mask: bit s = load the s-th 32-byte sector of the record (the others stay zero and are never read)
+template <int MASK>
 __device__ __forceinline__ SmvNode smv_load(const SmvNode *p) {
     SmvNode r;
     const int4 *q = reinterpret_cast<const int4 *>(p);
     int4 *d = reinterpret_cast<int4 *>(&r);
 #pragma unroll
-    for (int i = 0; i < 6; i++) d[i] = __ldg(q + i);
+    for (int i = 0; i < 6; i++) d[i] = ((MASK >> (i >> 1)) & 1) ? __ldg(q + i) : make_int4(0, 0, 0, 0);
     return r;
+}
+__device__ __forceinline__ void smv_load_sector(SmvNode &r, const SmvNode *p, int sec) {
+    const int4 *q = reinterpret_cast<const int4 *>(p);
+    int4 *d = reinterpret_cast<int4 *>(&r);
+    d[2 * sec] = __ldg(q + 2 * sec); d[2 * sec + 1] = __ldg(q + 2 * sec + 1);
 }
 
 // LeastAllocated + BalancedAllocation for a pod with scoring request (sc, sm) on a node whose NonZeroRequested is (nzc, nzm)
@@ -104,7 +126,8 @@ __device__ __forceinline__ int32_t smv_dom(const SmvParams &P, const SmvNode &n,
     return __ldg(P.topo_dom + (uint64_t)t * P.N + g);
 }
 
-__global__ void __launch_bounds__(256) simon_moves_kernel(const __grid_constant__ SmvParams P) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) simon_moves_kernel(const __grid_constant__ SmvParams P) {
     __shared__ uint32_t s_hist[SMV_NBINS];
     for (uint32_t q = threadIdx.x; q < SMV_NBINS; q += blockDim.x) s_hist[q] = 0;
     __syncthreads();
@@ -124,17 +147,28 @@ __global__ void __launch_bounds__(256) simon_moves_kernel(const __grid_constant_
         }
         if (code == SMV_OK) {
             const int32_t cls = __ldg(P.pod_class + pod);
-            const int64_t *cw = P.class_blob + __ldg(P.class_off + cls);
-            if (__ldg(cw + SCW_N_PTS_HARD) > 0 || __ldg(cw + SCW_GPU_MEM) > 0) code = SMV_NOT_MOVABLE;
+            const int4 *ch = reinterpret_cast<const int4 *>(P.classes + cls);
+            SmvClass kc;
+            {
+                int4 *d = reinterpret_cast<int4 *>(&kc);
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[i] = __ldg(ch + i);
+            }
+            const uint32_t bits = kc.bits, cflags = bits & 0xffu;
+            if (bits & SMC_NOT_MOVABLE) code = SMV_NOT_MOVABLE;
             else {
-                const SmvNode nb = smv_load(P.nodes + b), na = smv_load(P.nodes + a);
-                const uint32_t cflags = (uint32_t)__ldg(cw + SCW_FLAGS);
+                const uint32_t n_ports = SMC_NPORTS(bits), n_filt = SMC_NFILT(bits);
+                const bool need_ent = (n_ports | n_filt) != 0;
+                const SmvNode nb = smv_load<7>(P.nodes + b);
+                SmvNode na = smv_load<1>(P.nodes + a);
+                if (need_ent && (bits & SMC_OWN_INC)) smv_load_sector(na, P.nodes + a, 2);       // the source's domains: only to take p's own counts out
                 // ---- static verdict of (class, b): cached per (static signature, node) by the placement kernel, or computed here
-                const int64_t sig = __ldg(cw + SCW_STATIC_SIG);
-                unsigned long long rec = P.use_scache ? __ldcg(P.scache + (uint64_t)sig * P.N + b) : 0ull;
+                unsigned long long rec = P.use_scache ? __ldcg(P.scache + (uint64_t)kc.sig * P.N + b) : 0ull;
                 uint32_t st_code;
+                const int64_t *cw = nullptr;
                 if (rec & (1ull << 24)) st_code = (uint32_t)(rec & 0xff);
                 else {
+                    cw = P.class_blob + __ldg(P.class_off + cls);
                     const bool ok = selection_ok(cw, RC, b);
                     const int64_t *tol = cw + cw[SCW_OFF_TOL];
                     st_code = 0;
@@ -146,9 +180,8 @@ __global__ void __launch_bounds__(256) simon_moves_kernel(const __grid_constant_
                     if (!st_code && !ok) st_code = 4;
                 }
                 if (st_code) code = 1u << SFC_STATIC;
-                const int64_t *et = cw + cw[SCW_OFF_ENT];
-                const uint32_t n_ports = (uint32_t)cw[SCW_N_PORTS], n_soft = (uint32_t)cw[SCW_N_PTS_SOFT], n_aff = (uint32_t)cw[SCW_N_IPA_AFF];
-                const uint32_t n_anti = (uint32_t)cw[SCW_N_IPA_ANTI], n_exist = (uint32_t)cw[SCW_N_IPA_EXIST];
+                if (code == SMV_OK && need_ent && !cw) cw = P.class_blob + __ldg(P.class_off + cls);
+                const int64_t *et = need_ent && cw ? cw + cw[SCW_OFF_ENT] : nullptr;
                 // counter value of entry e at b's domain with p's own contribution (made from node a) removed
                 auto val_at = [&](uint32_t e, int32_t d) -> int32_t {
                     const int64_t *r = et + 8ull * e;
@@ -165,47 +198,53 @@ __global__ void __launch_bounds__(256) simon_moves_kernel(const __grid_constant_
                     uint32_t rs = 0;
                     if (nb.num_pods + 1 > nb.alloc_pods) rs |= 1u << SFC_TOO_MANY_PODS;
                     if (cflags & SIMON_CLS_HAS_REQUEST) {
-                        if (nb.alloc_mcpu < cw[SCW_REQ_MCPU] + nb.req_mcpu) rs |= 1u << SFC_CPU;
-                        if (nb.alloc_mem < cw[SCW_REQ_MEM] + nb.req_mem) rs |= 1u << SFC_MEM;
-                        if (nb.alloc_eph < cw[SCW_REQ_EPH] + nb.req_eph) rs |= 1u << SFC_EPH;
-                        const int64_t *sc_req = cw + cw[SCW_OFF_SCALARS];
-                        for (uint32_t k = 0; k < P.K; k++)
-                            if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * P.N + b] < sc_req[k] + P.req_scalar[(uint64_t)k * P.N + b]) rs |= 1u << (SFC_SCALAR0 + k);
+                        if (nb.alloc_mcpu < kc.req_mcpu + nb.req_mcpu) rs |= 1u << SFC_CPU;
+                        if (nb.alloc_mem < kc.req_mem + nb.req_mem) rs |= 1u << SFC_MEM;
+                        if (nb.alloc_eph < kc.req_eph + nb.req_eph) rs |= 1u << SFC_EPH;
+                        if (bits & SMC_HAS_SCALAR) {
+                            const int64_t *cw3 = cw ? cw : P.class_blob + __ldg(P.class_off + cls);
+                            const int64_t *sc_req = cw3 + cw3[SCW_OFF_SCALARS];
+                            for (uint32_t k = 0; k < P.K; k++)
+                                if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * P.N + b] < sc_req[k] + P.req_scalar[(uint64_t)k * P.N + b]) rs |= 1u << (SFC_SCALAR0 + k);
+                        }
                     }
                     code = rs;
                 }
                 // ---- InterPodAffinity (filtering.go:317-401) on the counters, p's own increments taken out
-                const uint32_t e_aff = n_ports + n_soft, e_anti = e_aff + n_aff, e_exist = e_anti + n_anti, e_end = e_exist + n_exist;
-                if (code == SMV_OK && n_aff) {
-                    bool pods_exist = true, missing = false;
-                    long long aff_total = 0;
-                    for (uint32_t e = e_aff; e < e_anti; e++) {
-                        const int64_t *r = et + 8ull * e;
-                        aff_total += __ldg(P.cnt_total + r[ER_K]);
-                        if (r[ER_INC] && smv_dom(P, na, (uint32_t)a, r[ER_T]) >= 0) aff_total -= 1;
-                        const int32_t d = smv_dom(P, nb, b, r[ER_T]);
-                        if (d < 0) { missing = true; continue; }
-                        if (val_at(e, d) <= 0) pods_exist = false;
+                if (code == SMV_OK && n_filt) {
+                    const uint32_t n_soft = (uint32_t)cw[SCW_N_PTS_SOFT], n_aff = (uint32_t)cw[SCW_N_IPA_AFF];
+                    const uint32_t n_anti = (uint32_t)cw[SCW_N_IPA_ANTI], n_exist = (uint32_t)cw[SCW_N_IPA_EXIST];
+                    const uint32_t e_aff = n_ports + n_soft, e_anti = e_aff + n_aff, e_exist = e_anti + n_anti, e_end = e_exist + n_exist;
+                    if (n_aff) {
+                        bool pods_exist = true, missing = false;
+                        long long aff_total = 0;
+                        for (uint32_t e = e_aff; e < e_anti; e++) {
+                            const int64_t *r = et + 8ull * e;
+                            aff_total += __ldg(P.cnt_total + r[ER_K]);
+                            if (r[ER_INC] && smv_dom(P, na, (uint32_t)a, r[ER_T]) >= 0) aff_total -= 1;
+                            const int32_t d = smv_dom(P, nb, b, r[ER_T]);
+                            if (d < 0) { missing = true; continue; }
+                            if (val_at(e, d) <= 0) pods_exist = false;
+                        }
+                        bool ok = true;
+                        if (missing) ok = false;
+                        else if (!pods_exist) ok = aff_total == 0 && (cflags & SIMON_CLS_IPA_SELF_MATCH);
+                        if (!ok) code = 1u << SFC_IPA_AFF;
                     }
-                    bool ok = true;
-                    if (missing) ok = false;
-                    else if (!pods_exist) ok = aff_total == 0 && (cflags & SIMON_CLS_IPA_SELF_MATCH);
-                    if (!ok) code = 1u << SFC_IPA_AFF;
+                    if (code == SMV_OK)
+                        for (uint32_t e = e_anti; e < e_exist; e++) {
+                            const int32_t d = smv_dom(P, nb, b, (et + 8ull * e)[ER_T]);
+                            if (d >= 0 && val_at(e, d) > 0) { code = 1u << SFC_IPA_ANTI; break; }
+                        }
+                    if (code == SMV_OK)
+                        for (uint32_t e = e_exist; e < e_end; e++) {
+                            const int32_t d = smv_dom(P, nb, b, (et + 8ull * e)[ER_T]);
+                            if (d >= 0 && val_at(e, d) > 0) { code = 1u << SFC_IPA_EXIST; break; }
+                        }
                 }
-                if (code == SMV_OK)
-                    for (uint32_t e = e_anti; e < e_exist; e++) {
-                        const int32_t d = smv_dom(P, nb, b, (et + 8ull * e)[ER_T]);
-                        if (d >= 0 && val_at(e, d) > 0) { code = 1u << SFC_IPA_ANTI; break; }
-                    }
-                if (code == SMV_OK)
-                    for (uint32_t e = e_exist; e < e_end; e++) {
-                        const int32_t d = smv_dom(P, nb, b, (et + 8ull * e)[ER_T]);
-                        if (d >= 0 && val_at(e, d) > 0) { code = 1u << SFC_IPA_EXIST; break; }
-                    }
                 if (code == SMV_OK) {
-                    const int32_t on_b = smv_own(nb.alloc_mcpu, nb.alloc_mem, nb.nz_mcpu, nb.nz_mem, cw[SCW_SCORE_MCPU], cw[SCW_SCORE_MEM]);
-                    const int32_t on_a = smv_own(na.alloc_mcpu, na.alloc_mem, na.nz_mcpu - cw[SCW_NZ_MCPU], na.nz_mem - cw[SCW_NZ_MEM],
-                                                 cw[SCW_SCORE_MCPU], cw[SCW_SCORE_MEM]);
+                    const int32_t on_b = smv_own(nb.alloc_mcpu, nb.alloc_mem, nb.nz_mcpu, nb.nz_mem, kc.score_mcpu, kc.score_mem);
+                    const int32_t on_a = smv_own(na.alloc_mcpu, na.alloc_mem, na.nz_mcpu - kc.nz_mcpu, na.nz_mem - kc.nz_mem, kc.score_mcpu, kc.score_mem);
                     gain = on_b - on_a;
                 }
             }

@@ -115,12 +115,17 @@ def scenario_key(sc: Scenario, res: Dict[str, int], max_cpu: int, max_mem: int) 
 Runner = Callable[[ScenarioSet, List[Scenario]], List[Dict[str, int]]]
 
 
-def gpu_runner(device: int = 0) -> Runner:
-    """Runs a shard of scenarios on one GPU through simon_scenarios_run (one thread-block cluster per scenario)."""
+def gpu_runner(device: int = 0, engine=None) -> Runner:
+    """Runs a shard of scenarios on one GPU through simon_scenarios_run (one thread-block cluster per scenario).
+    With `engine` (an Engine holding ss.compiled) the context, its uploaded snapshot and its pooled scenario buffers are
+    reused across calls - the shape of a capacity search that tries several candidate sets on one cluster."""
     def run(ss: ScenarioSet, shard: List[Scenario]) -> List[Dict[str, int]]:
         from .engine import Engine
         if not shard:
             return []
+        if engine is not None:
+            out, _ = engine.run_scenarios([sc.nodes for sc in shard])
+            return out
         with Engine(ss.compiled, device=device) as eng:
             out, _ = eng.run_scenarios([sc.nodes for sc in shard])
         return out
