@@ -1056,13 +1056,15 @@ def _emit_term(body: List[int], term):
         _emit_req(body, r)
 
 
-def _simon_raw(reqs: Dict[str, Quantity], alloc: Dict[str, Quantity]) -> int:
-    """Simon.Score raw value (pkg/simulator/plugin/simon.go:45-68)."""
-    if len(reqs) == 0:
-        return 100
-    res = 0.0
-    for name, aq in alloc.items():
-        pq = reqs.get(name)
+_SHARE_MEMO: Dict[tuple, float] = {}
+
+
+def _simon_share(pq: Optional[Quantity], aq: Quantity) -> float:
+    """algo.Share(podReq, nodeAlloc - podReq) of one resource (pkg/algo/greed.go:70-83, simon.go:56-62), memoised on the two
+    quantities' (value, scale, format) keys: clusters have few distinct request / allocatable values per resource."""
+    key = (pq.key() if pq is not None else None, aq.key())
+    v = _SHARE_MEMO.get(key)
+    if v is None:
         if pq is None:
             pq = Quantity()
         avail = aq.copy()
@@ -1070,9 +1072,22 @@ def _simon_raw(reqs: Dict[str, Quantity], alloc: Dict[str, Quantity]) -> int:
         a = pq.as_approximate_float64()
         t = avail.as_approximate_float64()
         if t == 0:
-            share = 0.0 if a == 0 else 1.0
+            v = 0.0 if a == 0 else 1.0
         else:
-            share = a / t
+            v = a / t
+        if len(_SHARE_MEMO) > 200000:
+            _SHARE_MEMO.clear()
+        _SHARE_MEMO[key] = v
+    return v
+
+
+def _simon_raw(reqs: Dict[str, Quantity], alloc: Dict[str, Quantity]) -> int:
+    """Simon.Score raw value (pkg/simulator/plugin/simon.go:45-68)."""
+    if len(reqs) == 0:
+        return 100
+    res = 0.0
+    for name, aq in alloc.items():
+        share = _simon_share(reqs.get(name), aq)
         if share > res:
             res = share
     x = float(100) * res

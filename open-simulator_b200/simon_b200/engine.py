@@ -21,7 +21,7 @@ EXPORTS = ["simon_gpu_version", "simon_ctx_create", "simon_ctx_destroy", "simon_
            "simon_pods_upload", "simon_state_reset", "simon_schedule", "simon_results_download", "simon_last_kernel_ms",
            "simon_launch_count", "simon_state_download", "simon_scenarios_run", "simon_replay", "simon_stats",
            "simon_gpu_slots_download", "simon_state_download_ext", "simon_debug_set_dump_pod", "simon_debug_dump_read",
-           "simon_moves_upload", "simon_moves_run", "simon_moves_replay"]
+           "simon_moves_upload", "simon_moves_run", "simon_moves_replay", "simon_host_go118_sort"]
 
 
 class EngineUnavailable(RuntimeError):
@@ -78,6 +78,8 @@ def lib():
     L.simon_moves_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.simon_moves_replay.restype = C.c_int
     L.simon_moves_replay.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    L.simon_host_go118_sort.restype = C.c_int
+    L.simon_host_go118_sort.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     _LIB = L
     return L
 

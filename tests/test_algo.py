@@ -231,3 +231,18 @@ def test_order_app_pods_runs_both_sorts_in_sequence():
             R("d", {"nodeSelector": {"k": "v"}, "tolerations": [{"operator": "Exists"}]})]
     order_app_pods(pods)
     assert [p.name for p in pods] == ["b", "d", "a", "c"]
+
+
+@pytest.mark.parametrize("n,seed", [(64, 1), (400, 6), (5000, 8), (100000, 9)])
+def test_compiled_sort_matches_python_restatement(n, seed):
+    """simon_host_go118_sort (the compiled host-side restatement inside the engine library) gives the permutation of algo.py."""
+    import numpy as np
+    from simon_b200.engine import lib
+    rng = random.Random(seed)
+    flags = [rng.random() < 0.3 for _ in range(n)]
+    want = list(range(n))
+    go118_sort(want, lambda a, b: flags[a])
+    fl = np.array(flags, dtype=np.uint8)
+    perm = np.arange(n, dtype=np.uint32)
+    assert lib().simon_host_go118_sort(fl.ctypes.data, n, perm.ctypes.data) == 0
+    assert perm.tolist() == want

@@ -82,7 +82,7 @@ def test_abi_library_exports():
     import os, re
     from simon_b200 import engine
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "simon_gpu.h")).read()
-    declared = set(re.findall(r"^(?:int|void|float|uint64_t|const char \*)\s*(simon_[a-z_]+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^(?:int|void|float|uint64_t|const char \*)\s*(simon_[a-z0-9_]+)\s*\(", hdr, re.M))
     L = engine.lib()
     for name in declared:
         assert hasattr(L, name), name
