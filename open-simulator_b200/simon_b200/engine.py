@@ -203,7 +203,9 @@ class Engine:
         return dict(req_scalar=rs[:K, :N], gpu_used=gu[:, :N])
 
     def dump_pod(self, pod: int):
-        """Schedule up to and including `pod`; return (out_node of the range, per-node totals, per-node filter verdicts)."""
+        """From the EMPTY state, schedule up to and including `pod`; return (out_node of the range, per-node totals,
+        per-node filter verdicts of that pod).  Leaves the context in that partial state."""
+        self.reset()
         self._check(lib().simon_debug_set_dump_pod(self.h, pod))
         out = self.schedule(0, pod + 1)[0]
         self._check(lib().simon_debug_set_dump_pod(self.h, 0xffffffff))

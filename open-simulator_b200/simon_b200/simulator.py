@@ -61,6 +61,7 @@ class SimulatorOptions:
 
 
 Option = Callable[[SimulatorOptions], None]
+MAX_GPU_FAIL_DETAIL = 32      # unschedulable GPU-share pods whose per-node failure list is collected (one partial re-run each)
 
 
 def WithKubeConfig(path: str) -> Option:
@@ -121,8 +122,11 @@ _DYNAMIC_REASONS = {
 }
 
 
-def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active: Optional[List[int]] = None) -> str:
-    """FitError.Error() (generic_scheduler.go:72-90) + the wrapper of Simulator.update (simulator.go:465)."""
+def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active: Optional[List[int]] = None,
+                     gpu_nodes: Optional[List[str]] = None) -> str:
+    """FitError.Error() (generic_scheduler.go:72-90) + the wrapper of Simulator.update (simulator.go:465).
+    gpu_nodes: names of the nodes the Open-Gpu-Share filter rejected - its status message is "Node:<name>"
+    (pkg/simulator/plugin/open-gpu-share.go:66-79), so every such node contributes its own reason string with count 1."""
     from .selectors import pod_matches_node_selector_and_affinity, tolerations_tolerate_taint
     reasons = {}
     spec = rec.tmpl.spec
@@ -158,7 +162,11 @@ def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active
         if c:
             reasons["Insufficient " + nm] = reasons.get("Insufficient " + nm, 0) + c
     if int(counts[19]):
-        reasons["Node:<gpu>"] = int(counts[19])
+        if gpu_nodes is not None and len(gpu_nodes) == int(counts[19]):
+            for nm in gpu_nodes:
+                reasons["Node:" + nm] = reasons.get("Node:" + nm, 0) + 1
+        else:       # node list not collected (more failing GPU pods than the re-evaluation budget): counts only
+            reasons["Node:<%d nodes rejected by Open-Gpu-Share>" % int(counts[19])] = int(counts[19])
     total = len(idxs)
     parts = sorted(f"{v} {k}" for k, v in reasons.items())
     msg = f"0/{total} nodes are available: {', '.join(parts)}."
@@ -166,7 +174,7 @@ def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active
     return f"failed to schedule pod ({ns}/{rec.name}): Unschedulable: {msg}"
 
 
-def build_result(compiled: Compiled, p: Plan, out_node: np.ndarray, fail_counts, fail_pod) -> SimulateResult:
+def build_result(compiled: Compiled, p: Plan, out_node: np.ndarray, fail_counts, fail_pod, gpu_fail_nodes=None) -> SimulateResult:
     res = SimulateResult()
     statuses = [NodeStatus(Node=n) for n in p.nodes]
     by_sorted = {i: statuses[compiled.node_orig_index[i]] for i in range(compiled.n_nodes)}
@@ -180,7 +188,7 @@ def build_result(compiled: Compiled, p: Plan, out_node: np.ndarray, fail_counts,
         elif n == -1:
             j = fail_idx.get(i)
             counts = fail_counts[j] if j is not None and j < len(fail_counts) else np.zeros(24, np.uint32)
-            res.UnscheduledPods.append(UnscheduledPod(rec, format_fit_error(compiled, rec, counts)))
+            res.UnscheduledPods.append(UnscheduledPod(rec, format_fit_error(compiled, rec, counts, gpu_nodes=(gpu_fail_nodes or {}).get(i))))
     res.NodeStatus = statuses
     return res
 
@@ -204,6 +212,14 @@ def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> 
     from .engine import Engine     # raises if libsimon_gpu.so / CUDA is unavailable: no CPU fallback
     p = plan(cluster, apps)
     compiled = compile_cluster(p.nodes, p.pods, p.ctx)
+    gpu_fail_nodes = {}
     with Engine(compiled, device=options.device, record_scores=options.record_scores) as eng:
         out_node, _scores, fail_counts, fail_pod = eng.schedule()
-    return build_result(compiled, p, out_node, fail_counts, fail_pod)
+        # Open-Gpu-Share's failure reason names the node, so the histogram needs the node LIST of such pods, not a count:
+        # re-evaluate those pods with the per-node verdict dump (a bounded number of them - each costs a partial re-run)
+        gpu_bit = 1 << 19
+        todo = [int(pod) for j, pod in enumerate(fail_pod) if j < len(fail_counts) and int(fail_counts[j][19]) > 0][:MAX_GPU_FAIL_DETAIL]
+        for pod in todo:
+            _o, _t, code = eng.dump_pod(pod)
+            gpu_fail_nodes[pod] = [compiled.node_names[g] for g in np.nonzero(code & gpu_bit)[0]]
+    return build_result(compiled, p, out_node, fail_counts, fail_pod, gpu_fail_nodes)

@@ -104,3 +104,73 @@ def test_scenarios_gpu_match_oracle():
     best_gpu, _ = capacity.search(ss, capacity.gpu_runner(0))
     best_ref, _ = capacity.search(ss, oracle_runner)
     assert best_gpu == best_ref
+
+
+def _oracle_factory(ss):
+    return oracle_runner
+
+
+def test_auto_add_nodes_sweep_and_bisect_agree():
+    """The automatic replacement of the interactive add-node loop (pkg/apply/apply.go:203-259): the sweep over k and the
+    bisection find the same minimal node count, and that count is tight (k-1 leaves pods unscheduled or breaks a cap)."""
+    from simon_b200 import apply as A, capacity, synth
+    cluster, apps, specs = synth.make_c4(n_nodes=12, n_workloads=8, replicas=15, seed_no=4)
+    sweep = A.auto_add_nodes(cluster, apps, specs[1], _oracle_factory, kmax=24, method="sweep")
+    bis = A.auto_add_nodes(cluster, apps, specs[1], _oracle_factory, kmax=24, method="bisect")
+    assert sweep.new_node_num == bis.new_node_num and sweep.new_node_num > 0
+    assert sweep.unscheduled_without_new_nodes > 0
+    assert bis.scenarios_evaluated < sweep.scenarios_evaluated and bis.rounds <= 7
+    k = sweep.new_node_num
+    r1, r0 = sweep.per_k[k], sweep.per_k[k - 1]
+    assert r1["n_unscheduled"] == 0 and capacity.occupancy_ok(r1)
+    assert r0["n_unscheduled"] > 0 or not capacity.occupancy_ok(r0)
+    # monotone: every k beyond the minimum is feasible as well
+    assert all(sweep.per_k[q]["n_unscheduled"] == 0 for q in range(k, 25))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/example"), reason="reference tree not present (GPU box)")
+def test_apply_config_of_the_reference_example(tmp_path):
+    """example/simon-config.yaml with `customConfig: example/cluster/demo_1` (the shipped file points at a developer's
+    kubeConfig) and the non-chart, non-open-local apps: the 4-node demo cluster cannot hold them, the search
+    reports how many copies of example/newnode/demo_1 are needed."""
+    import yaml
+    from simon_b200 import apply as A
+    cfg = {"apiVersion": "simon/v1alpha1", "kind": "Config", "metadata": {"name": "simon-config"},
+           "spec": {"cluster": {"customConfig": "example/cluster/demo_1"},
+                    "appList": [{"name": "simple", "path": "example/application/simple"},
+                                {"name": "complicated", "path": "example/application/complicate"},
+                                {"name": "more_pods", "path": "example/application/more_pods"}],
+                    "newNode": "example/newnode/demo_1"}}
+    path = tmp_path / "simon-config.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    cluster, apps, new_node = A.load_config(str(path), base_dir="/root/reference")
+    assert len(cluster.Nodes) == 4 and len(apps) == 3 and new_node["metadata"]["name"] == "node-1"
+    res = A.auto_add_nodes(cluster, apps, new_node, _oracle_factory, kmax=32, method="bisect")
+    assert res.unscheduled_without_new_nodes > 0
+    assert res.new_node_num > 0
+    sweep = A.auto_add_nodes(cluster, apps, new_node, _oracle_factory, kmax=res.new_node_num + 2, method="sweep")
+    assert sweep.new_node_num == res.new_node_num
+    # the shipped config itself is refused for what it is (kubeConfig of a developer machine / Helm chart), not ignored
+    with pytest.raises(NotImplementedError):
+        A.load_config("/root/reference/example/simon-config.yaml", base_dir="/root/reference")
+
+
+@pytest.mark.gpu
+def test_auto_add_nodes_gpu_matches_oracle():
+    from simon_b200 import apply as A, capacity, synth
+    from simon_b200.engine import Engine
+    cluster, apps, specs = synth.make_c4(n_nodes=12, n_workloads=8, replicas=15, seed_no=4)
+    want = A.auto_add_nodes(cluster, apps, specs[1], _oracle_factory, kmax=16, method="sweep")
+    engines = []
+
+    def factory(ss):
+        e = Engine(ss.compiled, device=0)
+        engines.append(e)
+        return capacity.gpu_runner(0, engine=e)
+
+    got = A.auto_add_nodes(cluster, apps, specs[1], factory, kmax=16, method="sweep")
+    got_b = A.auto_add_nodes(cluster, apps, specs[1], factory, kmax=16, method="bisect")
+    for e in engines:
+        e.close()
+    assert got.new_node_num == want.new_node_num == got_b.new_node_num
+    assert got.per_k == want.per_k

@@ -187,3 +187,23 @@ def test_kernel_paths_agree(fast, monkeypatch):
     np.testing.assert_array_equal(score[sched & (rscore > 0)], rscore[sched & (rscore > 0)])
     for k in rstate:
         np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
+
+
+def test_gpu_share_failure_names_the_nodes():
+    """UnscheduledPod.Reason of a pod the Open-Gpu-Share filter rejects everywhere: one "Node:<name>" reason per node
+    (open-gpu-share.go:66-79 + FitError.Error, generic_scheduler.go:72-90), sorted like every other reason."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import kat_plugins
+    from simon_b200 import simulator
+    from simon_b200.objects import AppResource, ResourceTypes
+    kat = kat_plugins.CASES["gpu_share_per_device_fit"]
+    cluster = ResourceTypes()
+    cluster.Nodes.extend(kat["nodes"])
+    cluster.Pods.extend(kat["running"])
+    a1, a2 = AppResource("kat", ResourceTypes()), AppResource("kat2", ResourceTypes())
+    a1.Resource.Pods.extend(kat["pod"])
+    a2.Resource.Pods.extend(kat["pod2"])
+    res = simulator.Simulate(cluster, [a1, a2], simulator.DisablePTerm(True))
+    assert [u.Pod.name for u in res.UnscheduledPods] == ["b"]
+    assert res.UnscheduledPods[0].Reason == ("failed to schedule pod (default/b): Unschedulable: 0/2 nodes are available: "
+                                             "1 Node:g1, 1 Node:g2.")
