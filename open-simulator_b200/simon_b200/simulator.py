@@ -198,9 +198,15 @@ def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> 
     options = SimulatorOptions()
     for o in opts:
         o(options)
+    extra_plugins = []
     if options.extraRegistry:
-        raise NotImplementedError("WithExtraRegistry: out-of-tree Go plugins cannot run on the device "
-                                  "(SURVEY.md §8b plugin surface); refusing to ignore them silently")
+        from .compiler import ExtraScorePlugin
+        for name, pl in options.extraRegistry.items():
+            if not isinstance(pl, ExtraScorePlugin):
+                raise NotImplementedError(f"WithExtraRegistry[{name}]: out-of-tree Go plugins cannot run on the device (SURVEY.md §8b plugin "
+                                          "surface); register a host-side compiler.ExtraScorePlugin (node-local score column) instead - "
+                                          "refusing to ignore the plugin silently")
+            extra_plugins.append(pl)
     if options.schedulerConfig:
         # the reference merges a user KubeSchedulerConfiguration over its defaults (pkg/simulator/utils.go:304-381); the
         # engine implements exactly the default plugin set and weights, so a custom file cannot be honoured
@@ -211,7 +217,7 @@ def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> 
                                   "ResourceTypes (objects.create_cluster_resource_from_cluster_config)")
     from .engine import Engine     # raises if libsimon_gpu.so / CUDA is unavailable: no CPU fallback
     p = plan(cluster, apps)
-    compiled = compile_cluster(p.nodes, p.pods, p.ctx)
+    compiled = compile_cluster(p.nodes, p.pods, p.ctx, extra_plugins=extra_plugins or None)
     gpu_fail_nodes = {}
     with Engine(compiled, device=options.device, record_scores=options.record_scores) as eng:
         out_node, _scores, fail_counts, fail_pod = eng.schedule()

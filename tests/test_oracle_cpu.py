@@ -186,3 +186,32 @@ def test_numeric_ranges_are_proven_at_compile_time():
         {"weight": 1 << 31, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "x"}}, "topologyKey": "kubernetes.io/hostname"}}]}}}
     with pytest.raises(CompileError, match="2\\^31"):
         one(ipa)
+
+
+def test_extra_registry_host_side_score_plugin():
+    """WithExtraRegistry's supported form: a node-local Score plugin evaluated by the host per (pod class, node) and uploaded
+    as the class's extra column.  Four equal nodes; the plugin prefers nodes labelled tier=gold with weight 3: the total of a
+    gold node exceeds the others by exactly 3 x (100 - 20)."""
+    from simon_b200 import simulator
+    from simon_b200.compiler import ExtraScorePlugin, CompileError, compile_cluster
+    from simon_b200.objects import AppResource, ResourceTypes
+    from oracle.binding import Oracle
+    cluster = ResourceTypes()
+    for i, tier in enumerate(["silver", "gold", "silver", "gold"]):
+        cluster.Nodes.append({"kind": "Node", "metadata": {"name": f"n{i}", "labels": {"kubernetes.io/hostname": f"n{i}", "tier": tier}}, "spec": {},
+                              "status": {"allocatable": {"cpu": "4", "memory": "8Gi", "pods": "110"}}})
+    app = AppResource("a", ResourceTypes())
+    app.Resource.Pods.append({"kind": "Pod", "metadata": {"name": "p", "namespace": "default"},
+                              "spec": {"containers": [{"name": "c", "image": "x", "resources": {"requests": {"cpu": "1", "memory": "1Gi"}}}]}})
+    pl = ExtraScorePlugin("TierPreference", 3, lambda pod, node: 100 if node["metadata"]["labels"].get("tier") == "gold" else 20)
+    p = simulator.plan(cluster, [app])
+    c = compile_cluster(p.nodes, p.pods, p.ctx, extra_plugins=[pl])
+    o = Oracle(c)
+    o.enable_dump()
+    out, score, _, _ = o.schedule()
+    _, sc = o.last_detail()
+    tot = {c.node_names[i]: int(sc[i][8]) for i in range(4)}
+    assert c.node_names[int(out[0])] == "n1"                       # first gold node in nodeTree order
+    assert tot["n1"] - tot["n0"] == 3 * 80 and tot["n3"] == tot["n1"] and tot["n2"] == tot["n0"]
+    with pytest.raises(CompileError, match="outside"):
+        compile_cluster(p.nodes, p.pods, p.ctx, extra_plugins=[ExtraScorePlugin("bad", 1, lambda pod, node: 101)])
