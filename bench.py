@@ -230,6 +230,7 @@ def block_c2(args, local, flush, torch):
             flush.zero_()
             torch.cuda.synchronize()
             ms += eng.replay(1)
+        eng.reset()
         out = eng.schedule()[0]
     o = Oracle(c)
     t0 = time.perf_counter()

@@ -550,7 +550,7 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
         // default: prefetch on, merged arg-max off - on C3 a third of the decisions see a feasibility flip (the winner of a
         // class with required anti-affinity always leaves the feasible set), those are redone, and the larger merged message
         // costs more than the exchange it saves (profiles/r02_ubench_cluster.txt, r02_kernel_variants.txt)
-        ctx->fast = fv ? (uint32_t)strtoul(fv, nullptr, 0) : 2u;
+        ctx->fast = fv ? (uint32_t)strtoul(fv, nullptr, 0) : 2u;      // bit 2 (incremental filters / raw scores) is evaluated per round
     }
     CU(cudaStreamSynchronize(st));
     ctx->max_fail = std::max(1u, p->n_pods);      // every pod of the list may fail: one histogram row each (96 B)

@@ -131,6 +131,15 @@ __device__ __noinline__ int gpu_allocate(const SkParams &P, const SkScenario &SC
 #define VAL(e, idx) S.a32[(B_N32 + T + (e)) * L + (idx)]
 #define A8(k, idx) S.a8[(k) * L + (idx)]
 
+// Decision-path features compiled into the kernels (ANDed with SkParams::fast at run time): bit 0 merged arg-max, bit 1
+// class-context prefetch, bit 2 incremental feasibility bits / raw scores.  The merged arg-max is compiled out by default: on
+// the C3 workload a third of the decisions see a feasibility flip and are redone, and its larger message costs more than the
+// exchange it saves (profiles/r02_kernel_variants.txt); leaving it out also shortens the kernel and frees registers.
+#ifndef SIMON_FAST_MASK
+#define SIMON_FAST_MASK 6u
+#endif
+#define FAST(bit) ((SIMON_FAST_MASK & (bit)) != 0 && (P.fast & (bit)) != 0)
+
 // per-pod record of the scheduling queue (SkParams::pod_meta): loaded two pods ahead
 struct PodMeta {
     int32_t cls, fixed, guard, extra_row, sig, static_row;
@@ -355,6 +364,19 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         long long v = sk_dec(enc64);
         return w_enc(v > (long long)INT32_MAX ? INT32_MAX : (v < (long long)INT32_MIN ? INT32_MIN : (int32_t)v));
     };
+    // raw PodTopologySpread score of one node under the current weights (scoring.go:175-208)
+    auto pts_raw_node = [&](uint32_t idx) -> int64_t {
+        double score = 0.0;
+        #pragma unroll 1
+        for (uint32_t js = 0; js < C.n_soft; js++) {
+            uint32_t e = C.e_soft + js;
+            double sfc = (double)VAL(e, idx) * S.soft_w[js] + (double)(ENT(ER_A, e) - 1);
+            score = score + sfc;
+        }
+        int64_t raw = f2i(score);
+        A32(B_RAW_PTS, idx) = (int32_t)raw;
+        return raw;
+    };
     auto pts_pass = [&](unsigned long long &lo, unsigned long long &hi) {
         lo = sk_enc(INT64_MAX);
         hi = sk_enc(0);
@@ -364,16 +386,29 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             uint32_t idx = s * TPB + tid;
             uint8_t nf = A8(C_NFLAGS, idx);
             if ((nf & (NF_FEASIBLE | NF_IGNORED)) != NF_FEASIBLE) continue;
-            double score = 0.0;
-            #pragma unroll 1
-            for (uint32_t js = 0; js < C.n_soft; js++) {
-                uint32_t e = C.e_soft + js;
-                double sfc = (double)VAL(e, idx) * S.soft_w[js] + (double)(ENT(ER_A, e) - 1);
-                score = score + sfc;
+            unsigned long long er = sk_enc(pts_raw_node(idx));
+            lo = er < lo ? er : lo;
+            hi = er > hi ? er : hi;
+        }
+    };
+    // the same local ranges from the cached raw scores (incremental mode: the raw scores of a node are recomputed only when
+    // one of its counter values changed or the weights changed), plus the InterPodAffinity range
+    auto ranges_cached = [&](unsigned long long &lo, unsigned long long &hi, int64_t &ilo, int64_t &ihi) {
+        lo = sk_enc(INT64_MAX);
+        hi = sk_enc(0);
+        ilo = 0; ihi = 0;
+        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+        for (uint32_t s = 0; s < NPT; s++) {
+            uint32_t idx = s * TPB + tid;
+            uint8_t nf = A8(C_NFLAGS, idx);
+            if (!(nf & NF_FEASIBLE)) continue;
+            if (C.n_isc) {
+                const int64_t ip = (int64_t)A32(B_RAW_IPA, idx);
+                ihi = ip > ihi ? ip : ihi;
+                ilo = ip < ilo ? ip : ilo;
             }
-            int64_t raw = f2i(score);
-            A32(B_RAW_PTS, idx) = (int32_t)raw;
-            unsigned long long er = sk_enc(raw);
+            if (C.n_soft == 0 || (nf & NF_IGNORED)) continue;
+            unsigned long long er = sk_enc((int64_t)A32(B_RAW_PTS, idx));
             lo = er < lo ? er : lo;
             hi = er > hi ? er : hi;
         }
@@ -404,6 +439,14 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     // prediction of the score ranges of the next decision of the current class (merged arg-max); any value is safe: verified
     bool rng_valid = false;
     int32_t pr_pts_min = 0, pr_pts_max = 0, pr_ipa_min = 0, pr_ipa_max = 0;
+    // Incremental mode (P.fast bit 2): within a visit of a class the feasibility bits and raw scores of a node are brought up
+    // to date when its state changes (commit fold: the winner's node and the nodes whose cached counter values were bumped)
+    // instead of being re-evaluated for every node in every decision; flips found there are reported by the next decision's
+    // reduction.  Not for classes whose filters depend on cluster-wide values that change per decision (DoNotSchedule
+    // minima, the "no pod matches yet" escape of required affinity, per-domain tables).
+    bool inc_valid = false;
+    uint32_t acc_fl = 0, acc_nf = 0;
+    int32_t acc_dc = 0;
     // static-normalised part of the total (NodeAffinity + TaintToleration + 2 x Simon + extra) under the current normalisers
     auto snorm_pass = [&]() {
         const int64_t range = C.simon_max - C.simon_min;
@@ -432,15 +475,15 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             if (SC.csum) sk_cp_async16_cg(S.pred + buf * SK_CSUM_W + 2 * tid, SC.csum + (uint64_t)m.cls * SK_CSUM_W + 2 * tid);
             else { S.pred[buf * SK_CSUM_W + 2 * tid] = 0; S.pred[buf * SK_CSUM_W + 2 * tid + 1] = 0; }
         }
-        // commit tables + the int32 entry table: 17 chunks of 16 bytes, then 8 per entry-table row (only the used columns)
+        // commit tables (17 chunks of 16 bytes) + the int32 entry table (per row only the chunks that hold entries)
         {
-            const uint32_t ncol4 = (m.n_ent + 3u) >> 2;                       // 16-byte chunks per entry-table row that hold entries
-            const uint32_t q = tid - 32;
-            if (tid >= 32 && q < SK_AUX_ENT / 4)
-                sk_cp_async16_cg(S.aux + buf * SK_AUX_W + 4 * q, P.cls_aux + (uint64_t)m.cls * SK_AUX_W + 4 * q);
-            else if (tid >= 32 && q < SK_AUX_ENT / 4 + ER_ROWS * ncol4) {
-                const uint32_t r = (q - SK_AUX_ENT / 4) / ncol4, cc = (q - SK_AUX_ENT / 4) % ncol4;
-                const uint32_t w = SK_AUX_ENT + r * SK_MAX_ENT + 4 * cc;
+            const uint32_t ncol4 = (m.n_ent + 3u) >> 2;
+            const uint32_t total = SK_AUX_ENT / 4 + ER_ROWS * ncol4;
+            #pragma unroll 1
+            for (uint32_t q = tid >= 32 ? tid - 32 : tid + TPB - 32; q < total; q += TPB) {
+                uint32_t w;
+                if (q < SK_AUX_ENT / 4) w = 4 * q;
+                else { const uint32_t r = (q - SK_AUX_ENT / 4) / ncol4, cc = (q - SK_AUX_ENT / 4) % ncol4; w = SK_AUX_ENT + r * SK_MAX_ENT + 4 * cc; }
                 sk_cp_async16_cg(S.aux + buf * SK_AUX_W + w, P.cls_aux + (uint64_t)m.cls * SK_AUX_W + w);
             }
         }
@@ -604,6 +647,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             last_win_r = 0xffffffffu;
             bits_dirty = !restore;
             rng_valid = false;
+            inc_valid = false;
+            acc_fl = 0; acc_nf = 0; acc_dc = 0;
             if (restore) {
                 C.F = pred[9]; C.n_ign = pred[10]; C.na_max = pred[11]; C.tt_max = pred[12]; C.simon_max = pred[13]; C.simon_min = pred[14];
                 if (pred[15] >= 0) {
@@ -786,7 +831,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
 
         // ---- the context of the NEXT pod's class, if it differs: record + summary + commit tables by cp.async into the
         // other buffer now, the per-node inputs (registers) while the arg-max messages travel ----
-        const bool pf_next = (P.fast & 2u) && have_nxt && nxt.fixed == -1 && nxt.guard == -1 && nxt.cls != cls;
+        const bool pf_next = FAST(2u) && have_nxt && nxt.fixed == -1 && nxt.guard == -1 && nxt.cls != cls;
         if (pf_next && pf_cls != nxt.cls) {
             if (pf_cls != -1) { sk_cp_async_wait_all(); __syncthreads(); }      // an unused prefetch occupies the buffer (rare)
             issue_ctx_prefetch(nxt, cb ^ 1u);
@@ -824,20 +869,18 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         uint32_t my_nf = 0;
         int32_t my_dc = 0;                  // net change of the counted (feasible, not ignored) set seen by this thread
         int64_t ipa_lo = 0, ipa_hi = 0;     // min/max of raw InterPodAffinity scores (initialised to 0: scoring.go:255)
-        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-        for (uint32_t s = 0; s < NPT; s++) {
-            uint32_t idx = s * TPB + tid;
+        // filter + raw InterPodAffinity score of one node; flips against the stored bits go to (fl, nf, dc)
+        auto p1_node = [&](uint32_t s, uint32_t idx, uint32_t &fl, uint32_t &nfc, int32_t &dc) -> bool {
             uint8_t nf = A8(C_NFLAGS, idx);
-            if (!(nf & NF_VALID)) continue;
             bool feas = filter_node(idx, nf, hard_min, false) == 0;
             if (feas != ((nf & NF_FEASIBLE) != 0)) {
-                my_fl |= 1u; my_nf++;
+                fl |= 1u; nfc++;
                 if (!feas && s * CT + gtid == last_win_r)
-                    my_fl |= 2u | ((int64_t)(uint32_t)A32(B_RAW_NA, idx) == C.na_max ? 4u : 0u) | ((int64_t)(uint32_t)A32(B_RAW_TT, idx) == C.tt_max ? 8u : 0u) |
-                             (A64(A_SIMON, idx) == C.simon_max ? 16u : 0u) | (A64(A_SIMON, idx) == C.simon_min ? 32u : 0u);
+                    fl |= 2u | ((int64_t)(uint32_t)A32(B_RAW_NA, idx) == C.na_max ? 4u : 0u) | ((int64_t)(uint32_t)A32(B_RAW_TT, idx) == C.tt_max ? 8u : 0u) |
+                          (A64(A_SIMON, idx) == C.simon_max ? 16u : 0u) | (A64(A_SIMON, idx) == C.simon_min ? 32u : 0u);
             }
             bool counted = feas && !(nf & NF_IGNORED);
-            my_dc += (int32_t)counted - (int32_t)((nf & NF_COUNTED) != 0);
+            dc += (int32_t)counted - (int32_t)((nf & NF_COUNTED) != 0);
             if (C.any_table && counted != ((nf & NF_COUNTED) != 0)) {
                 #pragma unroll 1
                 for (uint32_t js = 0; js < C.n_soft; js++) {
@@ -855,10 +898,26 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 for (uint32_t e = C.e_isc; e < C.E; e++)
                     if (DOM(ENT(ER_T, e), idx) >= 0) ip += (int64_t)ENT(ER_A, e) * VAL(e, idx);
                 A32(B_RAW_IPA, idx) = (int32_t)ip;
-                ipa_hi = ip > ipa_hi ? ip : ipa_hi;
-                ipa_lo = ip < ipa_lo ? ip : ipa_lo;
+            }
+            return feas;
+        };
+        const bool inc_ok = FAST(4u) && C.n_hard == 0 && !C.any_table && C.n_aff == 0;
+        const bool inc_now = inc_ok && inc_valid;          // this decision runs on the incrementally maintained bits / raw scores
+        if (inc_now) {
+            my_fl = acc_fl; my_nf = acc_nf; my_dc = acc_dc;
+        } else {
+            #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+            for (uint32_t s = 0; s < NPT; s++) {
+                uint32_t idx = s * TPB + tid;
+                if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
+                if (p1_node(s, idx, my_fl, my_nf, my_dc) && C.n_isc) {
+                    const int64_t ip = (int64_t)A32(B_RAW_IPA, idx);
+                    ipa_hi = ip > ipa_hi ? ip : ipa_hi;
+                    ipa_lo = ip < ipa_lo ? ip : ipa_lo;
+                }
             }
         }
+        acc_fl = 0; acc_nf = 0; acc_dc = 0;
         if (C.any_table) __threadfence();
         TICK(4);
 
@@ -908,24 +967,33 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // ---- P2 + all-reduce: spread raw scores under the predicted summary, verified by the same reduction ----
         int64_t pts_min = 0, pts_max = 0, ipa_min = 0, ipa_max = 0;
         unsigned long long plo, phi;
+        bool raws_stale = false;
         unsigned long long best = 0;
         uint32_t who = 0;
         bool have_winner = false;           // the merged arg-max already produced this decision's winner
         if (C.sum_valid) {
             // steady state: the summary is exact unless some node flipped feasibility since it was taken
-            pts_pass(plo, phi);
+            if (inc_now) ranges_cached(plo, phi, ipa_lo, ipa_hi); else pts_pass(plo, phi);
             TICK(15);
-            uint32_t pv[7] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_fl, (uint32_t)my_dc, my_nf};
-            const int pop[7] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM, W_SUM};
-            const bool merged = (P.fast & 1u) && rng_valid;
+            // 6 words: the spread / affinity ranges, the flip flags and (net change of the counted set << 16) + flipped nodes
+            uint32_t pv[7] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_fl, ((uint32_t)my_dc << 16) + my_nf, 0u};
+            const int pop[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
+            uint32_t (&pv6)[6] = reinterpret_cast<uint32_t (&)[6]>(pv);
+            const bool merged = FAST(1u) && rng_valid;
             if (merged) {
                 // ONE exchange: totals under the predicted ranges + arg-max, the actual ranges and the flip flags ride along
                 const unsigned long long my_best = p3_pass(pr_pts_min, pr_pts_max, pr_ipa_min, pr_ipa_max);
-                const unsigned long long warp_best = sk_argmaxx_send<7>(R, my_best, CT, TPB, pv, pop);
+                const unsigned long long warp_best = sk_argmaxx_send<6>(R, my_best, CT, TPB, pv6, pop);
                 if (pf_nodes_due) { prefetch_static(nxt, 0); pf_nodes_cls = nxt.cls; pf_nodes_due = false; }
                 spec_eval(my_best, warp_best);
-                best = sk_argmaxx_wait<7>(R, who, pv, pop);
-            } else sk_allreduce_w<7>(R, pv, pop);
+                best = sk_argmaxx_wait<6>(R, who, pv6, pop);
+            } else sk_allreduce_w<6>(R, pv6, pop);
+            {
+                // unpack: flipped nodes (< 2^16: at most ~15,000 nodes per scenario) and the signed net change above them
+                const uint32_t packed = pv[5];
+                pv[6] = packed & 0xffffu;
+                pv[5] = (uint32_t)((int32_t)(packed - pv[6]) >> 16);
+            }
             pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]); ipa_min = w_dec(pv[2]); ipa_max = w_dec(pv[3]);
             have_winner = merged && !(pv[4] & 1u) && pts_min == (int64_t)pr_pts_min && pts_max == (int64_t)pr_pts_max &&
                           ipa_min == (int64_t)pr_ipa_min && ipa_max == (int64_t)pr_ipa_max;
@@ -1074,7 +1142,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 const int pop[2] = {W_MIN, W_MAX};
                 sk_allreduce_w<2>(R, pv, pop);
                 pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]);
-            } else if (!sizes_ok) set_weights();
+            } else if (!sizes_ok) { set_weights(); raws_stale = C.n_soft > 0; }     // weights changed, raw scores not recomputed
             if (!(C.snorm_valid && C.nm_na_max == C.na_max && C.nm_tt_max == C.tt_max && C.nm_simon_min == C.simon_min &&
                   C.nm_simon_max == C.simon_max)) {
                 snorm_pass();
@@ -1129,7 +1197,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         rng_valid = pts_min == (int64_t)pr_pts_min && pts_max == (int64_t)pr_pts_max;
         const uint32_t win_r = 0xFFFFFFu - (uint32_t)(best & 0xFFFFFFu);
         const int64_t win_total = (int64_t)(best >> 24) - 1;
-        const bool win_ignored = ((uint32_t)sk_wpay(S, who, 8) & NF_IGNORED) != 0;
+        const bool win_ignored = ((uint32_t)sk_wpay(S, who, T) & NF_IGNORED) != 0;
 
         // ---- commit (AssumePod / NodeInfo.AddPod) ----
         // Commit.  The owning thread only touches its node's shared-memory state (its next filter pass needs it); the
@@ -1206,6 +1274,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 #pragma unroll 1
                 for (uint32_t k = n_dom; k < n_all; k++) VAL(s_inc[k] & 0xff, own_idx) += 1;
             }
+            unsigned long long touched = own_thread ? 1ull << (win_r / CT) : 0ull;     // node slots whose state changed in this commit
             uint32_t cur_row = 0xffffffffu;
             unsigned long long match = 0;                        // which of this thread's nodes share the winner's domain of cur_row (NPT <= 64)
             #pragma unroll 1
@@ -1226,9 +1295,24 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 if ((rec & (1u << 16)) && win_ignored) continue;
                 if (rec & (1u << 17)) { if (sk_wpay(S, who, trow) >= 0) C.aff_total += 1; }
                 if (!match) continue;
+                touched |= match;
                 #pragma unroll (NPT_T > 0 ? NPT_T : 1)
                 for (uint32_t s = 0; s < NPT; s++)
                     if (match >> s & 1) VAL(e, s * TPB + tid) += 1;
+            }
+            // incremental mode: bring the touched nodes' feasibility bits and raw scores up to date now; flips are collected for
+            // the next decision's reduction
+            if (inc_ok) {
+                if (touched) {
+                    #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+                    for (uint32_t s = 0; s < NPT; s++) {
+                        if (!(touched >> s & 1)) continue;
+                        const uint32_t idx = s * TPB + tid;
+                        if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
+                        if (p1_node(s, idx, acc_fl, acc_nf, acc_dc) && C.n_soft && !(A8(C_NFLAGS, idx) & NF_IGNORED)) pts_raw_node(idx);
+                    }
+                }
+                inc_valid = !raws_stale;
             }
         }
         n_sched++;

@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 #define SK_MAX_CS 16
 #define SK_MAXW 6           // domain-bitmask words available per decision
 #define SK_NV 16            // max values per all-reduce
-#define SK_PLW 5            // payload: 10 int32 packed in 5 u64 (T domains + flags)
+#define SK_PLW 5            // payload: up to 10 int32 packed in 5 u64 (T domains + flags); only (T + 2) / 2 of them are sent
 #define SK_MAX_WARPS 16     // threads per CTA <= 512 (the shipped variants use <= 320)
 #define SK_CSUM_W 30          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains, score ranges (4) + their valid flag
 #define SK_AUX_W 324          // per-class tables built at upload: [0..32] compact commit list (+ count word), [33..64] counter bases, pad,
@@ -109,7 +109,8 @@ struct SkParams {
     // static cache: per (static signature, node) verdicts, filled on first use
     uint32_t n_sigs, use_scache;
     uint32_t simon32, fast;        // simon32: every raw Simon score lies in [0, 2^31) -> reduced as a 32-bit word
-                                   // fast: bit 0 merged arg-max (one reduction per steady decision), bit 1 class-context prefetch
+                                   // fast: bit 0 merged arg-max (one reduction per steady decision), bit 1 class-context prefetch,
+                                   //       bit 2 incremental feasibility bits / raw scores within a class visit
     uint32_t dump_pod, pad_d;      // debug: pod index whose per-node totals / filter reasons are written out (0xffffffff: none)
     long long *dump_total;         // [N]
     int32_t *dump_code;            // [N] 0 = feasible, else the reason bitmask
@@ -360,7 +361,8 @@ __device__ __forceinline__ unsigned long long sk_argmax_send(SkRed &R, unsigned 
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     SkSmem &S = *R.S;
     const uint32_t ph = R.mph, buf = ph & 1, ns = S.nslots;
-    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (1 + SK_PLW) * 8u);
+    const uint32_t plw = (S.T + 2u) >> 1;          // payload rows in use: T domains + the flags word, two per message
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (1 + plw) * 8u);
     key = warp_maxu64(key);
     if (lane == 0) S.wpart[warp] = key;
     const long long pt0 = R.prof ? clock64() : 0;
@@ -373,7 +375,7 @@ __device__ __forceinline__ unsigned long long sk_argmax_send(SkRed &R, unsigned 
             uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
             uint32_t idx = (r / CT) * TPB + (r % CT) % TPB;
             if (lane < S.T) pw = S.a32[(B_N32 + lane) * S.L + idx];
-            else if (lane == 8) pw = S.a8[C_NFLAGS * S.L + idx];
+            else if (lane == S.T) pw = S.a8[C_NFLAGS * S.L + idx];
         }
         unsigned long long w[SK_PLW];
 #pragma unroll
@@ -386,7 +388,8 @@ __device__ __forceinline__ unsigned long long sk_argmax_send(SkRed &R, unsigned 
             const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), lane);
             sk_st_async(rbox, k, rbar);
 #pragma unroll
-            for (int j = 0; j < SK_PLW; j++) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
+            for (int j = 0; j < SK_PLW; j++)
+                if ((uint32_t)j < plw) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
         }
     }
     return key;
@@ -420,7 +423,8 @@ __device__ __forceinline__ unsigned long long sk_argmaxx_send(SkRed &R, unsigned
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     SkSmem &S = *R.S;
     const uint32_t ph = R.mph, buf = ph & 1, ns = S.nslots;
-    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (SK_XROW + NM) * 8u);
+    const uint32_t plw = (S.T + 2u) >> 1;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (1 + plw + NM) * 8u);
     key = warp_maxu64(key);
 #pragma unroll
     for (int i = 0; i < NX; i++) xw[i] = warp_w(xw[i], xop[i]);
@@ -443,7 +447,7 @@ __device__ __forceinline__ unsigned long long sk_argmaxx_send(SkRed &R, unsigned
             uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
             uint32_t idx = (r / CT) * TPB + (r % CT) % TPB;
             if (lane < S.T) pw = S.a32[(B_N32 + lane) * S.L + idx];
-            else if (lane == 8) pw = S.a8[C_NFLAGS * S.L + idx];
+            else if (lane == S.T) pw = S.a8[C_NFLAGS * S.L + idx];
         }
         unsigned long long w[SK_PLW];
 #pragma unroll
@@ -456,7 +460,8 @@ __device__ __forceinline__ unsigned long long sk_argmaxx_send(SkRed &R, unsigned
             const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), lane);
             sk_st_async(rbox, k, rbar);
 #pragma unroll
-            for (int j = 0; j < SK_PLW; j++) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
+            for (int j = 0; j < SK_PLW; j++)
+                if ((uint32_t)j < plw) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
         } else if (lane >= 16 && lane - 16 < R.CS) {
             const uint32_t dst = lane - 16;
             const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), dst);
@@ -503,7 +508,7 @@ __device__ __forceinline__ void sk_cp_async16_cg(void *smem_dst, const void *gsr
 }
 __device__ __forceinline__ void sk_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// word j (0..9) of the winner's payload: j < T -> domain of topology j, 8 -> node flags
+// word j of the winner's payload: j < T -> domain of topology j, j == T -> node flags
 __device__ __forceinline__ int32_t sk_wpay(const SkSmem &S, uint32_t who, uint32_t j) {
     return ((const int32_t *)(S.box + who + (size_t)(1 + (j >> 1)) * S.nslots))[j & 1];
 }

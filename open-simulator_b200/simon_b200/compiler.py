@@ -440,6 +440,13 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
         if rec.node_name:
             pod_fixed[i] = name_to_idx.get(rec.node_name, -2)
     C = len(classes)
+    # DefaultPreemption (PL/defaultpreemption/default_preemption.go:91-167) only ever evicts pods of strictly lower priority
+    # than the pod that failed to schedule.  Priorities come from spec.priority alone (no admission controller resolves
+    # priorityClassName in the simulator), so with a single priority value in the pod list PostFilter is inert - the only
+    # case the engine implements.  A list that mixes priorities is refused instead of being placed without preemption.
+    prios = {int((c.spec.get("priority") or 0)) for c in classes}
+    if len(prios) > 1:
+        raise CompileError(f"pods with different spec.priority values {sorted(prios)[:4]}...: DefaultPreemption is not implemented by this engine")
 
     # ---- scalar columns: names requested by any class ----
     scalar_names = sorted({n for c in classes for n in c.scalars})

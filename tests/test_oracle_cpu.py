@@ -215,3 +215,22 @@ def test_extra_registry_host_side_score_plugin():
     assert tot["n1"] - tot["n0"] == 3 * 80 and tot["n3"] == tot["n1"] and tot["n2"] == tot["n0"]
     with pytest.raises(CompileError, match="outside"):
         compile_cluster(p.nodes, p.pods, p.ctx, extra_plugins=[ExtraScorePlugin("bad", 1, lambda pod, node: 101)])
+
+
+def test_mixed_priorities_are_refused():
+    """DefaultPreemption is inert when every pod has the same priority (the reference's shipped inputs set only
+    priorityClassName, which nothing resolves); a list that mixes explicit spec.priority values would preempt in the reference
+    and is refused here."""
+    from simon_b200 import simulator
+    from simon_b200.compiler import CompileError, compile_cluster
+    from simon_b200.objects import AppResource, ResourceTypes
+    cluster = ResourceTypes()
+    cluster.Nodes.append({"kind": "Node", "metadata": {"name": "n1", "labels": {"kubernetes.io/hostname": "n1"}}, "spec": {},
+                          "status": {"allocatable": {"cpu": "4", "memory": "8Gi", "pods": "110"}}})
+    app = AppResource("a", ResourceTypes())
+    for nm, pr in (("lo", 0), ("hi", 1000)):
+        app.Resource.Pods.append({"kind": "Pod", "metadata": {"name": nm, "namespace": "default"},
+                                  "spec": {"priority": pr, "priorityClassName": "x", "containers": [{"name": "c", "image": "x"}]}})
+    p = simulator.plan(cluster, [app])
+    with pytest.raises(CompileError, match="DefaultPreemption"):
+        compile_cluster(p.nodes, p.pods, p.ctx)
