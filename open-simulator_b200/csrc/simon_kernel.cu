@@ -447,6 +447,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     bool inc_valid = false;
     uint32_t acc_fl = 0, acc_nf = 0;
     int32_t acc_dc = 0;
+    unsigned long long acc_mask = 0;        // node slots of this thread whose feasibility bit flipped in the last commit's re-evaluation
     // static-normalised part of the total (NodeAffinity + TaintToleration + 2 x Simon + extra) under the current normalisers
     auto snorm_pass = [&]() {
         const int64_t range = C.simon_max - C.simon_min;
@@ -601,11 +602,20 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     rec[0] = 1;
                 }
                 if (bits_dirty) {
+                    // The stored bits must be the ones the stored summary is exact for.  In incremental mode the last commit's
+                    // re-evaluation may already have flipped bits that no reduction has reported yet (acc_mask): store those
+                    // nodes with their PREVIOUS bits, so that the next visit's filter pass finds the flip again.
                     #pragma unroll 1
                     for (uint32_t s = 0; s < NPT; s++) {
                         uint32_t idx = s * TPB + tid;
                         uint8_t nf = A8(C_NFLAGS, idx);
-                        if (nf & NF_VALID) SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = nf & (NF_FEASIBLE | NF_COUNTED);
+                        if (!(nf & NF_VALID)) continue;
+                        uint8_t bits = nf & (NF_FEASIBLE | NF_COUNTED);
+                        if (acc_mask >> s & 1) {
+                            const bool was_feas = !(nf & NF_FEASIBLE);
+                            bits = was_feas ? (uint8_t)(NF_FEASIBLE | ((nf & NF_IGNORED) ? 0 : NF_COUNTED)) : (uint8_t)0;
+                        }
+                        SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = bits;
                     }
                 }
             }
@@ -648,7 +658,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             bits_dirty = !restore;
             rng_valid = false;
             inc_valid = false;
-            acc_fl = 0; acc_nf = 0; acc_dc = 0;
+            acc_fl = 0; acc_nf = 0; acc_dc = 0; acc_mask = 0;
             if (restore) {
                 C.F = pred[9]; C.n_ign = pred[10]; C.na_max = pred[11]; C.tt_max = pred[12]; C.simon_max = pred[13]; C.simon_min = pred[14];
                 if (pred[15] >= 0) {
@@ -903,9 +913,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         };
         const bool inc_ok = FAST(4u) && C.n_hard == 0 && !C.any_table && C.n_aff == 0;
         const bool inc_now = inc_ok && inc_valid;          // this decision runs on the incrementally maintained bits / raw scores
-        if (inc_now) {
-            my_fl = acc_fl; my_nf = acc_nf; my_dc = acc_dc;
-        } else {
+        // flips found by the previous commit's re-evaluation are reported now in either mode: the bits were already updated
+        // when they were found, so a full pass below cannot see them again
+        my_fl = acc_fl; my_nf = acc_nf; my_dc = acc_dc;
+        if (!inc_now) {
             #pragma unroll (NPT_T > 0 ? NPT_T : 1)
             for (uint32_t s = 0; s < NPT; s++) {
                 uint32_t idx = s * TPB + tid;
@@ -917,7 +928,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 }
             }
         }
-        acc_fl = 0; acc_nf = 0; acc_dc = 0;
+        acc_fl = 0; acc_nf = 0; acc_dc = 0; acc_mask = 0;
         if (C.any_table) __threadfence();
         TICK(4);
 
@@ -1309,7 +1320,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         if (!(touched >> s & 1)) continue;
                         const uint32_t idx = s * TPB + tid;
                         if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
-                        if (p1_node(s, idx, acc_fl, acc_nf, acc_dc) && C.n_soft && !(A8(C_NFLAGS, idx) & NF_IGNORED)) pts_raw_node(idx);
+                        const uint32_t nf_before = acc_nf;
+                        const bool feas = p1_node(s, idx, acc_fl, acc_nf, acc_dc);
+                        if (acc_nf != nf_before) acc_mask |= 1ull << s;
+                        if (feas && C.n_soft && !(A8(C_NFLAGS, idx) & NF_IGNORED)) pts_raw_node(idx);
                     }
                 }
                 inc_valid = !raws_stale;

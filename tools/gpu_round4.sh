@@ -3,11 +3,14 @@
 TAG=${1:-x}
 OUT=gpurun_out
 mkdir -p $OUT
-echo "== ubench (trimmed payload)"; timeout 180 tools/ubench_cluster > $OUT/ubench_$TAG.txt 2>&1; grep -E "cs=16 tpb= 320" $OUT/ubench_$TAG.txt | grep -E "argmax|arg-max|allreduce_w<6>"
-echo "== parity of the default build (quick subset + kernel paths)"
-timeout 900 python -m pytest tests/test_gpu_detail.py tests/test_gpu_parity.py -x -q -m gpu -k "not full_size" 2>&1 | tail -6
-for M in 0 2 4 6 7; do
+for lib in variants/libsimon_m*.so; do
+  M=$(basename $lib .so | sed 's/libsimon_m//')
   echo "-- variant mask $M"
-  SIMON_GPU_LIB=$PWD/variants/libsimon_m$M.so SIMON_FAST=7 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "mixed or parity_with_oracle" 2>&1 | tail -1
-  SIMON_GPU_LIB=$PWD/variants/libsimon_m$M.so SIMON_FAST=7 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-blocks 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mask $M value', round(d['value']), 'ms', round(d['ms_per_step'],1), d['kernel_stats'])"
+  SIMON_GPU_LIB=$PWD/$lib SIMON_FAST=7 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_detail.py tests/test_golden.py tests/test_capacity.py -q -m gpu -k "not full_size" 2>&1 | grep -E "FAILED|passed|failed|mismatch|Mismatch|first" | head -12
+  SIMON_GPU_LIB=$PWD/$lib SIMON_FAST=7 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-blocks 2>/dev/null | python -c "
+import sys,json
+t=sys.stdin.read()
+try:
+    d=json.loads(t); print('mask $M value', round(d['value']), 'ms', round(d['ms_per_step'],1), d['kernel_stats'])
+except Exception as e: print('mask $M bench failed', t[:200])"
 done
