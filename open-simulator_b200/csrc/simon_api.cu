@@ -128,13 +128,10 @@ struct simon_ctx {
     DevBuf<uint64_t> d_class_off, d_cnt_off;
     DevBuf<int64_t> d_class_blob, d_simon_raw;
     DevBuf<int32_t> d_pod_class, d_pod_fixed, d_pod_guard, d_extra;
-    DevBuf<ulonglong2> d_pod_meta;
-    DevBuf<uint32_t> d_cls_aux;
     // debug dump of one pod's per-node totals / filter verdicts (simon_debug_*)
     uint32_t dump_pod = 0xffffffffu;
     DevBuf<long long> d_dump_total;
     DevBuf<int32_t> d_dump_code;
-    uint32_t fast = 2;
     // candidate-move scoring (simon_moves_*)
     DevBuf<uint2> d_moves;
     DevBuf<int32_t> d_mv_gain;
@@ -242,8 +239,6 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.emax = ctx->emax;
     P.stats = ctx->d_stats.p;
     P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p;
-    P.pod_meta = ctx->d_pod_meta.p; P.cls_aux = ctx->d_cls_aux.p;
-    P.fast = ctx->fast;
     P.dump_pod = 0xffffffffu; P.dump_total = nullptr; P.dump_code = nullptr;
 }
 
@@ -461,61 +456,7 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     for (size_t q = 0; q < (size_t)p->n_static_rows * ctx->NC; q++)
         if (p->simon_raw[q] < 0 || p->simon_raw[q] >= (1ll << 31)) { ctx->simon32 = 0; break; }
     CU(ctx->d_extra.upload(p->extra_score, (size_t)std::max(1u, p->n_extra_rows) * std::max(1u, ctx->N), st));
-    // per-class commit tables (what warp 0 of every CTA used to derive at each class switch) and the per-pod queue
-    // records the kernel reads two pods ahead (class-context prefetch)
     if (blob_words >= (1ull << 32)) return fail(ctx, SIMON_ERR_LIMIT, "class records exceed 2^32 words");
-    std::vector<uint32_t> aux((size_t)std::max(1u, p->n_classes) * SK_AUX_W, 0u);
-    for (uint32_t c = 0; c < p->n_classes; c++) {
-        const int64_t *cw = p->class_blob + p->class_off[c];
-        const int64_t *et = cw + cw[SCW_OFF_ENT];
-        const uint32_t E = (uint32_t)(cw[SCW_N_PORTS] + cw[SCW_N_PTS_HARD] + cw[SCW_N_PTS_SOFT] + cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] +
-                                      cw[SCW_N_IPA_EXIST] + cw[SCW_N_IPA_SCORE]);
-        if ((uint64_t)cw[SCW_OFF_ENT] + 8ull * E > p->class_off[c + 1] - p->class_off[c] || (uint32_t)cw[SCW_N_ENT] != E)
-            return fail(ctx, SIMON_ERR_INVALID, "class %u: entry table does not match the list sizes", c);
-        uint32_t *ax = aux.data() + (size_t)c * SK_AUX_W;
-        uint32_t recs[SK_MAX_ENT];
-        bool node_lvl[SK_MAX_ENT], incs[SK_MAX_ENT];
-        uint32_t n_dom = 0, n_all = 0, n_aff_node = 0;
-        for (uint32_t e = 0; e < E; e++) {
-            const int64_t *r = et + 8ull * e;
-            const int32_t kind = (int32_t)r[ER_KIND];
-            const bool host = kind == EK_SOFT && r[ER_B] != 0;
-            incs[e] = r[ER_INC] != 0;
-            // entry | topology row << 8 | flags << 16 (bit 16: domain-level soft constraint, bit 17: required affinity term)
-            recs[e] = e | ((host ? 0u : (uint32_t)r[ER_T]) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) | (kind == EK_AFF ? 1u << 17 : 0u);
-            // entries on topology row 0 (the node itself) can only match the winner's own node: they go to the end of the
-            // list and are applied by the owning thread alone; every thread walks the others
-            node_lvl[e] = incs[e] && ((recs[e] >> 8) & 0xff) == 0;
-            if (incs[e]) { n_all++; if (!node_lvl[e]) n_dom++; else if (recs[e] & (1u << 17)) n_aff_node++; }
-        }
-        uint32_t kd = 0, kn = n_dom;
-        for (uint32_t e = 0; e < E; e++) {
-            if (!incs[e]) continue;
-            if (node_lvl[e]) ax[kn++] = recs[e]; else ax[kd++] = recs[e];
-        }
-        ax[SK_MAX_ENT] = n_dom | (n_all << 8) | (n_aff_node << 16);
-        const int64_t *inc = cw + cw[SCW_OFF_INC];
-        for (uint32_t e = 0; e < E; e++)
-            for (uint32_t r = 0; r < ER_ROWS; r++) ax[SK_AUX_ENT + r * SK_MAX_ENT + e] = (uint32_t)(int32_t)et[8ull * e + r];
-        for (uint32_t u = 0; u < 32 && (int64_t)u < cw[SCW_N_INC]; u++) {
-            if (inc[3 * u] < 0 || (uint64_t)inc[3 * u] >= p->n_counters) return fail(ctx, SIMON_ERR_INVALID, "class %u: bad counter in the commit list", c);
-            ax[SK_AUX_INCB + u] = (uint32_t)cnt_off[inc[3 * u]];
-        }
-    }
-    std::vector<ulonglong2> meta((size_t)std::max(1u, p->n_pods) * 2);
-    for (uint32_t i = 0; i < p->n_pods; i++) {
-        const uint32_t c = (uint32_t)p->pod_class[i];
-        const int64_t *cw = p->class_blob + p->class_off[c];
-        const uint64_t words = p->class_off[c + 1] - p->class_off[c];
-        ulonglong2 a, b;
-        a.x = (uint64_t)c | ((uint64_t)(uint32_t)p->pod_fixed_node[i] << 32);
-        const uint64_t n_ent = (uint64_t)(cw[SCW_N_PORTS] + cw[SCW_N_PTS_HARD] + cw[SCW_N_PTS_SOFT] + cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] +
-                                          cw[SCW_N_IPA_EXIST] + cw[SCW_N_IPA_SCORE]);
-        a.y = (uint64_t)(uint32_t)guard[i] | (words << 32) | (n_ent << 56);       // words <= 16384, entries <= 32
-        b.x = (uint64_t)(uint32_t)p->class_off[c] | ((uint64_t)(uint32_t)(int32_t)cw[SCW_EXTRA_ROW] << 32);
-        b.y = (uint64_t)(uint32_t)(int32_t)cw[SCW_STATIC_SIG] | ((uint64_t)(uint32_t)(int32_t)cw[SCW_STATIC_ROW] << 32);
-        meta[2ull * i] = a; meta[2ull * i + 1] = b;
-    }
     {
         // compact per-class header of the move kernel (simon_moves.cu): scoring + Fit inputs and a few counts in 64 bytes
         std::vector<SmvClass> mc(std::max(1u, p->n_classes));
@@ -543,15 +484,6 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     }
     ctx->bypass.assign(std::max(1u, p->n_pods), 0);
     for (uint32_t i = 0; i < p->n_pods; i++) ctx->bypass[i] = (guard[i] == -2 || p->pod_fixed_node[i] != -1) ? 1 : 0;
-    CU(ctx->d_cls_aux.upload(aux.data(), aux.size(), st));
-    CU(ctx->d_pod_meta.upload(meta.data(), meta.size(), st));
-    {
-        const char *fv = getenv("SIMON_FAST");      // diagnostic switch: bit 0 merged arg-max, bit 1 class-context prefetch
-        // default: prefetch on, merged arg-max off - on C3 a third of the decisions see a feasibility flip (the winner of a
-        // class with required anti-affinity always leaves the feasible set), those are redone, and the larger merged message
-        // costs more than the exchange it saves (profiles/r02_ubench_cluster.txt, r02_kernel_variants.txt)
-        ctx->fast = fv ? (uint32_t)strtoul(fv, nullptr, 0) : 2u;      // bit 2 (incremental filters / raw scores) is evaluated per round
-    }
     CU(cudaStreamSynchronize(st));
     ctx->max_fail = std::max(1u, p->n_pods);      // every pod of the list may fail: one histogram row each (96 B)
     int rc = alloc_state(ctx, ctx->st, ctx->max_fail, (ctx->opt_flags & SIMON_OPT_RECORD_SCORES) != 0);

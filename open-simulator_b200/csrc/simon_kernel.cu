@@ -124,36 +124,12 @@ __device__ __noinline__ int gpu_allocate(const SkParams &P, const SkScenario &SC
     return got == req_num ? got : 0;
 }
 
-#define ENT(row, e) s_ent[(row) * SK_MAX_ENT + (e)]
+#define ENT(row, e) S.ent[(row) * SK_MAX_ENT + (e)]
 #define A64(k, idx) S.a64[(k) * L + (idx)]
 #define A32(k, idx) S.a32[(k) * L + (idx)]
 #define DOM(t, idx) S.a32[(B_N32 + (t)) * L + (idx)]
 #define VAL(e, idx) S.a32[(B_N32 + T + (e)) * L + (idx)]
 #define A8(k, idx) S.a8[(k) * L + (idx)]
-
-// Decision-path features compiled into the kernels (ANDed with SkParams::fast at run time): bit 0 merged arg-max, bit 1
-// class-context prefetch, bit 2 incremental feasibility bits / raw scores.  The merged arg-max is compiled out by default: on
-// the C3 workload a third of the decisions see a feasibility flip and are redone, and its larger message costs more than the
-// exchange it saves (profiles/r02_kernel_variants.txt); leaving it out also shortens the kernel and frees registers.
-#ifndef SIMON_FAST_MASK
-#define SIMON_FAST_MASK 6u
-#endif
-#define FAST(bit) ((SIMON_FAST_MASK & (bit)) != 0 && (P.fast & (bit)) != 0)
-
-// per-pod record of the scheduling queue (SkParams::pod_meta): loaded two pods ahead
-struct PodMeta {
-    int32_t cls, fixed, guard, extra_row, sig, static_row;
-    uint32_t words, off, n_ent;
-};
-__device__ __forceinline__ PodMeta ld_meta(const SkParams &P, uint32_t i) {
-    const ulonglong2 a = __ldg(P.pod_meta + 2ull * i), b = __ldg(P.pod_meta + 2ull * i + 1);
-    PodMeta m;
-    m.cls = (int32_t)(uint32_t)a.x; m.fixed = (int32_t)(uint32_t)(a.x >> 32);
-    m.guard = (int32_t)(uint32_t)a.y; m.words = (uint32_t)(a.y >> 32) & 0xffffffu; m.n_ent = (uint32_t)(a.y >> 56);
-    m.off = (uint32_t)b.x; m.extra_row = (int32_t)(uint32_t)(b.x >> 32);
-    m.sig = (int32_t)(uint32_t)b.y; m.static_row = (int32_t)(uint32_t)(b.y >> 32);
-    return m;
-}
 
 // Per-class uniform state (identical in every thread of the cluster)
 struct ClassState {
@@ -198,7 +174,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     sk_red_init(R);
     const ReqCtx RC{P.label_bits, N};
     const bool leader = (gtid == 0);
-    unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0, st_fast = 0, st_merged = 0, st_mredo = 0;
+    unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0, st_fast = 0;
     uint32_t last_win_r = 0xffffffffu;     // scenario rank of the last winner while its class stays current
     bool last_win_ign = false;
     bool bits_dirty = true;                // the feasibility bits changed since they were loaded from / stored to fbits
@@ -246,7 +222,6 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     C.snorm_valid = false;
     C.n_soft = 0;
     const int64_t *cw = S.blob;
-    const int32_t *s_ent = (const int32_t *)(S.aux + SK_AUX_ENT);     // entry table of the current class: int32 rows [ER_ROWS][SK_MAX_ENT]
 
     // NodeResourcesFit verdict + LeastAllocated + BalancedAllocation of one node for the current class, with `add` more
     // pods of this class already on the node (add = 0: the node as it is; add = 1: as it will be after winning this pod).
@@ -364,19 +339,6 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         long long v = sk_dec(enc64);
         return w_enc(v > (long long)INT32_MAX ? INT32_MAX : (v < (long long)INT32_MIN ? INT32_MIN : (int32_t)v));
     };
-    // raw PodTopologySpread score of one node under the current weights (scoring.go:175-208)
-    auto pts_raw_node = [&](uint32_t idx) -> int64_t {
-        double score = 0.0;
-        #pragma unroll 1
-        for (uint32_t js = 0; js < C.n_soft; js++) {
-            uint32_t e = C.e_soft + js;
-            double sfc = (double)VAL(e, idx) * S.soft_w[js] + (double)(ENT(ER_A, e) - 1);
-            score = score + sfc;
-        }
-        int64_t raw = f2i(score);
-        A32(B_RAW_PTS, idx) = (int32_t)raw;
-        return raw;
-    };
     auto pts_pass = [&](unsigned long long &lo, unsigned long long &hi) {
         lo = sk_enc(INT64_MAX);
         hi = sk_enc(0);
@@ -386,29 +348,16 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             uint32_t idx = s * TPB + tid;
             uint8_t nf = A8(C_NFLAGS, idx);
             if ((nf & (NF_FEASIBLE | NF_IGNORED)) != NF_FEASIBLE) continue;
-            unsigned long long er = sk_enc(pts_raw_node(idx));
-            lo = er < lo ? er : lo;
-            hi = er > hi ? er : hi;
-        }
-    };
-    // the same local ranges from the cached raw scores (incremental mode: the raw scores of a node are recomputed only when
-    // one of its counter values changed or the weights changed), plus the InterPodAffinity range
-    auto ranges_cached = [&](unsigned long long &lo, unsigned long long &hi, int64_t &ilo, int64_t &ihi) {
-        lo = sk_enc(INT64_MAX);
-        hi = sk_enc(0);
-        ilo = 0; ihi = 0;
-        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-        for (uint32_t s = 0; s < NPT; s++) {
-            uint32_t idx = s * TPB + tid;
-            uint8_t nf = A8(C_NFLAGS, idx);
-            if (!(nf & NF_FEASIBLE)) continue;
-            if (C.n_isc) {
-                const int64_t ip = (int64_t)A32(B_RAW_IPA, idx);
-                ihi = ip > ihi ? ip : ihi;
-                ilo = ip < ilo ? ip : ilo;
+            double score = 0.0;
+            #pragma unroll 1
+            for (uint32_t js = 0; js < C.n_soft; js++) {
+                uint32_t e = C.e_soft + js;
+                double sfc = (double)VAL(e, idx) * S.soft_w[js] + (double)(ENT(ER_A, e) - 1);
+                score = score + sfc;
             }
-            if (C.n_soft == 0 || (nf & NF_IGNORED)) continue;
-            unsigned long long er = sk_enc((int64_t)A32(B_RAW_PTS, idx));
+            int64_t raw = f2i(score);
+            A32(B_RAW_PTS, idx) = (int32_t)raw;
+            unsigned long long er = sk_enc(raw);
             lo = er < lo ? er : lo;
             hi = er > hi ? er : hi;
         }
@@ -425,29 +374,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
 
     const uint32_t end = P.first + P.count;
     uint32_t i = P.first;
-    const uint32_t MBW = P.max_blob_words;
-    uint32_t cb = 0;                                   // which of the two class-context buffers is current
-    const uint32_t *s_inc = S.aux, *s_incb = S.aux + SK_AUX_INCB;
-    int32_t pf_cls = -1;                               // class whose record / summary / commit tables sit in the other buffer
-    int32_t pf_nodes_cls = -1;                         // class whose per-node static inputs sit in the pf_* registers
-    unsigned long long pf_rec[4], pf_oc[4];
-    long long pf_sim[4];
-    int32_t pf_ex[4];
-    uint8_t pf_fb[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) { pf_rec[u] = 0; pf_oc[u] = 0; pf_sim[u] = 0; pf_ex[u] = 1000000; pf_fb[u] = 0; }
-    // prediction of the score ranges of the next decision of the current class (merged arg-max); any value is safe: verified
-    bool rng_valid = false;
-    int32_t pr_pts_min = 0, pr_pts_max = 0, pr_ipa_min = 0, pr_ipa_max = 0;
-    // Incremental mode (P.fast bit 2): within a visit of a class the feasibility bits and raw scores of a node are brought up
-    // to date when its state changes (commit fold: the winner's node and the nodes whose cached counter values were bumped)
-    // instead of being re-evaluated for every node in every decision; flips found there are reported by the next decision's
-    // reduction.  Not for classes whose filters depend on cluster-wide values that change per decision (DoNotSchedule
-    // minima, the "no pod matches yet" escape of required affinity, per-domain tables).
-    bool inc_valid = false;
-    uint32_t acc_fl = 0, acc_nf = 0;
-    int32_t acc_dc = 0;
-    unsigned long long acc_mask = 0;        // node slots of this thread whose feasibility bit flipped in the last commit's re-evaluation
+    int32_t nx_cls = P.pod_class[i], nx_fixed = P.pod_fixed[i], nx_guard = P.pod_guard[i];
     // static-normalised part of the total (NodeAffinity + TaintToleration + 2 x Simon + extra) under the current normalisers
     auto snorm_pass = [&]() {
         const int64_t range = C.simon_max - C.simon_min;
@@ -467,60 +394,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         C.nm_na_max = C.na_max; C.nm_tt_max = C.tt_max; C.nm_simon_min = C.simon_min; C.nm_simon_max = C.simon_max;
         C.snorm_valid = true;
     };
-    // class context into buffer `buf`: record, stored summary, commit tables (cp.async; completion is awaited at the switch)
-    auto issue_ctx_prefetch = [&](const PodMeta &m, uint32_t buf) {
-        const int64_t *gw = P.class_blob + m.off;
-        #pragma unroll 1
-        for (uint32_t w = tid; w < m.words; w += TPB) sk_cp_async8(S.blob + (size_t)buf * MBW + w, gw + w);
-        if (tid < SK_CSUM_W / 2) {
-            if (SC.csum) sk_cp_async16_cg(S.pred + buf * SK_CSUM_W + 2 * tid, SC.csum + (uint64_t)m.cls * SK_CSUM_W + 2 * tid);
-            else { S.pred[buf * SK_CSUM_W + 2 * tid] = 0; S.pred[buf * SK_CSUM_W + 2 * tid + 1] = 0; }
-        }
-        // commit tables (17 chunks of 16 bytes) + the int32 entry table (per row only the chunks that hold entries)
-        {
-            const uint32_t ncol4 = (m.n_ent + 3u) >> 2;
-            const uint32_t total = SK_AUX_ENT / 4 + ER_ROWS * ncol4;
-            #pragma unroll 1
-            for (uint32_t q = tid >= 32 ? tid - 32 : tid + TPB - 32; q < total; q += TPB) {
-                uint32_t w;
-                if (q < SK_AUX_ENT / 4) w = 4 * q;
-                else { const uint32_t r = (q - SK_AUX_ENT / 4) / ncol4, cc = (q - SK_AUX_ENT / 4) % ncol4; w = SK_AUX_ENT + r * SK_MAX_ENT + 4 * cc; }
-                sk_cp_async16_cg(S.aux + buf * SK_AUX_W + w, P.cls_aux + (uint64_t)m.cls * SK_AUX_W + w);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // per-node inputs of a class switch that do not depend on the counters: static verdict record, Simon row, extra score,
-    // stored feasibility bits, own-state score cache.  Up to 4 node slots per thread, loads issued back to back.
-    auto prefetch_static = [&](const PodMeta &m, uint32_t s0) {
-        const int64_t *simon_row = P.simon_raw + (uint64_t)m.static_row * P.NC;
-        const int32_t *extra = m.extra_row >= 0 ? P.extra_score + (uint64_t)m.extra_row * N : nullptr;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            uint32_t s = s0 + u;
-            uint32_t idx = s * TPB + tid;
-            bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
-            pf_rec[u] = 0; pf_sim[u] = 0; pf_ex[u] = 1000000; pf_fb[u] = 0; pf_oc[u] = 0;
-            if (valid) {
-                uint32_t g = (uint32_t)A32(B_NODE_G, idx);
-                if (P.use_scache) pf_rec[u] = __ldcg(&P.scache[(uint64_t)m.sig * N + g]);
-                pf_sim[u] = __ldg(&simon_row[A32(B_NODE_CLASS, idx)]);
-                if (extra) pf_ex[u] = __ldg(&extra[g]);
-                if (SC.fbits) pf_fb[u] = __ldcg(&SC.fbits[(uint64_t)m.cls * N + g]);
-                if (SC.ocache) pf_oc[u] = __ldcg(&SC.ocache[(uint64_t)m.cls * N + g]);
-            }
-        }
-    };
-
-    PodMeta m0 = ld_meta(P, i), m1 = m0;
-    if (i + 1 < end) m1 = ld_meta(P, i + 1);
     while (i < end) {
-        const PodMeta cur = m0, nxt = m1;
-        const bool have_nxt = i + 1 < end;
-        m0 = m1;
-        if (i + 2 < end) m1 = ld_meta(P, i + 2);          // consumed as `nxt` one iteration later
-        const int32_t cls = cur.cls, fixed = cur.fixed;
-        const int64_t guard = cur.guard;
+        const int32_t cls = nx_cls, fixed = nx_fixed;
+        const int64_t guard = nx_guard;
+        if (i + 1 < end) { nx_cls = P.pod_class[i + 1]; nx_fixed = P.pod_fixed[i + 1]; nx_guard = P.pod_guard[i + 1]; }
         bool exists = true;
         if (guard == -2) exists = false;
         else if (guard >= 0) exists = SC.rank_of ? (SC.rank_of[guard] >= 0) : true;
@@ -577,7 +454,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             cur_class = -1;
             TICK(1);
             i = j;
-            if (i < end) { m0 = ld_meta(P, i); m1 = m0; if (i + 1 < end) m1 = ld_meta(P, i + 1); }
+            if (i < end) { nx_cls = P.pod_class[i]; nx_fixed = P.pod_fixed[i]; nx_guard = P.pod_guard[i]; }
             continue;
         }
 
@@ -586,6 +463,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         // =================================================================================================
         if (cls != cur_class) {
             st_class++;
+            // remember the summary of the class we leave: it is the prediction for its next visit
             // remember the class we leave: its summary AND the feasibility bits it is exact for.  On the next visit the
             // bits are restored and P1 detects any change against them, exactly as between two pods of one class.
             if (cur_class >= 0 && C.sum_valid && SC.csum && SC.fbits && !C.any_table) {
@@ -598,49 +476,33 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     rec[15] = last_win_r == 0xffffffffu ? -1ll : (long long)last_win_r; rec[16] = last_win_ign ? 1 : 0;
 #pragma unroll
                     for (int q = 0; q < SIMON_MAX_TOPOS; q++) rec[17 + q] = (uint32_t)q < T ? S.lastdom[q] : -1;
-                    rec[25] = pr_pts_min; rec[26] = pr_pts_max; rec[27] = pr_ipa_min; rec[28] = pr_ipa_max; rec[29] = rng_valid ? 1 : 0;
                     rec[0] = 1;
                 }
                 if (bits_dirty) {
-                    // The stored bits must be the ones the stored summary is exact for.  In incremental mode the last commit's
-                    // re-evaluation may already have flipped bits that no reduction has reported yet (acc_mask): store those
-                    // nodes with their PREVIOUS bits, so that the next visit's filter pass finds the flip again.
                     #pragma unroll 1
                     for (uint32_t s = 0; s < NPT; s++) {
                         uint32_t idx = s * TPB + tid;
                         uint8_t nf = A8(C_NFLAGS, idx);
-                        if (!(nf & NF_VALID)) continue;
-                        uint8_t bits = nf & (NF_FEASIBLE | NF_COUNTED);
-                        if (acc_mask >> s & 1) {
-                            const bool was_feas = !(nf & NF_FEASIBLE);
-                            bits = was_feas ? (uint8_t)(NF_FEASIBLE | ((nf & NF_IGNORED) ? 0 : NF_COUNTED)) : (uint8_t)0;
-                        }
-                        SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = bits;
+                        if (nf & NF_VALID) SC.fbits[(uint64_t)cur_class * N + (uint32_t)A32(B_NODE_G, idx)] = nf & (NF_FEASIBLE | NF_COUNTED);
                     }
                 }
             }
             TICK(10);
             // the previous commits' counter updates (owner-thread atomics) must be visible before the counters are read:
-            // release here, acquire (barrier_wait) only where the first counter is loaded, so that everything that does
-            // not depend on the counters overlaps the barrier latency
+            // release here, acquire (barrier_wait) only where the first counter is loaded, so that the class blob, entry
+            // table and summary record loads overlap the barrier latency
             __threadfence();
             cluster.barrier_arrive();
-            // the class context: normally prefetched into the other buffer during the previous decision
-            if (pf_cls != cls) {
-                sk_cp_async_wait_all();
-                __syncthreads();                 // nobody still reads the buffer that is about to be overwritten
-                issue_ctx_prefetch(cur, cb ^ 1u);
-            }
-            sk_cp_async_wait_all();
-            __syncthreads();                     // record / summary / commit tables of `cls` are in shared memory
-            pf_cls = -1;
-            cb ^= 1u;
-            cw = S.blob + (size_t)cb * MBW;
-            s_inc = S.aux + cb * SK_AUX_W;
-            s_ent = (const int32_t *)(s_inc + SK_AUX_ENT);
-            s_incb = s_inc + SK_AUX_INCB;
-            const long long *pred = S.pred + cb * SK_CSUM_W;
+            __syncthreads();          // every thread of this CTA is done with the previous class's blob and entry table
             TICK(11);
+            const int64_t *gw = P.class_blob + P.class_off[cls];
+            const uint32_t words = (uint32_t)(P.class_off[cls + 1] - P.class_off[cls]);
+            #pragma unroll 1
+            for (uint32_t w = tid; w < words; w += TPB) S.blob[w] = gw[w];
+            // prediction of the topology sizes from the previous visit of this class (any value is safe: verified)
+            if (tid < SK_CSUM_W) S.pred[tid] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + tid) : 0;
+            __syncthreads();
+            const long long *pred = S.pred;
             TICK(12);
             C.cflags = (uint32_t)cw[SCW_FLAGS];
             C.n_ports = (uint32_t)cw[SCW_N_PORTS]; C.n_hard = (uint32_t)cw[SCW_N_PTS_HARD]; C.n_soft = (uint32_t)cw[SCW_N_PTS_SOFT];
@@ -656,9 +518,6 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             const bool restore = C.have_pred && !C.any_table && SC.fbits;
             last_win_r = 0xffffffffu;
             bits_dirty = !restore;
-            rng_valid = false;
-            inc_valid = false;
-            acc_fl = 0; acc_nf = 0; acc_dc = 0; acc_mask = 0;
             if (restore) {
                 C.F = pred[9]; C.n_ign = pred[10]; C.na_max = pred[11]; C.tt_max = pred[12]; C.simon_max = pred[13]; C.simon_min = pred[14];
                 if (pred[15] >= 0) {
@@ -668,30 +527,79 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         if (tid == (uint32_t)q && (uint32_t)q < T) S.lastdom[q] = (int32_t)pred[17 + q];
                 }
                 C.sum_valid = true;
-                if (pred[29] == 1) {
-                    rng_valid = true;
-                    pr_pts_min = (int32_t)pred[25]; pr_pts_max = (int32_t)pred[26]; pr_ipa_min = (int32_t)pred[27]; pr_ipa_max = (int32_t)pred[28];
-                }
             }
 #pragma unroll
             for (int js = 0; js < SK_MAX_SOFT; js++) {
                 long long v = pred[1 + js];
                 psz[js] = (C.have_pred && v >= 0 && v + 2 < (long long)P.n_log) ? (int32_t)v : 0;
             }
+            {
+                // the entry table was laid out by the snapshot compiler (SCW_OFF_ENT): 8 words per entry -> 8 rows in smem
+                const int64_t *et = cw + cw[SCW_OFF_ENT];
+#pragma unroll 1
+                for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // compact list of the entries this class increments on commit: entry | topology row << 8 | flags << 16
+                // (lane e looks at entry e; SK_MAX_ENT == 32)
+                const uint32_t e = tid;
+                uint32_t rec = 0;
+                bool inc = e < C.E && ENT(ER_INC, e) != 0;
+                if (inc) {
+                    const int32_t kind = ENT(ER_KIND, e);
+                    const bool host = kind == EK_SOFT && ENT(ER_B, e);
+                    rec = e | ((host ? 0u : (uint32_t)ENT(ER_T, e)) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) |
+                          (kind == EK_AFF ? 1u << 17 : 0u);
+                }
+                // entries on topology row 0 (the node itself) can only match the winner's own node: they go to the end of the
+                // list and are applied by the owning thread alone; every thread walks the others
+                const bool node_lvl = inc && ((rec >> 8) & 0xff) == 0;
+                const uint32_t m_all = __ballot_sync(0xffffffffu, inc), m_node = __ballot_sync(0xffffffffu, node_lvl);
+                const uint32_t m_dom = m_all & ~m_node, lt = (1u << e) - 1u;
+                if (inc) S.inc[node_lvl ? __popc(m_dom) + __popc(m_node & lt) : __popc(m_dom & lt)] = rec;
+                const uint32_t n_aff_node = __popc(__ballot_sync(0xffffffffu, node_lvl && (rec & (1u << 17))));
+                if (e == 0) S.inc[SK_MAX_ENT] = __popc(m_dom) | (__popc(m_all) << 8) | (n_aff_node << 16);
+                // counter bases of the commit list: fetched once per class switch, not by the committing thread
+                if ((int64_t)e < cw[SCW_N_INC]) S.incb[e] = (uint32_t)P.cnt_off[(cw + cw[SCW_OFF_INC])[3 * e]];
+            }
             // ---- node-static verdicts: from the per-(static signature, node) cache, or computed and cached ----
             // All long-latency loads of up to 4 nodes (cache records, Simon row, first 4 counter values each) are issued back
-            // to back before any of them is consumed.  The loads that do not depend on the counters were normally issued
-            // during the previous decision (pf_nodes_cls == cls); otherwise they are issued here, BEFORE the cluster barrier
-            // is awaited.
+            // to back before any of them is consumed.  The loads that do not depend on the counters (everything but the
+            // counter values) of the first batch are issued BEFORE the cluster barrier is awaited.
+            const int64_t sig = cw[SCW_STATIC_SIG];
             const int64_t *tol = cw + cw[SCW_OFF_TOL];
-            if (pf_nodes_cls != cls) prefetch_static(cur, 0);
-            pf_nodes_cls = -1;
+            const int64_t *simon_row = P.simon_raw + (uint64_t)cw[SCW_STATIC_ROW] * P.NC;
+            const int32_t *extra = cw[SCW_EXTRA_ROW] >= 0 ? P.extra_score + (uint64_t)cw[SCW_EXTRA_ROW] * N : nullptr;
+            unsigned long long rec4[4];
+            long long sim4[4];
+            int32_t ex4[4];
+            uint8_t fb4[4];
+            unsigned long long oc4[4];
+            auto prefetch_static = [&](uint32_t s0) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t s = s0 + u;
+                    uint32_t idx = s * TPB + tid;
+                    bool valid = s < NPT && (A8(C_NFLAGS, idx) & NF_VALID);
+                    rec4[u] = 0; sim4[u] = 0; ex4[u] = 1000000; fb4[u] = 0; oc4[u] = 0;
+                    if (valid) {
+                        uint32_t g = (uint32_t)A32(B_NODE_G, idx);
+                        if (P.use_scache) rec4[u] = __ldcg(&P.scache[(uint64_t)sig * N + g]);
+                        sim4[u] = __ldg(&simon_row[A32(B_NODE_CLASS, idx)]);
+                        if (extra) ex4[u] = __ldg(&extra[g]);
+                        if (restore) fb4[u] = __ldcg(&SC.fbits[(uint64_t)cls * N + g]);
+                        if (SC.ocache) oc4[u] = __ldcg(&SC.ocache[(uint64_t)cls * N + g]);
+                    }
+                }
+            };
+            prefetch_static(0);
             cluster.barrier_wait();
             TICK(13);
             #pragma unroll 1
             for (uint32_t s0 = 0; s0 < NPT; s0 += 4) {
                 int32_t v4[4][4];
-                if (s0 > 0) prefetch_static(cur, s0);
+                if (s0 > 0) prefetch_static(s0);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     uint32_t s = s0 + u;
@@ -721,7 +629,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     int32_t na, tt;
                     // record = {code:8, flags:8, tt:8, valid:1 (bit 24), na:32 (bits 32..63)}; 8-byte loads/stores are atomic, so a
                     // record is either absent (computed here and published) or complete, also across concurrent scenarios
-                    unsigned long long rec = pf_rec[u];
+                    unsigned long long rec = rec4[u];
                     if (rec & (1ull << 24)) {
                         code = (uint8_t)rec; fl = (uint8_t)(rec >> 8); tt = (int32_t)((rec >> 16) & 0xff); na = (int32_t)(rec >> 32);
                     } else {
@@ -752,16 +660,16 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         if (hk) fl |= NF_HARDKEYS;
                         if (ign) fl |= NF_IGNORED;
                         if (P.use_scache && tt < 256)
-                            P.scache[(uint64_t)cur.sig * N + g] = (unsigned long long)code | ((unsigned long long)fl << 8) |
-                                                                 ((unsigned long long)(uint32_t)tt << 16) | (1ull << 24) |
-                                                                 ((unsigned long long)(uint32_t)na << 32);
+                            P.scache[(uint64_t)sig * N + g] = (unsigned long long)code | ((unsigned long long)fl << 8) |
+                                                             ((unsigned long long)(uint32_t)tt << 16) | (1ull << 24) |
+                                                             ((unsigned long long)(uint32_t)na << 32);
                     }
-                    nf |= fl | (code ? NF_STATIC_FAIL : 0) | (restore ? pf_fb[u] : (uint8_t)0);
+                    nf |= fl | (code ? NF_STATIC_FAIL : 0) | fb4[u];
                     A8(C_ST_CODE, idx) = code;
                     A32(B_RAW_NA, idx) = na;
                     A32(B_RAW_TT, idx) = tt;
-                    A64(A_SIMON, idx) = pf_sim[u];
-                    A32(B_EXTRA, idx) = pf_ex[u];
+                    A64(A_SIMON, idx) = sim4[u];
+                    A32(B_EXTRA, idx) = ex4[u];
                     A8(C_NFLAGS, idx) = nf;
 #pragma unroll
                     for (int e = 0; e < 4; e++)
@@ -774,8 +682,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     A8(C_REGBITS, idx) = 0;
                     // own-state score: unchanged since the class's last visit unless the node received a pod in between
                     const uint32_t ver = (uint32_t)A32(B_NUM_PODS, idx) + 1u;
-                    if ((uint32_t)(pf_oc[u] >> 32) == ver) {
-                        const uint32_t lo = (uint32_t)pf_oc[u];
+                    if ((uint32_t)(oc4[u] >> 32) == ver) {
+                        const uint32_t lo = (uint32_t)oc4[u];
                         A8(C_NFLAGS, idx) = (nf & ~NF_FIT_OK) | ((lo & 1u) ? NF_FIT_OK : 0);
                         A32(B_OWN, idx) = (int32_t)lo >> 1;
                     } else {
@@ -839,16 +747,6 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             TICK(2);
         }
 
-        // ---- the context of the NEXT pod's class, if it differs: record + summary + commit tables by cp.async into the
-        // other buffer now, the per-node inputs (registers) while the arg-max messages travel ----
-        const bool pf_next = FAST(2u) && have_nxt && nxt.fixed == -1 && nxt.guard == -1 && nxt.cls != cls;
-        if (pf_next && pf_cls != nxt.cls) {
-            if (pf_cls != -1) { sk_cp_async_wait_all(); __syncthreads(); }      // an unused prefetch occupies the buffer (rare)
-            issue_ctx_prefetch(nxt, cb ^ 1u);
-            pf_cls = nxt.cls;
-        }
-        bool pf_nodes_due = pf_next && pf_nodes_cls != nxt.cls;
-
         // =================================================================================================
         // one placement decision
         // =================================================================================================
@@ -879,18 +777,20 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         uint32_t my_nf = 0;
         int32_t my_dc = 0;                  // net change of the counted (feasible, not ignored) set seen by this thread
         int64_t ipa_lo = 0, ipa_hi = 0;     // min/max of raw InterPodAffinity scores (initialised to 0: scoring.go:255)
-        // filter + raw InterPodAffinity score of one node; flips against the stored bits go to (fl, nf, dc)
-        auto p1_node = [&](uint32_t s, uint32_t idx, uint32_t &fl, uint32_t &nfc, int32_t &dc) -> bool {
+        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+        for (uint32_t s = 0; s < NPT; s++) {
+            uint32_t idx = s * TPB + tid;
             uint8_t nf = A8(C_NFLAGS, idx);
+            if (!(nf & NF_VALID)) continue;
             bool feas = filter_node(idx, nf, hard_min, false) == 0;
             if (feas != ((nf & NF_FEASIBLE) != 0)) {
-                fl |= 1u; nfc++;
+                my_fl |= 1u; my_nf++;
                 if (!feas && s * CT + gtid == last_win_r)
-                    fl |= 2u | ((int64_t)(uint32_t)A32(B_RAW_NA, idx) == C.na_max ? 4u : 0u) | ((int64_t)(uint32_t)A32(B_RAW_TT, idx) == C.tt_max ? 8u : 0u) |
-                          (A64(A_SIMON, idx) == C.simon_max ? 16u : 0u) | (A64(A_SIMON, idx) == C.simon_min ? 32u : 0u);
+                    my_fl |= 2u | ((int64_t)(uint32_t)A32(B_RAW_NA, idx) == C.na_max ? 4u : 0u) | ((int64_t)(uint32_t)A32(B_RAW_TT, idx) == C.tt_max ? 8u : 0u) |
+                             (A64(A_SIMON, idx) == C.simon_max ? 16u : 0u) | (A64(A_SIMON, idx) == C.simon_min ? 32u : 0u);
             }
             bool counted = feas && !(nf & NF_IGNORED);
-            dc += (int32_t)counted - (int32_t)((nf & NF_COUNTED) != 0);
+            my_dc += (int32_t)counted - (int32_t)((nf & NF_COUNTED) != 0);
             if (C.any_table && counted != ((nf & NF_COUNTED) != 0)) {
                 #pragma unroll 1
                 for (uint32_t js = 0; js < C.n_soft; js++) {
@@ -908,107 +808,32 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 for (uint32_t e = C.e_isc; e < C.E; e++)
                     if (DOM(ENT(ER_T, e), idx) >= 0) ip += (int64_t)ENT(ER_A, e) * VAL(e, idx);
                 A32(B_RAW_IPA, idx) = (int32_t)ip;
-            }
-            return feas;
-        };
-        const bool inc_ok = FAST(4u) && C.n_hard == 0 && !C.any_table && C.n_aff == 0;
-        const bool inc_now = inc_ok && inc_valid;          // this decision runs on the incrementally maintained bits / raw scores
-        // flips found by the previous commit's re-evaluation are reported now in either mode: the bits were already updated
-        // when they were found, so a full pass below cannot see them again
-        my_fl = acc_fl; my_nf = acc_nf; my_dc = acc_dc;
-        if (!inc_now) {
-            #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-            for (uint32_t s = 0; s < NPT; s++) {
-                uint32_t idx = s * TPB + tid;
-                if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
-                if (p1_node(s, idx, my_fl, my_nf, my_dc) && C.n_isc) {
-                    const int64_t ip = (int64_t)A32(B_RAW_IPA, idx);
-                    ipa_hi = ip > ipa_hi ? ip : ipa_hi;
-                    ipa_lo = ip < ipa_lo ? ip : ipa_lo;
-                }
+                ipa_hi = ip > ipa_hi ? ip : ipa_hi;
+                ipa_lo = ip < ipa_lo ? ip : ipa_lo;
             }
         }
-        acc_fl = 0; acc_nf = 0; acc_dc = 0; acc_mask = 0;
         if (C.any_table) __threadfence();
         TICK(4);
-
-        // totals of this thread's feasible nodes under the given score ranges; returns the best key (0 = none)
-        auto p3_pass = [&](int64_t pts_min, int64_t pts_max, int64_t ipa_min, int64_t ipa_max) -> unsigned long long {
-            unsigned long long best = 0;
-            const int64_t ipa_diff = ipa_max - ipa_min;
-            const bool pts32 = pts_max > 0 && pts_max < (1 << 23) && pts_min >= 0;
-            const bool dump = PROF ? false : (i == P.dump_pod && P.dump_total != nullptr);
-            #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-            for (uint32_t s = 0; s < NPT; s++) {
-                uint32_t idx = s * TPB + tid;
-                uint8_t nf = A8(C_NFLAGS, idx);
-                if (!(nf & NF_FEASIBLE)) continue;
-                int64_t total = 0;
-                if (C.F > 1) {
-                    int64_t pts;
-                    if (C.n_soft == 0) pts = 100;
-                    else if (nf & NF_IGNORED) pts = 0;
-                    else if (pts_max == 0) pts = 100;
-                    else if (pts32) pts = (int64_t)((uint32_t)(100 * (uint32_t)(pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / (uint32_t)pts_max);
-                    else pts = (100 * (pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / pts_max;
-                    int64_t ip = 0;
-                    if (C.n_isc && ipa_diff > 0) ip = f2i(100.0 * ((double)((int64_t)A32(B_RAW_IPA, idx) - ipa_min) / (double)ipa_diff));
-                    total = (int64_t)A32(B_OWN, idx) + (int64_t)A32(B_SNORM, idx) + ip + 2 * pts;
-                }
-                if (dump) P.dump_total[(uint32_t)A32(B_NODE_G, idx)] = total;
-                uint32_t r = s * CT + gtid;
-                unsigned long long key = ((unsigned long long)(total + 1) << 24) | (unsigned long long)(0xFFFFFFu - r);
-                best = key > best ? key : best;
-            }
-            return best;
-        };
-        // speculative own-state evaluation of this warp's best candidate while the arg-max messages travel
-        bool spec_fit = false;
-        int32_t spec_own = 0;
-        auto spec_eval = [&](unsigned long long my_best, unsigned long long warp_best) {
-            if (my_best == warp_best && my_best != 0) {
-                const uint32_t r = 0xFFFFFFu - (uint32_t)(my_best & 0xFFFFFFu);
-                const uint32_t spec_idx = (r / CT) * TPB + tid;
-                const long long sc0 = PROF ? clock64() : 0;
-                own_core(spec_idx, 1, spec_fit, spec_own);
-                if (PROF) { spec_cyc += clock64() - sc0; spec_n++; }
-            }
-        };
 
         // ---- P2 + all-reduce: spread raw scores under the predicted summary, verified by the same reduction ----
         int64_t pts_min = 0, pts_max = 0, ipa_min = 0, ipa_max = 0;
         unsigned long long plo, phi;
-        bool raws_stale = false;
-        unsigned long long best = 0;
-        uint32_t who = 0;
-        bool have_winner = false;           // the merged arg-max already produced this decision's winner
         if (C.sum_valid) {
             // steady state: the summary is exact unless some node flipped feasibility since it was taken
-            if (inc_now) ranges_cached(plo, phi, ipa_lo, ipa_hi); else pts_pass(plo, phi);
+            pts_pass(plo, phi);
             TICK(15);
             // 6 words: the spread / affinity ranges, the flip flags and (net change of the counted set << 16) + flipped nodes
+            // (a scenario holds at most ~15,000 nodes, so both fields of the last word fit 16 bits)
             uint32_t pv[7] = {e32(plo), e32(phi), w_enc((int32_t)ipa_lo), w_enc((int32_t)ipa_hi), my_fl, ((uint32_t)my_dc << 16) + my_nf, 0u};
-            const int pop[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
-            uint32_t (&pv6)[6] = reinterpret_cast<uint32_t (&)[6]>(pv);
-            const bool merged = FAST(1u) && rng_valid;
-            if (merged) {
-                // ONE exchange: totals under the predicted ranges + arg-max, the actual ranges and the flip flags ride along
-                const unsigned long long my_best = p3_pass(pr_pts_min, pr_pts_max, pr_ipa_min, pr_ipa_max);
-                const unsigned long long warp_best = sk_argmaxx_send<6>(R, my_best, CT, TPB, pv6, pop);
-                if (pf_nodes_due) { prefetch_static(nxt, 0); pf_nodes_cls = nxt.cls; pf_nodes_due = false; }
-                spec_eval(my_best, warp_best);
-                best = sk_argmaxx_wait<6>(R, who, pv6, pop);
-            } else sk_allreduce_w<6>(R, pv6, pop);
             {
-                // unpack: flipped nodes (< 2^16: at most ~15,000 nodes per scenario) and the signed net change above them
+                const int pop[6] = {W_MIN, W_MAX, W_MIN, W_MAX, W_OR, W_SUM};
+                uint32_t (&pv6)[6] = reinterpret_cast<uint32_t (&)[6]>(pv);
+                sk_allreduce_w<6>(R, pv6, pop);
                 const uint32_t packed = pv[5];
                 pv[6] = packed & 0xffffu;
                 pv[5] = (uint32_t)((int32_t)(packed - pv[6]) >> 16);
             }
             pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]); ipa_min = w_dec(pv[2]); ipa_max = w_dec(pv[3]);
-            have_winner = merged && !(pv[4] & 1u) && pts_min == (int64_t)pr_pts_min && pts_max == (int64_t)pr_pts_max &&
-                          ipa_min == (int64_t)pr_ipa_min && ipa_max == (int64_t)pr_ipa_max;
-            if (merged) { st_merged++; if (!have_winner) st_mredo++; }
             if (pv[4] & 1u) {
                 bits_dirty = true;
                 // some node flipped.  The hostname-topology sizes (= counted nodes) follow from the net change at once.
@@ -1153,7 +978,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 const int pop[2] = {W_MIN, W_MAX};
                 sk_allreduce_w<2>(R, pv, pop);
                 pts_min = w_dec(pv[0]); pts_max = w_dec(pv[1]);
-            } else if (!sizes_ok) { set_weights(); raws_stale = C.n_soft > 0; }     // weights changed, raw scores not recomputed
+            } else if (!sizes_ok) set_weights();
             if (!(C.snorm_valid && C.nm_na_max == C.na_max && C.nm_tt_max == C.tt_max && C.nm_simon_min == C.simon_min &&
                   C.nm_simon_max == C.simon_max)) {
                 snorm_pass();
@@ -1185,27 +1010,55 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             }
             if (leader) { SC.out_node[i] = -1; if (SC.out_score) SC.out_score[i] = 0; if (SC.out_gpu) SC.out_gpu[i] = 0; }
             n_fail++;
-            rng_valid = false;
             i++;
             continue;
         }
 
         // ---- P3: totals and arg-max (first node in scenario order wins ties) ----
-        if (!have_winner) {
-            const unsigned long long my_best = p3_pass(pts_min, pts_max, ipa_min, ipa_max);
-            TICK(7);
-            // The exchange of the arg-max takes ~1,000 cycles.  Meanwhile the owner of every warp's best candidate evaluates
-            // what its node's Fit verdict and own-state score WOULD be after receiving this pod, so that the one true winner
-            // finds them ready at commit time instead of computing them on the critical path.
-            const unsigned long long warp_best = sk_argmax_send(R, my_best, CT, TPB);
-            if (pf_nodes_due) { prefetch_static(nxt, 0); pf_nodes_cls = nxt.cls; pf_nodes_due = false; }
-            spec_eval(my_best, warp_best);
-            best = sk_argmax_wait(R, who);
+        unsigned long long best = 0;
+        const int64_t ipa_diff = ipa_max - ipa_min;
+        const bool pts32 = pts_max > 0 && pts_max < (1 << 23) && pts_min >= 0;
+        #pragma unroll (NPT_T > 0 ? NPT_T : 1)
+        for (uint32_t s = 0; s < NPT; s++) {
+            uint32_t idx = s * TPB + tid;
+            uint8_t nf = A8(C_NFLAGS, idx);
+            if (!(nf & NF_FEASIBLE)) continue;
+            int64_t total = 0;
+            if (C.F > 1) {
+                int64_t pts;
+                if (C.n_soft == 0) pts = 100;
+                else if (nf & NF_IGNORED) pts = 0;
+                else if (pts_max == 0) pts = 100;
+                else if (pts32) pts = (int64_t)((uint32_t)(100 * (uint32_t)(pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / (uint32_t)pts_max);
+                else pts = (100 * (pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / pts_max;
+                int64_t ip = 0;
+                if (C.n_isc && ipa_diff > 0) ip = f2i(100.0 * ((double)((int64_t)A32(B_RAW_IPA, idx) - ipa_min) / (double)ipa_diff));
+                total = (int64_t)A32(B_OWN, idx) + (int64_t)A32(B_SNORM, idx) + ip + 2 * pts;
+            }
+            if (!PROF && i == P.dump_pod && P.dump_total) P.dump_total[(uint32_t)A32(B_NODE_G, idx)] = total;
+            uint32_t r = s * CT + gtid;
+            unsigned long long key = ((unsigned long long)(total + 1) << 24) | (unsigned long long)(0xFFFFFFu - r);
+            best = key > best ? key : best;
         }
+        TICK(7);
+        // The exchange of the arg-max takes ~1,000 cycles.  Meanwhile the owner of every warp's best candidate evaluates
+        // what its node's Fit verdict and own-state score WOULD be after receiving this pod, so that the one true winner
+        // finds them ready at commit time instead of computing them on the critical path.
+        uint32_t who;
+        const unsigned long long my_best = best;
+        const unsigned long long warp_best = sk_argmax_send(R, best, CT, TPB);
+        bool spec_fit = false;
+        int32_t spec_own = 0;
+        uint32_t spec_idx = 0xffffffffu;
+        if (my_best == warp_best && my_best != 0) {
+            const uint32_t r = 0xFFFFFFu - (uint32_t)(my_best & 0xFFFFFFu);
+            spec_idx = (r / CT) * TPB + tid;
+            const long long sc0 = PROF ? clock64() : 0;
+            own_core(spec_idx, 1, spec_fit, spec_own);
+            if (PROF) { spec_cyc += clock64() - sc0; spec_n++; }
+        }
+        best = sk_argmax_wait(R, who);
         TICK(8);
-        // the ranges this decision was taken under predict the next decision of the class
-        pr_pts_min = (int32_t)pts_min; pr_pts_max = (int32_t)pts_max; pr_ipa_min = (int32_t)ipa_min; pr_ipa_max = (int32_t)ipa_max;
-        rng_valid = pts_min == (int64_t)pr_pts_min && pts_max == (int64_t)pr_pts_max;
         const uint32_t win_r = 0xFFFFFFu - (uint32_t)(best & 0xFFFFFFu);
         const int64_t win_total = (int64_t)(best >> 24) - 1;
         const bool win_ignored = ((uint32_t)sk_wpay(S, who, T) & NF_IGNORED) != 0;
@@ -1268,7 +1121,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         bool el = (sig == cw[SCW_ELIG_SIG]) ? !win_ignored : elig_eval(P, sig, RC, g);   // same signature: the winner passed NodeAffinity
                         if (!el) continue;
                     }
-                    const uint32_t base = u < 32 ? s_incb[u] : (uint32_t)P.cnt_off[k];
+                    const uint32_t base = u < 32 ? S.incb[u] : (uint32_t)P.cnt_off[k];
                     atomicAdd(&SC.cnt[base + d], 1);
                     atomicAdd(&SC.cnt_total[k], 1);
                 }
@@ -1276,21 +1129,20 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             }
         }
         if (C.has_gpu) __syncthreads();      // the owner's next filter pass reads gpu_used, written by the helper warp
-        // every thread folds the winner into its cached counter values (the commit list comes with the class context; the
+        // every thread folds the winner into its cached counter values (S.inc was built at the class change; the
         // reductions in between contain __syncthreads)
         {
-            const uint32_t inc_meta = s_inc[SK_MAX_ENT], n_dom = inc_meta & 0xff, n_all = (inc_meta >> 8) & 0xff;
+            const uint32_t inc_meta = S.inc[SK_MAX_ENT], n_dom = inc_meta & 0xff, n_all = (inc_meta >> 8) & 0xff;
             C.aff_total += (inc_meta >> 16) & 0xff;              // node-level required-affinity counters always match the winner's node
             if (own_thread) {
                 #pragma unroll 1
-                for (uint32_t k = n_dom; k < n_all; k++) VAL(s_inc[k] & 0xff, own_idx) += 1;
+                for (uint32_t k = n_dom; k < n_all; k++) VAL(S.inc[k] & 0xff, own_idx) += 1;
             }
-            unsigned long long touched = own_thread ? 1ull << (win_r / CT) : 0ull;     // node slots whose state changed in this commit
             uint32_t cur_row = 0xffffffffu;
             unsigned long long match = 0;                        // which of this thread's nodes share the winner's domain of cur_row (NPT <= 64)
             #pragma unroll 1
             for (uint32_t k = 0; k < n_dom; k++) {
-                const uint32_t rec = s_inc[k], e = rec & 0xff, trow = (rec >> 8) & 0xff;
+                const uint32_t rec = S.inc[k], e = rec & 0xff, trow = (rec >> 8) & 0xff;
                 if (trow != cur_row) {
                     cur_row = trow;
                     match = 0;
@@ -1306,27 +1158,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 if ((rec & (1u << 16)) && win_ignored) continue;
                 if (rec & (1u << 17)) { if (sk_wpay(S, who, trow) >= 0) C.aff_total += 1; }
                 if (!match) continue;
-                touched |= match;
                 #pragma unroll (NPT_T > 0 ? NPT_T : 1)
                 for (uint32_t s = 0; s < NPT; s++)
                     if (match >> s & 1) VAL(e, s * TPB + tid) += 1;
-            }
-            // incremental mode: bring the touched nodes' feasibility bits and raw scores up to date now; flips are collected for
-            // the next decision's reduction
-            if (inc_ok) {
-                if (touched) {
-                    #pragma unroll (NPT_T > 0 ? NPT_T : 1)
-                    for (uint32_t s = 0; s < NPT; s++) {
-                        if (!(touched >> s & 1)) continue;
-                        const uint32_t idx = s * TPB + tid;
-                        if (!(A8(C_NFLAGS, idx) & NF_VALID)) continue;
-                        const uint32_t nf_before = acc_nf;
-                        const bool feas = p1_node(s, idx, acc_fl, acc_nf, acc_dc);
-                        if (acc_nf != nf_before) acc_mask |= 1ull << s;
-                        if (feas && C.n_soft && !(A8(C_NFLAGS, idx) & NF_IGNORED)) pts_raw_node(idx);
-                    }
-                }
-                inc_valid = !raws_stale;
             }
         }
         n_sched++;
@@ -1347,7 +1181,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         if (SC.n_fail) *SC.n_fail = n_fail;
         if (SC.n_sched) *SC.n_sched = n_sched;
         if (SC.clk) SC.clk[1] = sk_globaltimer();
-        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; P.stats[6] = st_fast; P.stats[7] = st_merged | (st_mredo << 32); for (int q = 0; q < 16; q++) P.stats[8 + q] = (unsigned long long)tk[q]; for (int q = 0; q < 6; q++) if (q != 3) P.stats[24 + q] = (unsigned long long)rprof[q]; }
+        if (P.stats && scen_id == 0) { P.stats[0] = n_sched + n_fail; P.stats[1] = st_class; P.stats[2] = st_sum; P.stats[3] = st_redo; P.stats[4] = st_slow; P.stats[6] = st_fast; for (int q = 0; q < 16; q++) P.stats[8 + q] = (unsigned long long)tk[q]; for (int q = 0; q < 6; q++) if (q != 3) P.stats[24 + q] = (unsigned long long)rprof[q]; }
     }
     if (PROF && P.stats && scen_id == 0 && spec_n) { atomicAdd(&P.stats[27], (unsigned long long)spec_cyc); atomicAdd(&P.stats[5], (unsigned long long)spec_n); }
     if (PROF && P.stats && scen_id == 0 && owner_n) { atomicAdd(&P.stats[30], (unsigned long long)owner_cyc); atomicAdd(&P.stats[31], (unsigned long long)owner_n); }

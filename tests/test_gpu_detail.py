@@ -169,26 +169,6 @@ def test_scenarios_twice_on_one_context_with_different_node_lists():
     o.close()
 
 
-@pytest.mark.parametrize("fast", ["0", "1", "2", "3"])
-def test_kernel_paths_agree(fast, monkeypatch):
-    """SIMON_FAST selects the decision paths (bit 0 merged arg-max, bit 1 class-context prefetch): all four combinations
-    reproduce the oracle."""
-    from util import run_oracle
-    from simon_b200.engine import Engine
-    monkeypatch.setenv("SIMON_FAST", fast)
-    p, c = make_case("c3", n_nodes=500, n_workloads=80, replicas=12, n_apps=2, seed_no=23)
-    (ref, rscore, rfc, rfp), rstate = run_oracle(c)
-    with Engine(c, device=0, record_scores=True) as eng:
-        out, score, fc, fp = eng.schedule()
-        st = eng.state()
-    np.testing.assert_array_equal(out, ref)
-    np.testing.assert_array_equal(fc, rfc)
-    sched = ref >= 0
-    np.testing.assert_array_equal(score[sched & (rscore > 0)], rscore[sched & (rscore > 0)])
-    for k in rstate:
-        np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
-
-
 def test_gpu_share_failure_names_the_nodes():
     """UnscheduledPod.Reason of a pod the Open-Gpu-Share filter rejects everywhere: one "Node:<name>" reason per node
     (open-gpu-share.go:66-79 + FitError.Error, generic_scheduler.go:72-90), sorted like every other reason."""

@@ -1,3 +1,5 @@
+// EXPERIMENT HEADER (not part of the product): the round-2 variant of csrc/simon_kernel.cuh with the merged arg-max primitives
+// (sk_argmaxx_*) that tools/ubench_cluster.cu measures against the shipped ones.  See DESIGN.md, "tried and dropped".
 // simon_kernel.cuh — persistent thread-block-cluster placement kernel (sm_100a): shared declarations.
 //
 // One scenario = one thread-block cluster (up to 16 CTAs, DSMEM).  Every node of the scenario is owned by
@@ -14,7 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/simon_gpu.h"
+#include "../include/simon_gpu.h"
 
 namespace cg = cooperative_groups;
 
@@ -26,7 +28,12 @@ namespace cg = cooperative_groups;
 #define SK_NV 16            // max values per all-reduce
 #define SK_PLW 5            // payload: up to 10 int32 packed in 5 u64 (T domains + flags); only (T + 2) / 2 of them are sent
 #define SK_MAX_WARPS 16     // threads per CTA <= 512 (the shipped variants use <= 320)
-#define SK_CSUM_W 26          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains (+1 spare)
+#define SK_CSUM_W 30          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains, score ranges (4) + their valid flag
+#define SK_AUX_W 324          // per-class tables built at upload: [0..32] compact commit list (+ count word), [33..64] counter bases, pad,
+                              //   [68..323] the entry table transposed to int32 rows: [ER_ROWS][SK_MAX_ENT]
+#define SK_AUX_INCB 33
+#define SK_AUX_ENT 68
+#define SK_XROW (1 + SK_PLW)  // first inbox row of the extra words of the merged arg-max (rows 0..SK_PLW: key + payload)
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
 enum { ER_KIND = 0, ER_K, ER_T, ER_A, ER_B, ER_INC, ER_WOFF, ER_BASE, ER_ROWS };   // ER_BASE: offset of the counter in cnt[]
@@ -91,6 +98,9 @@ struct SkParams {
     const uint64_t *class_off;
     const int64_t *class_blob;
     const int32_t *pod_class, *pod_fixed, *pod_guard;
+    const ulonglong2 *pod_meta;    // [P][2] per-pod record: {class | fixed << 32, guard | blob words << 32}, {blob offset | extra row << 32,
+                                   //   static signature | static row << 32}: everything the class-context prefetch needs, one 32-byte sector
+    const uint32_t *cls_aux;       // [n_classes][SK_AUX_W] commit tables per class (built at upload)
     const uint64_t *cnt_off;
     const int64_t *simon_raw;
     const int32_t *extra_score;
@@ -100,7 +110,9 @@ struct SkParams {
     unsigned long long *stats; // optional [8]: decisions, class changes, summary rebuilds, redone decisions
     // static cache: per (static signature, node) verdicts, filled on first use
     uint32_t n_sigs, use_scache;
-    uint32_t simon32, pad32;       // simon32: every raw Simon score lies in [0, 2^31) -> reduced as a 32-bit word
+    uint32_t simon32, fast;        // simon32: every raw Simon score lies in [0, 2^31) -> reduced as a 32-bit word
+                                   // fast: bit 0 merged arg-max (one reduction per steady decision), bit 1 class-context prefetch,
+                                   //       bit 2 incremental feasibility bits / raw scores within a class visit
     uint32_t dump_pod, pad_d;      // debug: pod index whose per-node totals / filter reasons are written out (0xffffffff: none)
     long long *dump_total;         // [N]
     int32_t *dump_code;            // [N] 0 = feasible, else the reason bitmask
@@ -114,15 +126,13 @@ struct SkSmem {
     int64_t *a64;        // [A_N64][L]
     int32_t *a32;        // [B_N32 + T + emax][L]
     uint8_t *a8;         // [C_N8][L]
-    int64_t *blob;       // [max_blob_words]
+    int64_t *blob;       // [2][max_blob_words] current class record + the prefetched next one
     unsigned long long *box;     // [2][SK_NV][nslots] reduction inbox: one slot per CTA of the cluster, double buffered
     unsigned long long *wpart;   // [SK_NV][SK_MAX_WARPS] per-warp partials of the CTA-level fold (u64, or 2*SK_NV rows of u32)
-    int32_t *ent;        // [ER_ROWS][SK_MAX_ENT]
     uint32_t *tnd;       // [SIMON_MAX_TOPOS] topo_ndom copy
-    uint32_t *inc;       // [SK_MAX_ENT + 1] compact list of the entries the current class increments; [SK_MAX_ENT] = count
-    long long *pred;     // [SK_CSUM_W] the entered class's stored summary record (one global read per CTA)
+    uint32_t *aux;       // [2][SK_AUX_W] commit tables of the current / prefetched class (SkParams::cls_aux rows)
+    long long *pred;     // [2][SK_CSUM_W] stored summary record of the current / prefetched class
     int32_t *lastdom;    // [SIMON_MAX_TOPOS] topology domains of the last winner (single-node flip fast path)
-    uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
     SkScenario *scen;    // this cluster's scenario descriptor
     unsigned long long *mbar;    // [2] mbarriers guarding the two inbox buffers
@@ -134,10 +144,9 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * A_N64 * L);
     b += sk_align(4ull * (B_N32 + T + emax) * L);
     b += sk_align(1ull * C_N8 * L);
-    b += sk_align(8ull * blob_words);
+    b += sk_align(8ull * 2 * blob_words);
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
-    b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
-    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(8ull * SK_CSUM_W);
+    b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * 2 * SK_AUX_W) + sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(8ull * 2 * SK_CSUM_W);
     b += sk_align(8ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
@@ -148,15 +157,13 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.a64 = (int64_t *)p; p += sk_align(8ull * A_N64 * L);
     S.a32 = (int32_t *)p; p += sk_align(4ull * (B_N32 + T + emax) * L);
     S.a8 = (uint8_t *)p; p += sk_align(1ull * C_N8 * L);
-    S.blob = (int64_t *)p; p += sk_align(8ull * blob_words);
+    S.blob = (int64_t *)p; p += sk_align(8ull * 2 * blob_words);
     S.box = (unsigned long long *)p; p += sk_align(8ull * 2 * SK_NV * nslots);
     S.wpart = (unsigned long long *)p; p += sk_align(8ull * SK_NV * SK_MAX_WARPS);
-    S.ent = (int32_t *)p; p += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     S.tnd = (uint32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
-    S.inc = (uint32_t *)p; p += sk_align(4ull * (SK_MAX_ENT + 1));
-    S.incb = (uint32_t *)p; p += sk_align(4ull * 32);
+    S.aux = (uint32_t *)p; p += sk_align(4ull * 2 * SK_AUX_W);
     S.lastdom = (int32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
-    S.pred = (long long *)p; p += sk_align(8ull * SK_CSUM_W);
+    S.pred = (long long *)p; p += sk_align(8ull * 2 * SK_CSUM_W);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
     S.mbar = (unsigned long long *)p;
@@ -407,6 +414,102 @@ __device__ __forceinline__ unsigned long long sk_argmax(SkRed &R, unsigned long 
     sk_argmax_send(R, key, CT, TPB);
     return sk_argmax_wait(R, who);
 }
+// Merged arg-max: the arg-max message also carries NX 32-bit words that are all-reduced with their own operators (the
+// spread / affinity score ranges and the flip flags of the steady-state decision), so that a decision whose predicted
+// ranges hold needs ONE cluster exchange.  Lanes 0..CS-1 of warp 0 send key + payload, lanes 16..16+CS-1 the words.
+template <int NX>
+__device__ __forceinline__ unsigned long long sk_argmaxx_send(SkRed &R, unsigned long long key, uint32_t CT, uint32_t TPB,
+                                                              uint32_t (&xw)[NX], const int (&xop)[NX]) {
+    constexpr int NM = (NX + 1) / 2;
+    static_assert(SK_XROW + NM <= SK_NV && 2 + (NX + 1) / 2 <= SK_NV, "message too long for the inbox");
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    SkSmem &S = *R.S;
+    const uint32_t ph = R.mph, buf = ph & 1, ns = S.nslots;
+    const uint32_t plw = (S.T + 2u) >> 1;
+    if (threadIdx.x == 0) sk_mbar_expect(&S.mbar[buf], ns * (1 + plw + NM) * 8u);
+    key = warp_maxu64(key);
+#pragma unroll
+    for (int i = 0; i < NX; i++) xw[i] = warp_w(xw[i], xop[i]);
+    uint32_t *wp = (uint32_t *)(S.wpart + 2 * SK_MAX_WARPS);      // rows 0..1 of wpart belong to the key
+    if (lane == 0) {
+        S.wpart[warp] = key;
+#pragma unroll
+        for (int i = 0; i < NX; i++) wp[i * SK_MAX_WARPS + warp] = xw[i];
+    }
+    const long long pt0 = R.prof ? clock64() : 0;
+    __syncthreads();
+    if (R.prof) R.prof[3] += clock64() - pt0;
+    if (warp == 0) {
+        const unsigned long long k = warp_maxu64(lane < nwarp ? S.wpart[lane] : 0ull);
+        uint32_t c[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) c[i] = warp_w(lane < nwarp ? wp[i * SK_MAX_WARPS + lane] : w_ident(xop[i]), xop[i]);
+        int32_t pw = -1;
+        if (k != 0) {
+            uint32_t r = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFu);
+            uint32_t idx = (r / CT) * TPB + (r % CT) % TPB;
+            if (lane < S.T) pw = S.a32[(B_N32 + lane) * S.L + idx];
+            else if (lane == S.T) pw = S.a8[C_NFLAGS * S.L + idx];
+        }
+        unsigned long long w[SK_PLW];
+#pragma unroll
+        for (int j = 0; j < SK_PLW; j++) {
+            unsigned lo = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j), hi = (unsigned)__shfl_sync(0xffffffffu, pw, 2 * j + 1);
+            w[j] = ((unsigned long long)hi << 32) | lo;
+        }
+        if (lane < R.CS) {
+            const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), lane);
+            const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), lane);
+            sk_st_async(rbox, k, rbar);
+#pragma unroll
+            for (int j = 0; j < SK_PLW; j++)
+                if ((uint32_t)j < plw) sk_st_async(rbox + 8u * (1 + j) * ns, w[j], rbar);
+        } else if (lane >= 16 && lane - 16 < R.CS) {
+            const uint32_t dst = lane - 16;
+            const uint32_t rbar = sk_mapa(sk_saddr(&S.mbar[buf]), dst);
+            const uint32_t rbox = sk_mapa(sk_saddr(S.box + (size_t)buf * SK_NV * ns + R.crank), dst);
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const uint32_t hi = 2 * m + 1 < NX ? c[2 * m + 1 < NX ? 2 * m + 1 : 0] : 0u;
+                sk_st_async(rbox + 8u * (SK_XROW + m) * ns, ((unsigned long long)hi << 32) | c[2 * m], rbar);
+            }
+        }
+    }
+    return key;
+}
+template <int NX>
+__device__ __forceinline__ unsigned long long sk_argmaxx_wait(SkRed &R, uint32_t &who, uint32_t (&xw)[NX], const int (&xop)[NX]) {
+    constexpr int NM = (NX + 1) / 2;
+    const unsigned lane = threadIdx.x & 31;
+    SkSmem &S = *R.S;
+    const uint32_t ph = R.mph, buf = ph & 1, parity = (ph >> 1) & 1, ns = S.nslots;
+    const long long pt1 = R.prof ? clock64() : 0;
+    sk_mbar_wait(&S.mbar[buf], parity);
+    if (R.prof) { R.prof[4] += clock64() - pt1; R.prof[5] += 1; }
+    const unsigned long long *bx = S.box + (size_t)buf * SK_NV * ns;
+    const bool in = lane < ns;
+    const unsigned long long y = in ? bx[lane] : 0ull;
+    const unsigned long long m = warp_maxu64(y);
+    who = buf * SK_NV * ns + (__ffs(__ballot_sync(0xffffffffu, y == m)) - 1);
+#pragma unroll
+    for (int q = 0; q < NM; q++) {
+        const unsigned long long x = in ? bx[(SK_XROW + q) * ns + lane] : 0ull;
+        xw[2 * q] = warp_w(in ? (uint32_t)x : w_ident(xop[2 * q]), xop[2 * q]);
+        if (2 * q + 1 < NX) xw[2 * q + 1 < NX ? 2 * q + 1 : 0] = warp_w(in ? (uint32_t)(x >> 32) : w_ident(xop[2 * q + 1 < NX ? 2 * q + 1 : 0]), xop[2 * q + 1 < NX ? 2 * q + 1 : 0]);
+    }
+    R.mph++;
+    return m;
+}
+
+// cp.async helpers (class-context prefetch)
+__device__ __forceinline__ void sk_cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sk_saddr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sk_cp_async16_cg(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sk_saddr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sk_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // word j of the winner's payload: j < T -> domain of topology j, j == T -> node flags
 __device__ __forceinline__ int32_t sk_wpay(const SkSmem &S, uint32_t who, uint32_t j) {
     return ((const int32_t *)(S.box + who + (size_t)(1 + (j >> 1)) * S.nslots))[j & 1];

@@ -1,6 +1,6 @@
 // micro-benchmark: cost of cluster barriers and of the engine's all-reduce primitives on a 16-CTA cluster
 #include <cstdio>
-#include "../open-simulator_b200/csrc/simon_kernel.cuh"
+#include "sk_experimental.cuh"
 
 extern "C" __global__ void k_sync(long long *out, int iters, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
