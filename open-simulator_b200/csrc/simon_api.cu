@@ -128,6 +128,7 @@ struct simon_ctx {
     DevBuf<uint64_t> d_class_off, d_cnt_off;
     DevBuf<int64_t> d_class_blob, d_simon_raw;
     DevBuf<int32_t> d_pod_class, d_pod_fixed, d_pod_guard, d_extra;
+    DevBuf<uint32_t> d_cls_aux;
     // debug dump of one pod's per-node totals / filter verdicts (simon_debug_*)
     uint32_t dump_pod = 0xffffffffu;
     DevBuf<long long> d_dump_total;
@@ -142,6 +143,8 @@ struct simon_ctx {
     DevBuf<SmvClass> d_mv_classes;
     uint32_t mv_n = 0, mv_base = 0;
     std::vector<uint8_t> bypass;        // per pod: never reaches the scheduler in a single-scenario run (pre-bound or absent)
+    DevBuf<uint32_t> d_sig_class;       // a class per static signature (dense fill of the static verdict cache)
+    bool static_filled = false;
     // single-scenario state
     ScenState st;
     uint32_t max_fail = 0;
@@ -239,6 +242,7 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.emax = ctx->emax;
     P.stats = ctx->d_stats.p;
     P.n_sigs = ctx->n_sigs; P.use_scache = ctx->use_scache; P.simon32 = ctx->simon32; P.scache = ctx->d_scache.p;
+    P.cls_aux = ctx->d_cls_aux.p;
     P.dump_pod = 0xffffffffu; P.dump_total = nullptr; P.dump_code = nullptr;
 }
 
@@ -458,6 +462,49 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     CU(ctx->d_extra.upload(p->extra_score, (size_t)std::max(1u, p->n_extra_rows) * std::max(1u, ctx->N), st));
     if (blob_words >= (1ull << 32)) return fail(ctx, SIMON_ERR_LIMIT, "class records exceed 2^32 words");
     {
+        // per-class tables the kernel needs at every class switch, derived once here instead of by every CTA every time:
+        // the entry table as int32 rows, the compact list of the entries a commit of the class increments, counter bases
+        std::vector<uint32_t> aux((size_t)std::max(1u, p->n_classes) * SK_AUX_W, 0u);
+        for (uint32_t c = 0; c < p->n_classes; c++) {
+            const int64_t *cw = p->class_blob + p->class_off[c];
+            const int64_t *et = cw + cw[SCW_OFF_ENT];
+            const uint32_t E = (uint32_t)(cw[SCW_N_PORTS] + cw[SCW_N_PTS_HARD] + cw[SCW_N_PTS_SOFT] + cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] +
+                                          cw[SCW_N_IPA_EXIST] + cw[SCW_N_IPA_SCORE]);
+            if ((uint64_t)cw[SCW_OFF_ENT] + 8ull * E > p->class_off[c + 1] - p->class_off[c] || (uint32_t)cw[SCW_N_ENT] != E)
+                return fail(ctx, SIMON_ERR_INVALID, "class %u: entry table does not match the list sizes", c);
+            uint32_t *ax = aux.data() + (size_t)c * SK_AUX_W;
+            uint32_t recs[SK_MAX_ENT];
+            bool node_lvl[SK_MAX_ENT], incs[SK_MAX_ENT];
+            uint32_t n_dom = 0, n_all = 0, n_aff_node = 0;
+            for (uint32_t e = 0; e < E; e++) {
+                const int64_t *r = et + 8ull * e;
+                const int32_t kind = (int32_t)r[ER_KIND];
+                const bool host = kind == EK_SOFT && r[ER_B] != 0;
+                incs[e] = r[ER_INC] != 0;
+                // entry | topology row << 8 | flags << 16 (bit 16: domain-level soft constraint, bit 17: required affinity term)
+                recs[e] = e | ((host ? 0u : (uint32_t)r[ER_T]) << 8) | ((kind == EK_SOFT && !host) ? 1u << 16 : 0u) | (kind == EK_AFF ? 1u << 17 : 0u);
+                // entries on topology row 0 (the node itself) can only match the winner's own node: they go to the end of the
+                // list and are applied by the owning thread alone; every thread walks the others
+                node_lvl[e] = incs[e] && ((recs[e] >> 8) & 0xff) == 0;
+                if (incs[e]) { n_all++; if (!node_lvl[e]) n_dom++; else if (recs[e] & (1u << 17)) n_aff_node++; }
+                for (uint32_t q = 0; q < ER_ROWS; q++) ax[SK_AUX_ENT + q * SK_MAX_ENT + e] = (uint32_t)(int32_t)r[q];
+            }
+            uint32_t kd = 0, kn = n_dom;
+            for (uint32_t e = 0; e < E; e++) {
+                if (!incs[e]) continue;
+                if (node_lvl[e]) ax[kn++] = recs[e]; else ax[kd++] = recs[e];
+            }
+            ax[SK_MAX_ENT] = n_dom | (n_all << 8) | (n_aff_node << 16);
+            const int64_t *inc = cw + cw[SCW_OFF_INC];
+            for (uint32_t u = 0; u < 32 && (int64_t)u < cw[SCW_N_INC]; u++) {
+                if (inc[3 * u] < 0 || (uint64_t)inc[3 * u] >= p->n_counters) return fail(ctx, SIMON_ERR_INVALID, "class %u: bad counter in the commit list", c);
+                ax[SK_AUX_INCB + u] = (uint32_t)cnt_off[inc[3 * u]];
+            }
+        }
+        CU(ctx->d_cls_aux.upload(aux.data(), aux.size(), st));
+        CU(cudaStreamSynchronize(st));
+    }
+    {
         // compact per-class header of the move kernel (simon_moves.cu): scoring + Fit inputs and a few counts in 64 bytes
         std::vector<SmvClass> mc(std::max(1u, p->n_classes));
         for (uint32_t c = 0; c < p->n_classes; c++) {
@@ -479,6 +526,13 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
             for (uint32_t e = 0; e < E; e++) if (et[8ull * e + ER_INC]) bits |= SMC_OWN_INC;
             k.bits = bits;
         }
+        std::vector<uint32_t> sig_class(std::max(1u, p->n_static_sigs), 0u);
+        for (uint32_t c = p->n_classes; c-- > 0;) {
+            const int64_t sg = (p->class_blob + p->class_off[c])[SCW_STATIC_SIG];
+            if (sg >= 0 && (uint64_t)sg < sig_class.size()) sig_class[sg] = c;
+        }
+        CU(ctx->d_sig_class.upload(sig_class.data(), sig_class.size(), st));
+        ctx->static_filled = false;
         CU(ctx->d_mv_classes.upload(mc.data(), mc.size(), st));
         CU(cudaStreamSynchronize(st));       // `mc` leaves scope
     }
@@ -792,6 +846,17 @@ int simon_moves_upload(simon_ctx *ctx, const simon_move *moves, uint32_t n_moves
     CU(ctx->d_mv_gain.alloc(n_moves)); CU(ctx->d_mv_code.alloc(n_moves)); CU(ctx->d_mv_hist.alloc(SMV_NBINS)); CU(ctx->d_mv_topn.alloc(2));
     CU(ctx->d_mv_best_pod.alloc(std::max(1u, ctx->n_pods))); CU(ctx->d_mv_best.alloc(1)); CU(ctx->d_mv_nodes.alloc(std::max(1u, ctx->N)));
     ctx->mv_n = n_moves; ctx->mv_base = move_base;
+    if (!ctx->static_filled && ctx->use_scache && ctx->N && ctx->n_classes) {
+        // once per uploaded pod list: the static verdicts of every (signature, node) pair, densely
+        SkParams Pm;
+        fill_params(ctx, Pm);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        simon_static_fill<<<sms * 8, 256, 0, ctx->stream>>>(Pm, ctx->d_sig_class.p, ctx->n_sigs);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        ctx->static_filled = true;
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     return SIMON_OK;
 }

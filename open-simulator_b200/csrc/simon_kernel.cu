@@ -15,6 +15,15 @@
 // it with a 22-word reduction.
 #include "simon_kernel.cuh"
 
+// Compile-time options of the class switch (measured one by one, profiles/r02_kernel_variants.txt):
+//   bit 0  the entry table (int32 rows), the compact commit list and its counter bases come precomputed from the upload
+//          (SkParams::cls_aux) instead of being transposed / compacted by every CTA at every class switch
+//   bit 1  the log weights of the spread score come from two shared-memory windows of the log table (sizes 0..63 and 64 sizes
+//          around the class's hostname-topology size) instead of a dependent global load at every class switch / size change
+#ifndef SIMON_OPT
+#define SIMON_OPT 3
+#endif
+
 // ---- small helpers --------------------------------------------------------------------------------------
 __device__ __forceinline__ int32_t ldcg32(const int32_t *p) { return __ldcg(p); }
 
@@ -366,11 +375,23 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     int32_t psz[SK_MAX_SOFT];      // topology sizes the current weights were computed from (registers: static indexing only)
 #pragma unroll
     for (int q = 0; q < SK_MAX_SOFT; q++) psz[q] = 0;
+    uint32_t lw_base = 0xffffffffu;     // first table index held by the second log window (0xffffffff: not loaded)
     auto set_weights = [&]() {
 #pragma unroll
         for (int js = 0; js < SK_MAX_SOFT; js++)
-            if ((uint32_t)js < C.n_soft) S.soft_w[js] = __ldg(&P.log_table[psz[js] + 2]);
+            if ((uint32_t)js < C.n_soft) {
+                const uint32_t ti = (uint32_t)psz[js] + 2u;
+                double w;
+                if ((SIMON_OPT & 2) && ti < SK_LOGW) w = S.logw[ti];
+                else if ((SIMON_OPT & 2) && ti - lw_base < SK_LOGW) w = S.logw[SK_LOGW + ti - lw_base];
+                else w = __ldg(&P.log_table[ti]);
+                S.soft_w[js] = w;
+            }
     };
+    if (SIMON_OPT & 2) {
+        if (tid < SK_LOGW) S.logw[tid] = tid < P.n_log ? __ldg(&P.log_table[tid]) : 0.0;
+        __syncthreads();
+    }
 
     const uint32_t end = P.first + P.count;
     uint32_t i = P.first;
@@ -501,6 +522,17 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             for (uint32_t w = tid; w < words; w += TPB) S.blob[w] = gw[w];
             // prediction of the topology sizes from the previous visit of this class (any value is safe: verified)
             if (tid < SK_CSUM_W) S.pred[tid] = SC.csum ? __ldcg(SC.csum + (uint64_t)cls * SK_CSUM_W + tid) : 0;
+            if (SIMON_OPT & 1) {
+                // commit list, counter bases and the int32 entry table as the upload laid them out
+                const uint32_t *ax = P.cls_aux + (uint64_t)cls * SK_AUX_W;
+                #pragma unroll 1
+                for (uint32_t w = tid; w < SK_AUX_W; w += TPB) {
+                    const uint32_t v = __ldg(ax + w);
+                    if (w <= SK_MAX_ENT) S.inc[w] = v;
+                    else if (w < SK_AUX_INCB + 32) S.incb[w - SK_AUX_INCB] = v;
+                    else if (w >= SK_AUX_ENT) S.ent[w - SK_AUX_ENT] = (int32_t)v;
+                }
+            }
             __syncthreads();
             const long long *pred = S.pred;
             TICK(12);
@@ -533,14 +565,26 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 long long v = pred[1 + js];
                 psz[js] = (C.have_pred && v >= 0 && v + 2 < (long long)P.n_log) ? (int32_t)v : 0;
             }
-            {
+            if (SIMON_OPT & 2) {
+                // log-weight window around the largest predicted topology size (the hostname topology: ~ number of feasible nodes)
+                int32_t mx = 0;
+#pragma unroll
+                for (int js = 0; js < SK_MAX_SOFT; js++) mx = psz[js] > mx ? psz[js] : mx;
+                const uint32_t ti = (uint32_t)mx + 2u;                          // table index of the largest size
+                // keep ti inside [base + 8, base + 60): sizes shrink (nodes fill up, winners leave) far more often than they grow
+                if (lw_base == 0xffffffffu || ti < lw_base + 8u || ti >= lw_base + 60u) {
+                    lw_base = ti > 44u ? ti - 44u : 0u;
+                    if (tid < SK_LOGW) S.logw[SK_LOGW + tid] = lw_base + tid < P.n_log ? __ldg(&P.log_table[lw_base + tid]) : 0.0;
+                }
+            }
+            if (!(SIMON_OPT & 1)) {
                 // the entry table was laid out by the snapshot compiler (SCW_OFF_ENT): 8 words per entry -> 8 rows in smem
                 const int64_t *et = cw + cw[SCW_OFF_ENT];
 #pragma unroll 1
                 for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
             }
             __syncthreads();
-            if (tid < 32) {
+            if (!(SIMON_OPT & 1) && tid < 32) {
                 // compact list of the entries this class increments on commit: entry | topology row << 8 | flags << 16
                 // (lane e looks at entry e; SK_MAX_ENT == 32)
                 const uint32_t e = tid;

@@ -26,6 +26,11 @@ namespace cg = cooperative_groups;
 #define SK_NV 16            // max values per all-reduce
 #define SK_PLW 5            // payload: up to 10 int32 packed in 5 u64 (T domains + flags); only (T + 2) / 2 of them are sent
 #define SK_MAX_WARPS 16     // threads per CTA <= 512 (the shipped variants use <= 320)
+#define SK_AUX_W 324          // per-class tables built at upload (SkParams::cls_aux): [0..32] compact commit list (+ count word),
+                              //   [33..64] counter bases of the commit list, pad, [68..323] entry table as int32 rows [ER_ROWS][SK_MAX_ENT]
+#define SK_AUX_INCB 33
+#define SK_AUX_ENT 68
+#define SK_LOGW 64            // entries of each of the two log-weight windows kept in shared memory
 #define SK_CSUM_W 26          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains (+1 spare)
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
@@ -91,6 +96,7 @@ struct SkParams {
     const uint64_t *class_off;
     const int64_t *class_blob;
     const int32_t *pod_class, *pod_fixed, *pod_guard;
+    const uint32_t *cls_aux;       // [n_classes][SK_AUX_W] per-class commit / entry tables (built at upload)
     const uint64_t *cnt_off;
     const int64_t *simon_raw;
     const int32_t *extra_score;
@@ -124,6 +130,7 @@ struct SkSmem {
     int32_t *lastdom;    // [SIMON_MAX_TOPOS] topology domains of the last winner (single-node flip fast path)
     uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
+    double *logw;        // [2][SK_LOGW] windows of the log table: sizes 0..63, and 64 sizes around the current hostname-topology size
     SkScenario *scen;    // this cluster's scenario descriptor
     unsigned long long *mbar;    // [2] mbarriers guarding the two inbox buffers
     uint32_t L, T, nslots;
@@ -138,7 +145,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(8ull * SK_CSUM_W);
-    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
+    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(8ull * 2 * SK_LOGW) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
 }
@@ -158,6 +165,7 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.lastdom = (int32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.pred = (long long *)p; p += sk_align(8ull * SK_CSUM_W);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
+    S.logw = (double *)p; p += sk_align(8ull * 2 * SK_LOGW);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
     S.mbar = (unsigned long long *)p;
     S.L = L; S.T = T; S.nslots = nslots;

@@ -84,31 +84,47 @@ __global__ void simon_moves_pack(uint32_t N, uint32_t T, const int64_t *alloc_mc
     out[g] = r;
 }
 
+// one 32-byte sector with ONE 256-bit load (sm_100: LDG.E.256), read-only path
+__device__ __forceinline__ void smv_ld_sector(void *dst, const void *src) {
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(dst);
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(d[0]), "=l"(d[1]), "=l"(d[2]), "=l"(d[3]) : "l"(src));
+}
 // sector mask: bit s = load the s-th 32-byte sector of the record (the others stay zero and are never read)
 template <int MASK>
 __device__ __forceinline__ SmvNode smv_load(const SmvNode *p) {
     SmvNode r;
-    const int4 *q = reinterpret_cast<const int4 *>(p);
-    int4 *d = reinterpret_cast<int4 *>(&r);
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(&r);
 #pragma unroll
-    for (int i = 0; i < 6; i++) d[i] = ((MASK >> (i >> 1)) & 1) ? __ldg(q + i) : make_int4(0, 0, 0, 0);
+    for (int sec = 0; sec < 3; sec++) {
+        if ((MASK >> sec) & 1) smv_ld_sector(d + 4 * sec, reinterpret_cast<const unsigned long long *>(p) + 4 * sec);
+        else { d[4 * sec] = 0; d[4 * sec + 1] = 0; d[4 * sec + 2] = 0; d[4 * sec + 3] = 0; }
+    }
     return r;
 }
 __device__ __forceinline__ void smv_load_sector(SmvNode &r, const SmvNode *p, int sec) {
-    const int4 *q = reinterpret_cast<const int4 *>(p);
-    int4 *d = reinterpret_cast<int4 *>(&r);
-    d[2 * sec] = __ldg(q + 2 * sec); d[2 * sec + 1] = __ldg(q + 2 * sec + 1);
+    smv_ld_sector(reinterpret_cast<unsigned long long *>(&r) + 4 * sec, reinterpret_cast<const unsigned long long *>(p) + 4 * sec);
+}
+
+// exact floor(x / d) for 0 <= x < 2^63, 0 < d, quotient <= 100: one f64 division and an integer fix-up instead of the emulated
+// 64-bit integer division (the estimate is within 1e-13 of the true quotient, so it is off by at most one)
+__device__ __forceinline__ int64_t smv_div100(int64_t x, int64_t d, double dd) {
+    int64_t q = (int64_t)((double)x / dd);
+    const int64_t r = x - q * d;
+    if (r < 0) q--;
+    else if (r >= d) q++;
+    return q;
 }
 
 // LeastAllocated + BalancedAllocation for a pod with scoring request (sc, sm) on a node whose NonZeroRequested is (nzc, nzm)
-// (least_allocated.go:93-117, balanced_allocation.go:82-119); same arithmetic as the placement kernel's own_core
+// (least_allocated.go:93-117, balanced_allocation.go:82-119); same values as the placement kernel's own_core
 __device__ __forceinline__ int32_t smv_own(int64_t capc, int64_t capm, int64_t nzc, int64_t nzm, int64_t sc, int64_t sm) {
     const int64_t rqc = nzc + sc, rqm = nzm + sm;
-    const int64_t s1 = (capc == 0 || rqc > capc) ? 0 : ((capc - rqc) * 100) / capc;
-    const int64_t s2 = (capm == 0 || rqm > capm) ? 0 : ((capm - rqm) * 100) / capm;
+    const double dc = (double)capc, dm = (double)capm;
+    const int64_t s1 = (capc == 0 || rqc > capc) ? 0 : smv_div100((capc - rqc) * 100, capc, dc);
+    const int64_t s2 = (capm == 0 || rqm > capm) ? 0 : smv_div100((capm - rqm) * 100, capm, dm);
     const int64_t la = (s1 + s2) / 2;
-    const double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
-    const double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
+    const double cf = capc == 0 ? 1.0 : (double)rqc / dc;
+    const double mf = capm == 0 ? 1.0 : (double)rqm / dm;
     int64_t ba = 0;
     if (!(cf >= 1.0 || mf >= 1.0)) ba = f2i((1.0 - fabs(cf - mf)) * 100.0);
     return (int32_t)(la + ba);
@@ -147,13 +163,9 @@ __global__ void __launch_bounds__(256, MINB) simon_moves_kernel(const __grid_con
         }
         if (code == SMV_OK) {
             const int32_t cls = __ldg(P.pod_class + pod);
-            const int4 *ch = reinterpret_cast<const int4 *>(P.classes + cls);
             SmvClass kc;
-            {
-                int4 *d = reinterpret_cast<int4 *>(&kc);
-#pragma unroll
-                for (int i = 0; i < 4; i++) d[i] = __ldg(ch + i);
-            }
+            smv_ld_sector(&kc, P.classes + cls);
+            smv_ld_sector(reinterpret_cast<unsigned long long *>(&kc) + 4, reinterpret_cast<const unsigned long long *>(P.classes + cls) + 4);
             const uint32_t bits = kc.bits, cflags = bits & 0xffu;
             if (bits & SMC_NOT_MOVABLE) code = SMV_NOT_MOVABLE;
             else {
@@ -254,11 +266,11 @@ __global__ void __launch_bounds__(256, MINB) simon_moves_kernel(const __grid_con
         if (code == SMV_OK) {
             const uint32_t gm = P.move_base + m;
             const unsigned long long key = ((unsigned long long)(uint32_t)(gain + SMV_GAIN_BIAS) << 32) | (unsigned long long)(0xffffffffu - gm);
-            atomicMax(P.best_per_pod + pod, key);
+            asm volatile("red.global.max.u64 [%0], %1;" ::"l"(P.best_per_pod + pod), "l"(key) : "memory");
             my_best = key > my_best ? key : my_best;
             int bin = gain + 200;
             bin = bin < 0 ? 0 : (bin > SMV_NBINS - 1 ? SMV_NBINS - 1 : bin);
-            atomicAdd(&s_hist[bin], 1u);
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_hist[bin])) : "memory");
         }
     }
     my_best = warp_maxu64(my_best);
@@ -266,6 +278,45 @@ __global__ void __launch_bounds__(256, MINB) simon_moves_kernel(const __grid_con
     __syncthreads();
     for (uint32_t q = threadIdx.x; q < SMV_NBINS; q += blockDim.x)
         if (s_hist[q]) atomicAdd(P.hist + q, s_hist[q]);
+}
+
+// Static verdict records of EVERY (static signature, node) pair, computed densely (one thread per pair, the node index
+// fastest: label / taint words are read coalesced) - what the placement kernel's class switch fills lazily on first use
+// (same record format: code:8 | flags:8 | tt:8 | valid bit 24 | na:32).  A snapshot that was imported rather than placed
+// (all pods pre-bound) has an empty cache; scoring a million moves against it would otherwise evaluate a selector program
+// per move.  sig_class[s] = a class that carries signature s.
+__global__ void __launch_bounds__(256) simon_static_fill(SkParams P, const uint32_t *sig_class, uint32_t n_sigs) {
+    const ReqCtx RC{P.label_bits, P.N};
+    const uint64_t total = (uint64_t)n_sigs * P.N;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t sig = (uint32_t)(q / P.N), g = (uint32_t)(q % P.N);
+        if (__ldcg(P.scache + q) & (1ull << 24)) continue;
+        const int64_t *cw = P.class_blob + P.class_off[sig_class[sig]];
+        const uint32_t cflags = (uint32_t)cw[SCW_FLAGS];
+        const bool ok = selection_ok(cw, RC, g);
+        uint8_t fl = ok ? NF_SEL_OK : 0, code = 0;
+        const int64_t *tol = cw + cw[SCW_OFF_TOL];
+        if ((P.node_flags[g] & SIMON_NODE_UNSCHEDULABLE) && !(cflags & SIMON_CLS_TOL_UNSCHED)) code = 1;
+        if (!code && cw[SCW_NODE_NAME] != -1 && cw[SCW_NODE_NAME] != (int64_t)g) code = 2;
+        if (!code)
+            for (uint32_t w = 0; w < P.WT; w++)
+                if (P.taint_hard[(uint64_t)w * P.N + g] & ~(uint64_t)tol[w]) code = 3;
+        if (!code && !ok) code = 4;
+        const int64_t *p = cw + cw[SCW_OFF_PREF];
+        int64_t na64 = 0;
+        for (int64_t z = 0; z < cw[SCW_N_PREF]; z++) { int64_t w = *p++; if (term_eval(p, RC, g)) na64 += w; }
+        int32_t tt = 0;
+        for (uint32_t w = 0; w < P.WT; w++) tt += __popcll(P.taint_soft[(uint64_t)w * P.N + g] & ~(uint64_t)tol[P.WT + w]);
+        bool hk = true, ign = false;
+        const int64_t *hard = cw + cw[SCW_OFF_PTS_HARD], *soft = cw + cw[SCW_OFF_PTS_SOFT];
+        for (int64_t j = 0; j < cw[SCW_N_PTS_HARD]; j++) if (P.topo_dom[(uint64_t)hard[4 * j + 1] * P.N + g] < 0) hk = false;
+        for (int64_t j = 0; j < cw[SCW_N_PTS_SOFT]; j++) if (P.topo_dom[(uint64_t)soft[5 * j + 1] * P.N + g] < 0) ign = true;
+        if (hk) fl |= NF_HARDKEYS;
+        if (ign) fl |= NF_IGNORED;
+        if (tt < 256)
+            P.scache[q] = (unsigned long long)code | ((unsigned long long)fl << 8) | ((unsigned long long)(uint32_t)tt << 16) | (1ull << 24) |
+                          ((unsigned long long)(uint32_t)(int32_t)na64 << 32);
+    }
 }
 
 // Top-k by (gain descending, move index ascending): one block scans the move list in index order and keeps every feasible
