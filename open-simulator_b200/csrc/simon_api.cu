@@ -250,7 +250,7 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
 #define SIMON_AUTO_TPB 320u
 
 // choose cluster size / threads / nodes-per-thread for n_active nodes
-int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &TPB, uint32_t &NPT, size_t &smem) {
+int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &TPB, uint32_t &NPT, size_t &smem, uint32_t n_scen = 1) {
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     const uint32_t cs_opts[5] = {16, 8, 4, 2, 1};
@@ -259,7 +259,12 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
     for (uint32_t ci = 0; ci < 5; ci++) {
         uint32_t cs = cs_opts[ci];
         if (want_cs) { if (cs != want_cs) continue; }
-        else if (cs > 1 && (uint64_t)(cs / 2) * 256 * 3 >= n_active) continue;   // smallest cluster with <= 3 nodes/thread at 256 threads
+        else if (cs > 1 && (uint64_t)(cs / 2) * 256 * 3 >= n_active) {
+            // smallest cluster with <= 3 nodes/thread at 256 threads ... unless the batch is so small that larger clusters
+            // (fewer nodes per thread -> shorter decisions) still all run at once: one CTA per SM, 7 clusters of 16 / 14 of 8
+            const uint32_t fit = cs == 16 ? 7u : cs == 8 ? 14u : cs == 4 ? 32u : cs == 2 ? 70u : 148u;
+            if (n_scen < 2 || n_scen > fit || (uint64_t)(cs / 2) * 64 >= n_active) continue;
+        }
         for (uint32_t npt = 1; npt <= 64; npt++) {
             uint32_t t;
             if (want_t) {
@@ -752,7 +757,7 @@ int simon_scenarios_run(simon_ctx *ctx, const simon_scenario *scen, uint32_t n, 
     CU(ctx->d_scen.upload(h.data(), n, st));
     uint32_t CS, TPB, NPT;
     size_t smem;
-    int rc = choose_geometry(ctx, max_active, CS, TPB, NPT, smem);
+    int rc = choose_geometry(ctx, max_active, CS, TPB, NPT, smem, n);
     if (rc) return rc;
     SkParams Pm;
     fill_params(ctx, Pm);
