@@ -810,13 +810,11 @@ int simon_state_download_ext(simon_ctx *ctx, int64_t *req_scalar, int64_t *gpu_u
 static int moves_launch(simon_ctx *ctx, bool record) {
     cudaStream_t st = ctx->stream;
     const uint32_t N = ctx->N, n = ctx->mv_n;
-    CU(cudaMemsetAsync(ctx->d_mv_best_pod.p, 0, 8ull * std::max(1u, ctx->n_pods), st));
-    CU(cudaMemsetAsync(ctx->d_mv_best.p, 0, 8, st));
-    CU(cudaMemsetAsync(ctx->d_mv_hist.p, 0, 4ull * SMV_NBINS, st));
     if (record) CU(cudaEventRecord(ctx->ev0, st));
-    if (N) simon_moves_pack<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->T, ctx->d_alloc_mcpu.p, ctx->d_alloc_mem.p, ctx->d_alloc_eph.p, ctx->d_alloc_pods.p,
-                                                            ctx->d_topo_dom.p, ctx->st.req_mcpu.p, ctx->st.req_mem.p, ctx->st.req_eph.p,
-                                                            ctx->st.nz_mcpu.p, ctx->st.nz_mem.p, ctx->st.num_pods.p, ctx->d_mv_nodes.p);
+    simon_moves_pack<<<std::max(1u, (N + 255) / 256), 256, 0, st>>>(N, ctx->T, ctx->d_alloc_mcpu.p, ctx->d_alloc_mem.p, ctx->d_alloc_eph.p, ctx->d_alloc_pods.p,
+                                                                     ctx->d_topo_dom.p, ctx->st.req_mcpu.p, ctx->st.req_mem.p, ctx->st.req_eph.p,
+                                                                     ctx->st.nz_mcpu.p, ctx->st.nz_mem.p, ctx->st.num_pods.p, ctx->d_mv_nodes.p,
+                                                                     ctx->d_mv_best_pod.p, ctx->n_pods, ctx->d_mv_best.p, ctx->d_mv_hist.p);
     SmvParams P;
     memset(&P, 0, sizeof(P));
     P.N = N; P.K = ctx->K; P.WT = ctx->WT; P.T = ctx->T; P.n_pods = ctx->n_pods; P.n_moves = n; P.use_scache = ctx->use_scache;

@@ -72,7 +72,14 @@ struct SmvParams {
 
 __global__ void simon_moves_pack(uint32_t N, uint32_t T, const int64_t *alloc_mcpu, const int64_t *alloc_mem, const int64_t *alloc_eph,
                                  const int32_t *alloc_pods, const int32_t *topo_dom, const int64_t *req_mcpu, const int64_t *req_mem,
-                                 const int64_t *req_eph, const int64_t *nz_mcpu, const int64_t *nz_mem, const int32_t *num_pods, SmvNode *out) {
+                                 const int64_t *req_eph, const int64_t *nz_mcpu, const int64_t *nz_mem, const int32_t *num_pods, SmvNode *out,
+                                 unsigned long long *best_per_pod, uint32_t n_pods, unsigned long long *best_global, uint32_t *hist) {
+    // the per-launch outputs are cleared here too (one launch instead of three memsets + a kernel)
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pods; q += gridDim.x * blockDim.x) best_per_pod[q] = 0ull;
+    if (blockIdx.x == 0) {
+        for (uint32_t q = threadIdx.x; q < SMV_NBINS; q += blockDim.x) hist[q] = 0u;
+        if (threadIdx.x == 0) *best_global = 0ull;
+    }
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     SmvNode r;
