@@ -18,6 +18,8 @@
 // Compile-time options of the class switch (measured one by one, profiles/r02_kernel_variants.txt):
 //   bit 0  the entry table (int32 rows), the compact commit list and its counter bases come precomputed from the upload
 //          (SkParams::cls_aux) instead of being transposed / compacted by every CTA at every class switch
+//   bit 2  the class switch relies on the release / acquire semantics of barrier.cluster.arrive / .wait instead of a
+//          device-wide __threadfence() before the arrive
 //   bit 1  the log weights of the spread score come from two shared-memory windows of the log table (sizes 0..63 and 64 sizes
 //          around the class's hostname-topology size) instead of a dependent global load at every class switch / size change
 #ifndef SIMON_OPT
@@ -512,7 +514,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             // the previous commits' counter updates (owner-thread atomics) must be visible before the counters are read:
             // release here, acquire (barrier_wait) only where the first counter is loaded, so that the class blob, entry
             // table and summary record loads overlap the barrier latency
-            __threadfence();
+            // (SIMON_OPT bit 2: no separate fence - barrier.cluster.arrive is a release and .wait an acquire at cluster scope,
+            //  and every reader of the counters is a thread of this cluster)
+            if (!(SIMON_OPT & 4)) __threadfence();
             cluster.barrier_arrive();
             __syncthreads();          // every thread of this CTA is done with the previous class's blob and entry table
             TICK(11);
