@@ -457,7 +457,14 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     cnt_off[p->n_counters] = tot;
     ctx->cnt_words = tot;
     const uint64_t blob_words = p->class_off[p->n_classes];
-    CU(ctx->d_class_off.upload(p->class_off, p->n_classes + 1, st)); CU(ctx->d_class_blob.upload(p->class_blob, blob_words, st));
+    CU(ctx->d_class_off.upload(p->class_off, p->n_classes + 1, st));
+    {
+        // the kernel copies max_blob_words words per class switch regardless of the record's own length: pad the tail
+        std::vector<int64_t> padded(blob_words + max_words, 0);
+        if (blob_words) memcpy(padded.data(), p->class_blob, 8ull * blob_words);
+        CU(ctx->d_class_blob.upload(padded.data(), padded.size(), st));
+        CU(cudaStreamSynchronize(st));
+    }
     CU(ctx->d_pod_class.upload(p->pod_class, p->n_pods, st)); CU(ctx->d_pod_fixed.upload(p->pod_fixed_node, p->n_pods, st));
     CU(ctx->d_pod_guard.upload(guard.data(), p->n_pods, st)); CU(ctx->d_cnt_off.upload(cnt_off.data(), cnt_off.size(), st));
     CU(ctx->d_simon_raw.upload(p->simon_raw, (size_t)std::max(1u, p->n_static_rows) * ctx->NC, st));

@@ -20,10 +20,14 @@
 //          (SkParams::cls_aux) instead of being transposed / compacted by every CTA at every class switch
 //   bit 2  the class switch relies on the release / acquire semantics of barrier.cluster.arrive / .wait instead of a
 //          device-wide __threadfence() before the arrive
-//   bit 1  the log weights of the spread score come from two shared-memory windows of the log table (sizes 0..63 and 64 sizes
-//          around the class's hostname-topology size) instead of a dependent global load at every class switch / size change
+//   bit 1  (removed) log weights from shared-memory windows of the log table: measured 1.7 % slower
+//   bit 3  truncations whose argument is provably in range are plain casts (no Go out-of-range emulation)
+//   bit 4  with bit 0: one __syncthreads less in the class switch (nothing is transposed after the header is parsed)
+//   bit 5  the class record's offset is fetched one pod ahead and its length taken as the largest record's (no dependent
+//          global loads at the head of the class switch)
+//   bit 6  the per-node integer divisions of the totals pass by float-reciprocal estimate + exact fix-up
 #ifndef SIMON_OPT
-#define SIMON_OPT 1      // measured on C3: 0 -> 141.4k, 1 -> 141.8k, 2 -> 139.0k, 3 -> 138.7k decisions/s
+#define SIMON_OPT 5      // measured on C3 (profiles/r02_kernel_variants.txt): 0 -> 141.4k, 1 -> 141.8k, 5 -> 144.0k decisions/s
 #endif
 
 // ---- small helpers --------------------------------------------------------------------------------------
@@ -366,7 +370,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 double sfc = (double)VAL(e, idx) * S.soft_w[js] + (double)(ENT(ER_A, e) - 1);
                 score = score + sfc;
             }
-            int64_t raw = f2i(score);
+            int64_t raw = (SIMON_OPT & 8) ? (int64_t)score : f2i(score);      // 0 <= score < 2^40: counts x ln(size) + skews
             A32(B_RAW_PTS, idx) = (int32_t)raw;
             unsigned long long er = sk_enc(raw);
             lo = er < lo ? er : lo;
@@ -377,27 +381,16 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     int32_t psz[SK_MAX_SOFT];      // topology sizes the current weights were computed from (registers: static indexing only)
 #pragma unroll
     for (int q = 0; q < SK_MAX_SOFT; q++) psz[q] = 0;
-    uint32_t lw_base = 0xffffffffu;     // first table index held by the second log window (0xffffffff: not loaded)
     auto set_weights = [&]() {
 #pragma unroll
         for (int js = 0; js < SK_MAX_SOFT; js++)
-            if ((uint32_t)js < C.n_soft) {
-                const uint32_t ti = (uint32_t)psz[js] + 2u;
-                double w;
-                if ((SIMON_OPT & 2) && ti < SK_LOGW) w = S.logw[ti];
-                else if ((SIMON_OPT & 2) && ti - lw_base < SK_LOGW) w = S.logw[SK_LOGW + ti - lw_base];
-                else w = __ldg(&P.log_table[ti]);
-                S.soft_w[js] = w;
-            }
+            if ((uint32_t)js < C.n_soft) S.soft_w[js] = __ldg(&P.log_table[psz[js] + 2]);
     };
-    if (SIMON_OPT & 2) {
-        if (tid < SK_LOGW) S.logw[tid] = tid < P.n_log ? __ldg(&P.log_table[tid]) : 0.0;
-        __syncthreads();
-    }
 
     const uint32_t end = P.first + P.count;
     uint32_t i = P.first;
     int32_t nx_cls = P.pod_class[i], nx_fixed = P.pod_fixed[i], nx_guard = P.pod_guard[i];
+    uint64_t nx_off = (SIMON_OPT & 32) ? P.class_off[nx_cls] : 0;
     // static-normalised part of the total (NodeAffinity + TaintToleration + 2 x Simon + extra) under the current normalisers
     auto snorm_pass = [&]() {
         const int64_t range = C.simon_max - C.simon_min;
@@ -419,8 +412,12 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     };
     while (i < end) {
         const int32_t cls = nx_cls, fixed = nx_fixed;
+        const uint64_t cls_off = nx_off;
         const int64_t guard = nx_guard;
-        if (i + 1 < end) { nx_cls = P.pod_class[i + 1]; nx_fixed = P.pod_fixed[i + 1]; nx_guard = P.pod_guard[i + 1]; }
+        if (i + 1 < end) {
+            nx_cls = P.pod_class[i + 1]; nx_fixed = P.pod_fixed[i + 1]; nx_guard = P.pod_guard[i + 1];
+            if (SIMON_OPT & 32) nx_off = P.class_off[nx_cls];
+        }
         bool exists = true;
         if (guard == -2) exists = false;
         else if (guard >= 0) exists = SC.rank_of ? (SC.rank_of[guard] >= 0) : true;
@@ -477,7 +474,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             cur_class = -1;
             TICK(1);
             i = j;
-            if (i < end) { nx_cls = P.pod_class[i]; nx_fixed = P.pod_fixed[i]; nx_guard = P.pod_guard[i]; }
+            if (i < end) { nx_cls = P.pod_class[i]; nx_fixed = P.pod_fixed[i]; nx_guard = P.pod_guard[i]; if (SIMON_OPT & 32) nx_off = P.class_off[nx_cls]; }
             continue;
         }
 
@@ -520,8 +517,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             cluster.barrier_arrive();
             __syncthreads();          // every thread of this CTA is done with the previous class's blob and entry table
             TICK(11);
-            const int64_t *gw = P.class_blob + P.class_off[cls];
-            const uint32_t words = (uint32_t)(P.class_off[cls + 1] - P.class_off[cls]);
+            // (bit 5: the record's offset came with the pod one iteration ago; copying the largest record's length instead of this
+            //  one's reads into the next record - the upload pads the blob - and saves the dependent loads of the exact length)
+            const int64_t *gw = P.class_blob + ((SIMON_OPT & 32) ? cls_off : P.class_off[cls]);
+            const uint32_t words = (SIMON_OPT & 32) ? P.max_blob_words : (uint32_t)(P.class_off[cls + 1] - P.class_off[cls]);
             #pragma unroll 1
             for (uint32_t w = tid; w < words; w += TPB) S.blob[w] = gw[w];
             // prediction of the topology sizes from the previous visit of this class (any value is safe: verified)
@@ -569,25 +568,13 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 long long v = pred[1 + js];
                 psz[js] = (C.have_pred && v >= 0 && v + 2 < (long long)P.n_log) ? (int32_t)v : 0;
             }
-            if (SIMON_OPT & 2) {
-                // log-weight window around the largest predicted topology size (the hostname topology: ~ number of feasible nodes)
-                int32_t mx = 0;
-#pragma unroll
-                for (int js = 0; js < SK_MAX_SOFT; js++) mx = psz[js] > mx ? psz[js] : mx;
-                const uint32_t ti = (uint32_t)mx + 2u;                          // table index of the largest size
-                // keep ti inside [base + 8, base + 60): sizes shrink (nodes fill up, winners leave) far more often than they grow
-                if (lw_base == 0xffffffffu || ti < lw_base + 8u || ti >= lw_base + 60u) {
-                    lw_base = ti > 44u ? ti - 44u : 0u;
-                    if (tid < SK_LOGW) S.logw[SK_LOGW + tid] = lw_base + tid < P.n_log ? __ldg(&P.log_table[lw_base + tid]) : 0.0;
-                }
-            }
             if (!(SIMON_OPT & 1)) {
                 // the entry table was laid out by the snapshot compiler (SCW_OFF_ENT): 8 words per entry -> 8 rows in smem
                 const int64_t *et = cw + cw[SCW_OFF_ENT];
 #pragma unroll 1
                 for (uint32_t w = tid; w < C.E * 8; w += TPB) S.ent[(w & 7) * SK_MAX_ENT + (w >> 3)] = (int32_t)et[w];
             }
-            __syncthreads();
+            if (!((SIMON_OPT & 1) && (SIMON_OPT & 16))) __syncthreads();
             if (!(SIMON_OPT & 1) && tid < 32) {
                 // compact list of the entries this class increments on commit: entry | topology row << 8 | flags << 16
                 // (lane e looks at entry e; SK_MAX_ENT == 32)
@@ -1066,6 +1053,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         unsigned long long best = 0;
         const int64_t ipa_diff = ipa_max - ipa_min;
         const bool pts32 = pts_max > 0 && pts_max < (1 << 23) && pts_min >= 0;
+        const float pts_rinv = pts32 ? 1.0f / (float)pts_max : 0.0f;
         #pragma unroll (NPT_T > 0 ? NPT_T : 1)
         for (uint32_t s = 0; s < NPT; s++) {
             uint32_t idx = s * TPB + tid;
@@ -1077,10 +1065,23 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                 if (C.n_soft == 0) pts = 100;
                 else if (nf & NF_IGNORED) pts = 0;
                 else if (pts_max == 0) pts = 100;
-                else if (pts32) pts = (int64_t)((uint32_t)(100 * (uint32_t)(pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / (uint32_t)pts_max);
+                else if (pts32) {
+                    const uint32_t x = 100u * (uint32_t)(pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx)), d = (uint32_t)pts_max;
+                    if (SIMON_OPT & 64) {
+                        // x < 2^31, quotient <= 200: the float estimate is off by < 1, one fix-up step makes it exact
+                        uint32_t q = (uint32_t)((float)x * pts_rinv);
+                        const int32_t r = (int32_t)(x - q * d);
+                        if (r < 0) q--;
+                        else if ((uint32_t)r >= d) q++;
+                        pts = (int64_t)q;
+                    } else pts = (int64_t)(x / d);
+                }
                 else pts = (100 * (pts_max + pts_min - (int64_t)A32(B_RAW_PTS, idx))) / pts_max;
                 int64_t ip = 0;
-                if (C.n_isc && ipa_diff > 0) ip = f2i(100.0 * ((double)((int64_t)A32(B_RAW_IPA, idx) - ipa_min) / (double)ipa_diff));
+                if (C.n_isc && ipa_diff > 0) {
+                    const double fr = 100.0 * ((double)((int64_t)A32(B_RAW_IPA, idx) - ipa_min) / (double)ipa_diff);    // in [0, 100]
+                    ip = (SIMON_OPT & 8) ? (int64_t)fr : f2i(fr);
+                }
                 total = (int64_t)A32(B_OWN, idx) + (int64_t)A32(B_SNORM, idx) + ip + 2 * pts;
             }
             if (!PROF && i == P.dump_pod && P.dump_total) P.dump_total[(uint32_t)A32(B_NODE_G, idx)] = total;

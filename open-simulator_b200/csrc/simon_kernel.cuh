@@ -30,7 +30,6 @@ namespace cg = cooperative_groups;
                               //   [33..64] counter bases of the commit list, pad, [68..323] entry table as int32 rows [ER_ROWS][SK_MAX_ENT]
 #define SK_AUX_INCB 33
 #define SK_AUX_ENT 68
-#define SK_LOGW 64            // entries of each of the two log-weight windows kept in shared memory
 #define SK_CSUM_W 26          // valid, 8 sizes, 6 summary scalars, last winner: rank, ignored, 8 domains (+1 spare)
 
 enum { EK_PORT = 0, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE };
@@ -130,7 +129,6 @@ struct SkSmem {
     int32_t *lastdom;    // [SIMON_MAX_TOPOS] topology domains of the last winner (single-node flip fast path)
     uint32_t *incb;      // [32] counter base offsets (cnt_off) of the first 32 entries of the class's commit list
     double *soft_w;      // [SK_MAX_SOFT] log weights of the current class's soft constraints (uniform)
-    double *logw;        // [2][SK_LOGW] windows of the log table: sizes 0..63, and 64 sizes around the current hostname-topology size
     SkScenario *scen;    // this cluster's scenario descriptor
     unsigned long long *mbar;    // [2] mbarriers guarding the two inbox buffers
     uint32_t L, T, nslots;
@@ -145,7 +143,7 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
     b += sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(4ull * (SK_MAX_ENT + 1)) + sk_align(4ull * 32) + sk_align(4ull * SIMON_MAX_TOPOS) + sk_align(8ull * SK_CSUM_W);
-    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(8ull * 2 * SK_LOGW) + sk_align(sizeof(SkScenario));
+    b += sk_align(8ull * SK_MAX_SOFT) + sk_align(sizeof(SkScenario));
     b += sk_align(8ull * 2);
     return b + 64;
 }
@@ -165,7 +163,6 @@ __device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint
     S.lastdom = (int32_t *)p; p += sk_align(4ull * SIMON_MAX_TOPOS);
     S.pred = (long long *)p; p += sk_align(8ull * SK_CSUM_W);
     S.soft_w = (double *)p; p += sk_align(8ull * SK_MAX_SOFT);
-    S.logw = (double *)p; p += sk_align(8ull * 2 * SK_LOGW);
     S.scen = (SkScenario *)p; p += sk_align(sizeof(SkScenario));
     S.mbar = (unsigned long long *)p;
     S.L = L; S.T = T; S.nslots = nslots;
