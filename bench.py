@@ -528,6 +528,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * P + 8),
                         "path": "simon_snapshot_upload + simon_pods_upload + simon_schedule(host out_node), wall clock; the host-side snapshot "
                                 "compile (host_compile_s) happens once per cluster and is reported separately"},
+                "e2e_api": {"value": D / (host_s + float(te.item()) / len(e2e_times)), "unit": "decisions/s",
+                            "path": "objects in -> placements out: simulator.plan (workload expansion + queue sorts) + compile_cluster (snapshot "
+                                    "compiler, Python) + the e2e C-ABI calls; host_compile_s + one e2e pass, per GPU"},
                 "gpu_launches": int(launches), "clocks": clocks, "decisions_per_step": D, "prebound_pods_per_step": P - D, "placed": placed,
                 "unschedulable": int((out_node == -1).sum()), "wall_s_timed_region": wall, "host_compile_s": host_s,
                 "kernel_stats": {k: stats[k] for k in ("class_switches", "summary_rebuilds", "redone", "single_flip_fast", "merged_decisions", "merged_redone")}}

@@ -27,7 +27,7 @@
 //          global loads at the head of the class switch)
 //   bit 6  the per-node integer divisions of the totals pass by float-reciprocal estimate + exact fix-up
 #ifndef SIMON_OPT
-#define SIMON_OPT 5      // measured on C3 (profiles/r02_kernel_variants.txt): 0 -> 141.4k, 1 -> 141.8k, 5 -> 144.0k decisions/s
+#define SIMON_OPT 125    // measured on C3 (profiles/r02_kernel_variants.txt): 0 -> 141.4k, 1 -> 141.8k, 5 -> 144.2k, 125 -> 145.8k decisions/s
 #endif
 
 // ---- small helpers --------------------------------------------------------------------------------------
