@@ -249,7 +249,7 @@ def block_batch(args, c, D, P, placed, local, flush, torch):
     best = None
     tried = []
     act = np.arange(int(c.n_nodes), dtype=np.uint32)
-    for cs, tpb, nb in ((16, 320, 7), (8, 320, 14), (8, 320, 16)):
+    for cs, tpb, nb in ((16, 320, 7), (8, 320, 14), (0, 0, 14), (8, 320, 16)):      # (0, 0): the engine's own choice for a batch
         try:
             with Engine(c, device=local, cluster_ctas=cs, threads_per_cta=tpb) as eng:
                 eng.run_scenarios([act] * nb)                                   # warm-up

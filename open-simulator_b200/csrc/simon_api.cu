@@ -256,15 +256,37 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
     const uint32_t cs_opts[5] = {16, 8, 4, 2, 1};
     const uint32_t want_cs = ctx->opt_cluster, want_t = ctx->opt_threads;
     if (n_active == 0) n_active = 1;
+    if (n_scen > 1 && !want_cs && !want_t) {
+        // Batches are throughput work: small clusters waste the least on synchronisation (C4, 256 scenarios of ~2,000 nodes:
+        // 2 CTAs x 256 threads 147 ms, 4 x 256 207 ms, 8 x 256 368 ms; C3, 10,000 nodes: 14 x 8 CTAs beat 7 x 16).  Take the
+        // smallest cluster that fits shared memory while the batch still fills about half of the SMs; a batch too small for
+        // that gets the largest cluster with which it still runs in one wave.
+        uint32_t fit_cs[5], fit_t[5], fit_npt[5], nfit = 0;
+        size_t fit_smem[5];
+        for (uint32_t cs = 1; cs <= 16; cs *= 2) {
+            const uint32_t per_cta = (n_active + cs - 1) / cs;
+            uint32_t t = per_cta >= 256 ? 256u : std::max(64u, ((per_cta + 31) / 32) * 32);
+            const uint32_t npt = (per_cta + t - 1) / t;
+            const size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs);
+            if (npt <= 64 && b <= (size_t)max_smem) { fit_cs[nfit] = cs; fit_t[nfit] = t; fit_npt[nfit] = npt; fit_smem[nfit] = b; nfit++; }
+        }
+        if (nfit) {
+            int pick = -1;
+            for (uint32_t q = 0; q < nfit && pick < 0; q++)
+                if ((uint64_t)n_scen * fit_cs[q] >= 74) pick = (int)q;
+            if (pick < 0) {
+                pick = 0;
+                for (uint32_t q = 0; q < nfit; q++)
+                    if ((uint64_t)n_scen * fit_cs[q] <= 148) pick = (int)q;
+            }
+            CS = fit_cs[pick]; TPB = fit_t[pick]; NPT = fit_npt[pick]; smem = fit_smem[pick];
+            return SIMON_OK;
+        }
+    }
     for (uint32_t ci = 0; ci < 5; ci++) {
         uint32_t cs = cs_opts[ci];
         if (want_cs) { if (cs != want_cs) continue; }
-        else if (cs > 1 && (uint64_t)(cs / 2) * 256 * 3 >= n_active) {
-            // smallest cluster with <= 3 nodes/thread at 256 threads ... unless the batch is so small that larger clusters
-            // (fewer nodes per thread -> shorter decisions) still all run at once: one CTA per SM, 7 clusters of 16 / 14 of 8
-            const uint32_t fit = cs == 16 ? 7u : cs == 8 ? 14u : cs == 4 ? 32u : cs == 2 ? 70u : 148u;
-            if (n_scen < 2 || n_scen > fit || (uint64_t)(cs / 2) * 64 >= n_active) continue;
-        }
+        else if (cs > 1 && (uint64_t)(cs / 2) * 256 * 3 >= n_active) continue;   // smallest cluster with <= 3 nodes/thread at 256 threads
         for (uint32_t npt = 1; npt <= 64; npt++) {
             uint32_t t;
             if (want_t) {
