@@ -266,6 +266,7 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
         for (uint32_t cs = 1; cs <= 16; cs *= 2) {
             const uint32_t per_cta = (n_active + cs - 1) / cs;
             uint32_t t = per_cta >= 256 ? 256u : std::max(64u, ((per_cta + 31) / 32) * 32);
+            if (per_cta > 256 && (per_cta + 319) / 320 < (per_cta + 255) / 256) t = 320;      // fewer nodes per thread wins (C3: 8 x 320 x 4)
             const uint32_t npt = (per_cta + t - 1) / t;
             const size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs);
             if (npt <= 64 && b <= (size_t)max_smem) { fit_cs[nfit] = cs; fit_t[nfit] = t; fit_npt[nfit] = npt; fit_smem[nfit] = b; nfit++; }
