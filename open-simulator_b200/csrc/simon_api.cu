@@ -319,8 +319,8 @@ int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t T
     // carry no timers
     static const bool prof = getenv("SIMON_PROFILE") != nullptr;
     if (TPB > 256) {
-        if (prof) fn = npt == 1 ? simon_prof_kernel_320_1 : npt == 2 ? simon_prof_kernel_320_2 : simon_prof_kernel_320_0;
-        else fn = npt == 1 ? simon_place_kernel_320_1 : npt == 2 ? simon_place_kernel_320_2 : simon_place_kernel_320_0;
+        if (prof) fn = npt == 1 ? simon_prof_kernel_320_1 : npt == 2 ? simon_prof_kernel_320_2 : npt == 3 ? simon_prof_kernel_320_3 : npt == 4 ? simon_prof_kernel_320_4 : simon_prof_kernel_320_0;
+        else fn = npt == 1 ? simon_place_kernel_320_1 : npt == 2 ? simon_place_kernel_320_2 : npt == 3 ? simon_place_kernel_320_3 : npt == 4 ? simon_place_kernel_320_4 : simon_place_kernel_320_0;
     } else if (prof) fn = npt == 1 ? simon_prof_kernel_256_1 : npt == 2 ? simon_prof_kernel_256_2 : npt == 3 ? simon_prof_kernel_256_3 : npt == 4 ? simon_prof_kernel_256_4 : simon_prof_kernel_256_0;
     else fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

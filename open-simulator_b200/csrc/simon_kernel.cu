@@ -1298,3 +1298,5 @@ SIMON_KERNEL(256, 4)
 SIMON_KERNEL(320, 0)
 SIMON_KERNEL(320, 1)
 SIMON_KERNEL(320, 2)
+SIMON_KERNEL(320, 3)
+SIMON_KERNEL(320, 4)
