@@ -143,6 +143,9 @@ struct simon_ctx {
     DevBuf<SmvClass> d_mv_classes;
     uint32_t mv_n = 0, mv_base = 0;
     std::vector<uint8_t> bypass;        // per pod: never reaches the scheduler in a single-scenario run (pre-bound or absent)
+    DevBuf<unsigned char> d_gnode;      // large-cluster variant: per-node arrays in global memory
+    bool big = false;                   // set by choose_geometry for the next launch
+    size_t gnode_stride = 0;
     DevBuf<uint32_t> d_sig_class;       // a class per static signature (dense fill of the static verdict cache)
     bool static_filled = false;
     // single-scenario state
@@ -256,6 +259,7 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
     const uint32_t cs_opts[5] = {16, 8, 4, 2, 1};
     const uint32_t want_cs = ctx->opt_cluster, want_t = ctx->opt_threads;
     if (n_active == 0) n_active = 1;
+    ctx->big = false;
     if (n_scen > 1 && !want_cs && !want_t) {
         // Batches are throughput work: small clusters waste the least on synchronisation (C4, 256 scenarios of ~2,000 nodes:
         // 2 CTAs x 256 threads 147 ms, 4 x 256 207 ms, 8 x 256 368 ms; C3, 10,000 nodes: 14 x 8 CTAs beat 7 x 16).  Take the
@@ -305,7 +309,20 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
             if (want_t) break;
         }
     }
-    return fail(ctx, SIMON_ERR_LIMIT, "cluster of %u nodes does not fit the shared memory of one 16-CTA cluster", n_active);
+    // Large-cluster variant: 16 CTAs x 320 threads, as many node slots per thread as needed (<= 64: the commit fold tracks
+    // a thread's slots in one 64-bit mask), the per-node arrays in global memory.
+    if (!want_cs && !want_t) {
+        const uint32_t cs = 16, t = 320;
+        const uint32_t npt = (n_active + cs * t - 1) / (cs * t);
+        const size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs, false);
+        if (npt <= 64 && b <= (size_t)max_smem) {
+            CS = cs; TPB = t; NPT = npt; smem = b;
+            ctx->big = true;
+            ctx->gnode_stride = (sk_node_bytes(npt * t, ctx->T, ctx->emax) + 255) & ~(size_t)255;
+            return SIMON_OK;
+        }
+    }
+    return fail(ctx, SIMON_ERR_LIMIT, "cluster of %u nodes exceeds the engine limit (16 CTAs x 320 threads x 64 node slots)", n_active);
 }
 
 typedef void (*sk_kernel_fn)(const SkParams);
@@ -318,7 +335,11 @@ int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t T
     // SIMON_PROFILE=1 selects the variants with per-phase clock64 timers (simon_stats cycles); the default variants
     // carry no timers
     static const bool prof = getenv("SIMON_PROFILE") != nullptr;
-    if (TPB > 256) {
+    if (ctx->big) {
+        CU(ctx->d_gnode.alloc(ctx->gnode_stride * (size_t)n_scen * CS));
+        P.gnode = ctx->d_gnode.p; P.gnode_stride = ctx->gnode_stride;
+        fn = simon_place_kernel_big;
+    } else if (TPB > 256) {
         if (prof) fn = npt == 1 ? simon_prof_kernel_320_1 : npt == 2 ? simon_prof_kernel_320_2 : npt == 3 ? simon_prof_kernel_320_3 : npt == 4 ? simon_prof_kernel_320_4 : simon_prof_kernel_320_0;
         else fn = npt == 1 ? simon_place_kernel_320_1 : npt == 2 ? simon_place_kernel_320_2 : npt == 3 ? simon_place_kernel_320_3 : npt == 4 ? simon_place_kernel_320_4 : simon_place_kernel_320_0;
     } else if (prof) fn = npt == 1 ? simon_prof_kernel_256_1 : npt == 2 ? simon_prof_kernel_256_2 : npt == 3 ? simon_prof_kernel_256_3 : npt == 4 ? simon_prof_kernel_256_4 : simon_prof_kernel_256_0;

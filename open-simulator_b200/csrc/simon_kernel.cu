@@ -162,7 +162,7 @@ struct ClassState {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-template <int MAXT, int NPT_T, bool PROF>
+template <int MAXT, int NPT_T, bool PROF, bool BIG = false>
 __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -176,7 +176,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     const uint32_t N = P.N, T = P.T, K = P.K, WT = P.WT;
 
     SkSmem S;
-    sk_carve(S, smem_raw, L, T, P.emax, P.max_blob_words, CS);
+    // BIG: a scenario too large for the cluster's shared memory keeps its per-node arrays in global memory (one slice per CTA,
+    // touched by this CTA only, so L1 may cache it); everything else - and every line of the algorithm - is unchanged
+    sk_carve(S, smem_raw, L, T, P.emax, P.max_blob_words, CS, BIG ? P.gnode + (size_t)blockIdx.x * P.gnode_stride : nullptr);
     // the scenario descriptor lives in shared memory (kernel-lifetime constant, read after every barrier)
     if (tid < sizeof(SkScenario) / 8) ((unsigned long long *)S.scen)[tid] = ((const unsigned long long *)(P.scen + scen_id))[tid];
     __syncthreads();
@@ -1290,6 +1292,9 @@ extern "C" __global__ void __launch_bounds__(256) simon_import_kernel(const __gr
     extern "C" __global__ void __launch_bounds__(MAXT, 1) simon_prof_kernel_##MAXT##_##NPTT(const __grid_constant__ SkParams P) { \
         simon_place_body<MAXT, NPTT, true>(P);                                                           \
     }
+extern "C" __global__ void __launch_bounds__(320, 1) simon_place_kernel_big(const __grid_constant__ SkParams P) {
+    simon_place_body<320, 0, false, true>(P);
+}
 SIMON_KERNEL(256, 0)
 SIMON_KERNEL(256, 1)
 SIMON_KERNEL(256, 2)

@@ -106,6 +106,8 @@ struct SkParams {
     // static cache: per (static signature, node) verdicts, filled on first use
     uint32_t n_sigs, use_scache;
     uint32_t simon32, pad32;       // simon32: every raw Simon score lies in [0, 2^31) -> reduced as a 32-bit word
+    unsigned char *gnode;          // large-cluster variant: per-node arrays, one slice of gnode_stride bytes per CTA
+    size_t gnode_stride;
     uint32_t dump_pod, pad_d;      // debug: pod index whose per-node totals / filter reasons are written out (0xffffffff: none)
     long long *dump_total;         // [N]
     int32_t *dump_code;            // [N] 0 = feasible, else the reason bitmask
@@ -134,11 +136,14 @@ struct SkSmem {
     uint32_t L, T, nslots;
 };
 
-__host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words, uint32_t nslots) {
+// bytes of the per-node arrays of one CTA (shared memory normally; a slice of SkParams::gnode in the large-cluster variant)
+__host__ __device__ inline size_t sk_node_bytes(uint32_t L, uint32_t T, uint32_t emax) {
+    return sk_align(8ull * A_N64 * L) + sk_align(4ull * (B_N32 + T + emax) * L) + sk_align(1ull * C_N8 * L);
+}
+
+__host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words, uint32_t nslots, bool node_arrays = true) {
     size_t b = 0;
-    b += sk_align(8ull * A_N64 * L);
-    b += sk_align(4ull * (B_N32 + T + emax) * L);
-    b += sk_align(1ull * C_N8 * L);
+    if (node_arrays) b += sk_node_bytes(L, T, emax);
     b += sk_align(8ull * blob_words);
     b += sk_align(8ull * 2 * SK_NV * nslots) + sk_align(8ull * SK_NV * SK_MAX_WARPS);
     b += sk_align(4ull * ER_ROWS * SK_MAX_ENT);
@@ -148,11 +153,16 @@ __host__ __device__ inline size_t sk_smem_bytes(uint32_t L, uint32_t T, uint32_t
     return b + 64;
 }
 
-__device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words, uint32_t nslots) {
+// gnode == nullptr: everything in shared memory.  Otherwise the per-node arrays live in this CTA's slice of global memory
+// (large-cluster variant: the same code, the node state served by L1 / L2 instead of shared memory).
+__device__ inline void sk_carve(SkSmem &S, unsigned char *base, uint32_t L, uint32_t T, uint32_t emax, uint32_t blob_words, uint32_t nslots,
+                                unsigned char *gnode = nullptr) {
     unsigned char *p = base;
-    S.a64 = (int64_t *)p; p += sk_align(8ull * A_N64 * L);
-    S.a32 = (int32_t *)p; p += sk_align(4ull * (B_N32 + T + emax) * L);
-    S.a8 = (uint8_t *)p; p += sk_align(1ull * C_N8 * L);
+    unsigned char *q = gnode ? gnode : p;
+    S.a64 = (int64_t *)q; q += sk_align(8ull * A_N64 * L);
+    S.a32 = (int32_t *)q; q += sk_align(4ull * (B_N32 + T + emax) * L);
+    S.a8 = (uint8_t *)q; q += sk_align(1ull * C_N8 * L);
+    if (!gnode) p = q;
     S.blob = (int64_t *)p; p += sk_align(8ull * blob_words);
     S.box = (unsigned long long *)p; p += sk_align(8ull * 2 * SK_NV * nslots);
     S.wpart = (unsigned long long *)p; p += sk_align(8ull * SK_NV * SK_MAX_WARPS);
