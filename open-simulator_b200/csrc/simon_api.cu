@@ -141,6 +141,7 @@ struct simon_ctx {
     DevBuf<uint2> d_mv_topk;
     DevBuf<SmvNode> d_mv_nodes;
     DevBuf<SmvClass> d_mv_classes;
+    DevBuf<SmvPod> d_mv_pods;
     uint32_t mv_n = 0, mv_base = 0;
     std::vector<uint8_t> bypass;        // per pod: never reaches the scheduler in a single-scenario run (pre-bound or absent)
     DevBuf<unsigned char> d_gnode;      // large-cluster variant: per-node arrays in global memory
@@ -862,15 +863,17 @@ static int moves_launch(simon_ctx *ctx, bool record) {
     cudaStream_t st = ctx->stream;
     const uint32_t N = ctx->N, n = ctx->mv_n;
     if (record) CU(cudaEventRecord(ctx->ev0, st));
-    simon_moves_pack<<<std::max(1u, (N + 255) / 256), 256, 0, st>>>(N, ctx->T, ctx->d_alloc_mcpu.p, ctx->d_alloc_mem.p, ctx->d_alloc_eph.p, ctx->d_alloc_pods.p,
+    simon_moves_pack<<<std::max(std::max(1u, (N + 255) / 256), std::min(1184u, (ctx->n_pods + 255) / 256)), 256, 0, st>>>(N, ctx->T, ctx->d_alloc_mcpu.p, ctx->d_alloc_mem.p, ctx->d_alloc_eph.p, ctx->d_alloc_pods.p,
                                                                      ctx->d_topo_dom.p, ctx->st.req_mcpu.p, ctx->st.req_mem.p, ctx->st.req_eph.p,
                                                                      ctx->st.nz_mcpu.p, ctx->st.nz_mem.p, ctx->st.num_pods.p, ctx->d_mv_nodes.p,
-                                                                     ctx->d_mv_best_pod.p, ctx->n_pods, ctx->d_mv_best.p, ctx->d_mv_hist.p);
+                                                                     ctx->d_mv_best_pod.p, ctx->n_pods, ctx->d_mv_best.p, ctx->d_mv_hist.p,
+                                                                     ctx->d_pod_class.p, ctx->st.out_node.p, ctx->d_mv_classes.p, ctx->d_mv_pods.p);
     SmvParams P;
     memset(&P, 0, sizeof(P));
     P.N = N; P.K = ctx->K; P.WT = ctx->WT; P.T = ctx->T; P.n_pods = ctx->n_pods; P.n_moves = n; P.use_scache = ctx->use_scache;
     P.nodes = ctx->d_mv_nodes.p; P.alloc_scalar = ctx->d_alloc_scalar.p; P.req_scalar = ctx->st.req_scalar.p; P.node_flags = ctx->d_node_flags.p;
     P.label_bits = ctx->d_label_bits.p; P.taint_hard = ctx->d_taint_hard.p; P.topo_dom = ctx->d_topo_dom.p;
+    P.pods = ctx->d_mv_pods.p;
     P.class_off = ctx->d_class_off.p; P.class_blob = ctx->d_class_blob.p; P.classes = ctx->d_mv_classes.p; P.pod_class = ctx->d_pod_class.p; P.placement = ctx->st.out_node.p;
     P.cnt = ctx->st.cnt.p; P.cnt_total = ctx->st.cnt_total.p; P.scache = ctx->d_scache.p; P.moves = ctx->d_moves.p;
     P.out_gain = ctx->d_mv_gain.p; P.out_code = ctx->d_mv_code.p; P.best_per_pod = ctx->d_mv_best_pod.p; P.best_global = ctx->d_mv_best.p;
@@ -899,6 +902,7 @@ int simon_moves_upload(simon_ctx *ctx, const simon_move *moves, uint32_t n_moves
     CU(ctx->d_moves.upload(reinterpret_cast<const uint2 *>(moves), n_moves, ctx->stream));
     CU(ctx->d_mv_gain.alloc(n_moves)); CU(ctx->d_mv_code.alloc(n_moves)); CU(ctx->d_mv_hist.alloc(SMV_NBINS)); CU(ctx->d_mv_topn.alloc(2));
     CU(ctx->d_mv_best_pod.alloc(std::max(1u, ctx->n_pods))); CU(ctx->d_mv_best.alloc(1)); CU(ctx->d_mv_nodes.alloc(std::max(1u, ctx->N)));
+    CU(ctx->d_mv_pods.alloc(std::max(1u, ctx->n_pods)));
     ctx->mv_n = n_moves; ctx->mv_base = move_base;
     if (!ctx->static_filled && ctx->use_scache && ctx->N && ctx->n_classes) {
         // once per uploaded pod list: the static verdicts of every (signature, node) pair, densely

@@ -34,6 +34,12 @@ struct __align__(32) SmvClass {
     uint32_t bits;                                       //           flags:8 | not movable:1 | has scalar request:1 | n_ports:5 | n_filter entries (aff+anti+exist):6 | own increments:1
 };
 static_assert(sizeof(SmvClass) == 64, "SmvClass layout");
+// per-pod record built by the pack kernel of every launch: everything a move needs to know about its pod in ONE 16-byte load,
+// so that the class header, the static verdict record and both node records can be fetched in parallel afterwards
+struct __align__(16) SmvPod {
+    int32_t cls, node;      // class, current node (or < 0)
+    uint32_t sig, bits;     // static signature and SmvClass::bits of the class
+};
 #define SMC_NOT_MOVABLE (1u << 8)
 #define SMC_HAS_SCALAR (1u << 9)
 #define SMC_NPORTS(b) (((b) >> 10) & 31u)
@@ -58,6 +64,7 @@ struct SmvParams {
     const uint64_t *class_off;
     const int64_t *class_blob;
     const SmvClass *classes;
+    const SmvPod *pods;
     const int32_t *pod_class, *placement;
     const int32_t *cnt, *cnt_total;
     unsigned long long *scache;
@@ -73,9 +80,16 @@ struct SmvParams {
 __global__ void simon_moves_pack(uint32_t N, uint32_t T, const int64_t *alloc_mcpu, const int64_t *alloc_mem, const int64_t *alloc_eph,
                                  const int32_t *alloc_pods, const int32_t *topo_dom, const int64_t *req_mcpu, const int64_t *req_mem,
                                  const int64_t *req_eph, const int64_t *nz_mcpu, const int64_t *nz_mem, const int32_t *num_pods, SmvNode *out,
-                                 unsigned long long *best_per_pod, uint32_t n_pods, unsigned long long *best_global, uint32_t *hist) {
+                                 unsigned long long *best_per_pod, uint32_t n_pods, unsigned long long *best_global, uint32_t *hist,
+                                 const int32_t *pod_class, const int32_t *placement, const SmvClass *classes, SmvPod *pods) {
     // the per-launch outputs are cleared here too (one launch instead of three memsets + a kernel)
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pods; q += gridDim.x * blockDim.x) best_per_pod[q] = 0ull;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pods; q += gridDim.x * blockDim.x) {
+        best_per_pod[q] = 0ull;
+        const int32_t c = pod_class[q];
+        SmvPod r;
+        r.cls = c; r.node = placement[q]; r.sig = classes[c].sig; r.bits = classes[c].bits;
+        pods[q] = r;
+    }
     if (blockIdx.x == 0) {
         for (uint32_t q = threadIdx.x; q < SMV_NBINS; q += blockDim.x) hist[q] = 0u;
         if (threadIdx.x == 0) *best_global = 0ull;
@@ -162,27 +176,32 @@ __global__ void __launch_bounds__(256, MINB) simon_moves_kernel(const __grid_con
         uint32_t code = SMV_OK;
         int32_t gain = 0;
         int32_t a = -1;
+        SmvPod pr;
+        pr.cls = 0; pr.node = -1; pr.sig = 0; pr.bits = 0;
         if (pod >= P.n_pods || b >= P.N) code = SMV_BAD_INDEX;
         else {
-            a = __ldg(P.placement + pod);
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(P.pods + pod));
+            pr.cls = v.x; pr.node = v.y; pr.sig = (uint32_t)v.z; pr.bits = (uint32_t)v.w;
+            a = pr.node;
             if (a < 0 || (uint32_t)a >= P.N) code = SMV_NOT_PLACED;
             else if ((uint32_t)a == b) code = SMV_NOOP;
+            else if (pr.bits & SMC_NOT_MOVABLE) code = SMV_NOT_MOVABLE;
         }
         if (code == SMV_OK) {
-            const int32_t cls = __ldg(P.pod_class + pod);
+            const int32_t cls = pr.cls;
+            // the four gathers of a move are independent now: class header, static verdict record, target and source node
+            unsigned long long rec = P.use_scache ? __ldcg(P.scache + (uint64_t)pr.sig * P.N + b) : 0ull;
             SmvClass kc;
             smv_ld_sector(&kc, P.classes + cls);
             smv_ld_sector(reinterpret_cast<unsigned long long *>(&kc) + 4, reinterpret_cast<const unsigned long long *>(P.classes + cls) + 4);
             const uint32_t bits = kc.bits, cflags = bits & 0xffu;
-            if (bits & SMC_NOT_MOVABLE) code = SMV_NOT_MOVABLE;
-            else {
+            {
                 const uint32_t n_ports = SMC_NPORTS(bits), n_filt = SMC_NFILT(bits);
                 const bool need_ent = (n_ports | n_filt) != 0;
                 const SmvNode nb = smv_load<7>(P.nodes + b);
                 SmvNode na = smv_load<1>(P.nodes + a);
                 if (need_ent && (bits & SMC_OWN_INC)) smv_load_sector(na, P.nodes + a, 2);       // the source's domains: only to take p's own counts out
                 // ---- static verdict of (class, b): cached per (static signature, node) by the placement kernel, or computed here
-                unsigned long long rec = P.use_scache ? __ldcg(P.scache + (uint64_t)kc.sig * P.N + b) : 0ull;
                 uint32_t st_code;
                 const int64_t *cw = nullptr;
                 if (rec & (1ull << 24)) st_code = (uint32_t)(rec & 0xff);
