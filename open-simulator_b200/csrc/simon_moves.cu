@@ -126,13 +126,15 @@ __device__ __forceinline__ void smv_load_sector(SmvNode &r, const SmvNode *p, in
     smv_ld_sector(reinterpret_cast<unsigned long long *>(&r) + 4 * sec, reinterpret_cast<const unsigned long long *>(p) + 4 * sec);
 }
 
-// exact floor(x / d) for 0 <= x < 2^63, 0 < d, quotient <= 100: one f64 division and an integer fix-up instead of the emulated
-// 64-bit integer division (the estimate is within 1e-13 of the true quotient, so it is off by at most one)
-__device__ __forceinline__ int64_t smv_div100(int64_t x, int64_t d, double dd) {
-    int64_t q = (int64_t)((double)x / dd);
-    const int64_t r = x - q * d;
+// exact floor((cap - rq) * 100 / cap) for 0 <= rq <= cap, from the already computed fraction f = rq / cap (correctly rounded):
+// the estimate (1 - f) * 100 is within 1e-13 of the true quotient, so one integer fix-up step makes it exact - no second
+// division (the emulated 64-bit integer division costs ~100 instructions, an f64 division ~35)
+__device__ __forceinline__ int64_t smv_la(int64_t cap, int64_t rq, double f) {
+    const int64_t x = (cap - rq) * 100;
+    int64_t q = (int64_t)((1.0 - f) * 100.0);
+    const int64_t r = x - q * cap;
     if (r < 0) q--;
-    else if (r >= d) q++;
+    else if (r >= cap) q++;
     return q;
 }
 
@@ -140,12 +142,11 @@ __device__ __forceinline__ int64_t smv_div100(int64_t x, int64_t d, double dd) {
 // (least_allocated.go:93-117, balanced_allocation.go:82-119); same values as the placement kernel's own_core
 __device__ __forceinline__ int32_t smv_own(int64_t capc, int64_t capm, int64_t nzc, int64_t nzm, int64_t sc, int64_t sm) {
     const int64_t rqc = nzc + sc, rqm = nzm + sm;
-    const double dc = (double)capc, dm = (double)capm;
-    const int64_t s1 = (capc == 0 || rqc > capc) ? 0 : smv_div100((capc - rqc) * 100, capc, dc);
-    const int64_t s2 = (capm == 0 || rqm > capm) ? 0 : smv_div100((capm - rqm) * 100, capm, dm);
+    const double cf = capc == 0 ? 1.0 : (double)rqc / (double)capc;
+    const double mf = capm == 0 ? 1.0 : (double)rqm / (double)capm;
+    const int64_t s1 = (capc == 0 || rqc > capc) ? 0 : smv_la(capc, rqc, cf);
+    const int64_t s2 = (capm == 0 || rqm > capm) ? 0 : smv_la(capm, rqm, mf);
     const int64_t la = (s1 + s2) / 2;
-    const double cf = capc == 0 ? 1.0 : (double)rqc / dc;
-    const double mf = capm == 0 ? 1.0 : (double)rqm / dm;
     int64_t ba = 0;
     if (!(cf >= 1.0 || mf >= 1.0)) ba = f2i((1.0 - fabs(cf - mf)) * 100.0);
     return (int32_t)(la + ba);
