@@ -67,12 +67,16 @@ def go_probe() -> str:
 def build_workload(args, seed_no):
     from simon_b200 import simulator, synth
     from simon_b200.compiler import compile_cluster
-    t0 = time.time()
     cluster, apps = synth.make_c3(n_nodes=args.nodes, n_workloads=args.workloads, replicas=args.replicas,
                                   n_apps=10, seed_no=seed_no)
+    # host_compile_s: what Simulate() does on the host between receiving the objects and the first C-ABI call (workload expansion,
+    # queue sorts, snapshot compiler).  Generating the synthetic objects themselves is the caller's input, not part of it.
+    t0 = time.perf_counter()
     p = simulator.plan(cluster, apps)
     c = compile_cluster(p.nodes, p.pods, p.ctx)
-    return p, c, time.time() - t0
+    host_s = time.perf_counter() - t0
+    build_workload.last_objects = (cluster, apps)
+    return p, c, host_s
 
 
 class ClockSampler:
@@ -464,6 +468,25 @@ def main():
         dt = time.perf_counter() - t0
         if step >= 2:
             e2e_times.append(dt)
+    # ---- the public API itself: Simulate(objects) -> SimulateResult, wall clock (plan + compile + engine creation + uploads +
+    #      placement + result objects); one untimed call first (lazy imports), on fresh copies of the objects each time ----
+    api_s = None
+    if not args.no_blocks and rank == 0:
+        from simon_b200 import simulator as _sim
+        from simon_b200.objects import deep_copy as _dc
+        cl0, ap0 = build_workload.last_objects
+        api_times = []
+        for rep in range(3):
+            cl = type(cl0)(**{k: _dc(v) for k, v in vars(cl0).items()})
+            ap = [type(a)(Name=a.Name, Resource=type(a.Resource)(**{k: _dc(v) for k, v in vars(a.Resource).items()})) for a in ap0]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res_api = _sim.Simulate(cl, ap, _sim.WithDevice(local))
+            dt = time.perf_counter() - t0
+            if rep:
+                api_times.append(dt)
+        api_s = min(api_times)
+        api_placed = sum(len(ns.Pods) for ns in res_api.NodeStatus)
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -528,9 +551,11 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * P + 8),
                         "path": "simon_snapshot_upload + simon_pods_upload + simon_schedule(host out_node), wall clock; the host-side snapshot "
                                 "compile (host_compile_s) happens once per cluster and is reported separately"},
-                "e2e_api": {"value": D / (host_s + float(te.item()) / len(e2e_times)), "unit": "decisions/s",
-                            "path": "objects in -> placements out: simulator.plan (workload expansion + queue sorts) + compile_cluster (snapshot "
-                                    "compiler, Python) + the e2e C-ABI calls; host_compile_s + one e2e pass, per GPU"},
+                "e2e_api": {"value": (D / api_s) if api_s else None, "unit": "decisions/s", "simulate_s": api_s,
+                            "estimate_from_parts": D / (host_s + float(te.item()) / len(e2e_times)),
+                            "path": "simulator.Simulate(cluster objects, app objects) -> SimulateResult, wall clock of the call on rank 0, best of 2 "
+                                    "after one untimed call: workload expansion + queue sorts + snapshot compiler (Python, host_compile_s) + "
+                                    "engine creation + uploads + placement + per-node result lists; estimate_from_parts = host_compile_s + one e2e pass"},
                 "gpu_launches": int(launches), "clocks": clocks, "decisions_per_step": D, "prebound_pods_per_step": P - D, "placed": placed,
                 "unschedulable": int((out_node == -1).sum()), "wall_s_timed_region": wall, "host_compile_s": host_s,
                 "kernel_stats": {k: stats[k] for k in ("class_switches", "summary_rebuilds", "redone", "single_flip_fast", "merged_decisions", "merged_redone")}}

@@ -111,7 +111,8 @@ enum simon_class_word {
     SCW_GPU_MEM,        /* pod annotation alibabacloud.com/gpu-mem  open-gpu-share/utils/pod.go:83-98 */
     SCW_GPU_COUNT,
     SCW_FLAGS,          /* SIMON_CLS_* */
-    SCW_NODE_NAME,      /* spec.nodeName: -1 none, >=0 node index, -2 names no node of the cluster */
+    SCW_NODE_NAME,      /* spec.nodeName: -1 none; >=0 node index; -2 names no node of the cluster; -3 set, and the pod is bound to
+                           that node (pod_fixed): NodeName fails on every other node.  The snapshot compiler emits -1 / -3 only */
     SCW_STATIC_ROW,     /* row of simon_raw (>=0) */
     SCW_EXTRA_ROW,      /* row of extra_score or -1 (ImageLocality 0, NodePreferAvoidPods 100) */
     SCW_GUARD_NODE,     /* -1, or the node a DaemonSet pod was generated for: in a scenario where that node is

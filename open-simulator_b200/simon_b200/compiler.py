@@ -22,6 +22,7 @@ Reference semantics restated here (paths relative to the reference tree; K8S = v
 from __future__ import annotations
 
 import json
+import marshal
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -372,10 +373,15 @@ def _class_key(tmpl: PodTemplate) -> str:
         "ic": [[(c.get("resources") or {}).get("requests"), (c.get("resources") or {}).get("limits")]
                for c in (spec.get("initContainers") or [])],
         "ov": spec.get("overhead"), "nsel": spec.get("nodeSelector"), "aff": spec.get("affinity"),
-        "tol": spec.get("tolerations"), "nn": spec.get("nodeName"), "tsc": spec.get("topologySpreadConstraints"),
+        "tol": spec.get("tolerations"), "nn": bool(spec.get("nodeName")), "tsc": spec.get("topologySpreadConstraints"),
         "prio": spec.get("priority"),
     }
-    return json.dumps(keep, sort_keys=True, default=str)
+    # marshal is canonical for equal content built in the same key order (what one template / one YAML producer yields); content
+    # in a different key order merely lands in a second, equivalent class
+    try:
+        return marshal.dumps(keep)
+    except ValueError:
+        return json.dumps(keep, sort_keys=True, default=str)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -410,6 +416,12 @@ class ExtraScorePlugin:
 
 def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterContext] = None,
                     extra_log: int = 0, extra_plugins: Optional[List[ExtraScorePlugin]] = None) -> Compiled:
+    with O.gc_paused():
+        return _compile_cluster(nodes, pods, ctx, extra_log, extra_plugins)
+
+
+def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterContext],
+                     extra_log: int, extra_plugins: Optional[List[ExtraScorePlugin]]) -> Compiled:
     ctx = ctx or ClusterContext()
     order = node_tree_list(nodes)
     snodes = [nodes[i] for i in order]
@@ -422,23 +434,19 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
     key_to_cid: Dict[str, int] = {}
     classes: List[ClassInfo] = []
     tmpl_seen: Dict[int, int] = {}
-    pod_class = np.zeros(len(pods), dtype=np.int32)
-    pod_fixed = np.full(len(pods), -1, dtype=np.int32)
-    for i, rec in enumerate(pods):
-        t = rec.tmpl
-        cid = tmpl_seen.get(id(t))
+    # one pass over the distinct templates (a few hundred for 100,000 pods), then two list comprehensions over the pods
+    for t in {id(r.tmpl): r.tmpl for r in pods}.values():
+        k = _class_key(t)
+        cid = key_to_cid.get(k)
         if cid is None:
-            k = _class_key(t)
-            cid = key_to_cid.get(k)
-            if cid is None:
-                cid = len(classes)
-                key_to_cid[k] = cid
-                classes.append(_parse_class(cid, t))
-            tmpl_seen[id(t)] = cid
-            t.class_id = cid
-        pod_class[i] = cid
-        if rec.node_name:
-            pod_fixed[i] = name_to_idx.get(rec.node_name, -2)
+            cid = len(classes)
+            key_to_cid[k] = cid
+            classes.append(_parse_class(cid, t))
+        tmpl_seen[id(t)] = cid
+        t.class_id = cid
+    pod_class = np.fromiter((r.tmpl.class_id for r in pods), dtype=np.int32, count=len(pods))
+    nget = name_to_idx.get
+    pod_fixed = np.fromiter((nget(r.node_name, -2) if r.node_name else -1 for r in pods), dtype=np.int32, count=len(pods))
     C = len(classes)
     # DefaultPreemption (PL/defaultpreemption/default_preemption.go:91-167) only ever evicts pods of strictly lower priority
     # than the pod that failed to schedule.  Priorities come from spec.priority alone (no admission controller resolves
@@ -467,42 +475,58 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
     node_class = np.zeros(N, np.int32)
     nclass_ids = _Interner()
     nclass_alloc: List[Dict[str, Quantity]] = []
+    # Nodes come in a few resource shapes (instance types): the quantities of one shape are parsed once and the resulting column
+    # values, GPU figures and node class reused for every node with the same allocatable / capacity strings.
+    shape_memo: Dict = {}
     for i, n in enumerate(snodes):
         st = n.get("status") or {}
-        alloc = {str(k): Quantity.parse(v) for k, v in (st.get("allocatable") or {}).items()}
-        for name, q in alloc.items():
-            if name == "cpu":
-                alloc_mcpu[i] += q.milli_value()
-            elif name == "memory":
-                alloc_mem[i] += q.int_value()
-            elif name == "pods":
-                alloc_pods[i] += q.int_value()
-            elif name == "ephemeral-storage":
-                alloc_eph[i] += q.int_value()
-            elif name in scalar_names:
-                alloc_scalar[scalar_names.index(name), i] += q.int_value()
-        # leastRequestedScore computes (capacity - requested) * 100 in int64 (least_allocated.go:108-117): a capacity of
-        # 2^63 / 100 or more overflows in the reference too; refuse rather than reproduce the wrap-around
-        if max(int(alloc_mcpu[i]), int(alloc_mem[i])) >= (1 << 63) // 100:
-            raise CompileError(f"node {O.name_of(n)}: allocatable cpu/memory of 2^63/100 or more")
+        a_items = st.get("allocatable") or {}
+        c_items = st.get("capacity") or {}
+        try:
+            skey = (tuple(a_items.items()), tuple(c_items.items()))
+            shp = shape_memo.get(skey)
+        except TypeError:           # unhashable value (malformed object): no memo
+            skey, shp = None, None
+        if shp is None:
+            alloc = {str(k): Quantity.parse(v) for k, v in a_items.items()}
+            v_mcpu = v_mem = v_eph = v_pods = 0
+            v_scalar = [0] * max(K, 1)
+            for name, q in alloc.items():
+                if name == "cpu":
+                    v_mcpu += q.milli_value()
+                elif name == "memory":
+                    v_mem += q.int_value()
+                elif name == "pods":
+                    v_pods += q.int_value()
+                elif name == "ephemeral-storage":
+                    v_eph += q.int_value()
+                elif name in scalar_names:
+                    v_scalar[scalar_names.index(name)] += q.int_value()
+            # leastRequestedScore computes (capacity - requested) * 100 in int64 (least_allocated.go:108-117): a capacity of
+            # 2^63 / 100 or more overflows in the reference too; refuse rather than reproduce the wrap-around
+            if max(v_mcpu, v_mem) >= (1 << 63) // 100:
+                raise CompileError(f"node {O.name_of(n)}: allocatable cpu/memory of 2^63/100 or more")
+            cap = {str(k): Quantity.parse(v) for k, v in c_items.items()}
+            g_total = cap[GPU_MEM_NAME].int_value() if GPU_MEM_NAME in cap else 0
+            g_count = cap[GPU_COUNT_NAME].int_value() if GPU_COUNT_NAME in cap else 0
+            if g_count > MAX_GPU_DEV:
+                raise CompileError(f"node {node_names[i]} has more than {MAX_GPU_DEV} GPUs")
+            k = tuple(sorted((nm, q.key()) for nm, q in alloc.items()))
+            before = len(nclass_ids.items)
+            ncls = nclass_ids.get(k)
+            if len(nclass_ids.items) > before:
+                nclass_alloc.append(alloc)
+            shp = (v_mcpu, v_mem, v_eph, v_pods, v_scalar, g_total, g_count, g_total // g_count if g_count > 0 else 0, ncls)
+            if skey is not None:
+                shape_memo[skey] = shp
+        alloc_mcpu[i], alloc_mem[i], alloc_eph[i], alloc_pods[i] = shp[0], shp[1], shp[2], shp[3]
+        if K:
+            alloc_scalar[:, i] = shp[4]
+        gpu_total_mem[i], gpu_count[i], gpu_dev_mem[i], node_class[i] = shp[5], shp[6], shp[7], shp[8]
         if (n.get("spec") or {}).get("unschedulable"):
             node_flags[i] |= NODE_UNSCHEDULABLE
         if len(node_labels[i]) > 0:
             node_flags[i] |= NODE_HAS_LABELS
-        cap = {str(k): Quantity.parse(v) for k, v in (st.get("capacity") or {}).items()}
-        if GPU_MEM_NAME in cap:
-            gpu_total_mem[i] = cap[GPU_MEM_NAME].int_value()
-        if GPU_COUNT_NAME in cap:
-            gpu_count[i] = cap[GPU_COUNT_NAME].int_value()
-        if gpu_count[i] > MAX_GPU_DEV:
-            raise CompileError(f"node {node_names[i]} has more than {MAX_GPU_DEV} GPUs")
-        if gpu_count[i] > 0:
-            gpu_dev_mem[i] = gpu_total_mem[i] // int(gpu_count[i])
-        k = tuple(sorted((nm, q.key()) for nm, q in alloc.items()))
-        before = len(nclass_ids.items)
-        node_class[i] = nclass_ids.get(k)
-        if len(nclass_ids.items) > before:
-            nclass_alloc.append(alloc)
     NC = len(nclass_alloc)
 
     # ---- taints ----
@@ -590,22 +614,34 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
             key_atoms[a[1]] = aid
         else:
             cmp_atoms.setdefault(a[1], []).append((aid, a[2], a[3]))
+    # only label keys some selection program mentions can set a bit; the words are accumulated as Python ints per node and
+    # stored once (numpy scalar read-modify-writes cost a microsecond each)
+    ref_keys = {k for (k, _) in pair_atoms} | set(key_atoms) | set(cmp_atoms)
+    pair_get, key_get, cmp_get = pair_atoms.get, key_atoms.get, cmp_atoms.get
+    bit_rows = [[0] * N for _ in range(WL)]
     for i, labels in enumerate(node_labels):
+        acc = 0
         for k, v in labels.items():
+            if k not in ref_keys:
+                continue
             v = "" if v is None else str(v)
-            aid = pair_atoms.get((k, v))
+            aid = pair_get((k, v))
             if aid is not None:
-                label_bits[aid // 64, i] |= np.uint64(1) << np.uint64(aid % 64)
-            aid = key_atoms.get(k)
+                acc |= 1 << aid
+            aid = key_get(k)
             if aid is not None:
-                label_bits[aid // 64, i] |= np.uint64(1) << np.uint64(aid % 64)
-            for (aid, op, rv) in cmp_atoms.get(k, ()):
+                acc |= 1 << aid
+            for (aid, op, rv) in cmp_get(k, ()):
                 try:
                     lv = _parse_int64(v)
                 except ValueError:
                     continue
                 if (op == "Gt" and lv > rv) or (op == "Lt" and lv < rv):
-                    label_bits[aid // 64, i] |= np.uint64(1) << np.uint64(aid % 64)
+                    acc |= 1 << aid
+        if acc:
+            for w in range(WL):
+                bit_rows[w][i] = (acc >> (64 * w)) & 0xFFFFFFFFFFFFFFFF
+    label_bits = np.array(bit_rows, dtype=np.uint64).reshape(WL, N)
 
     # ---- default selectors (helper.DefaultSelector) ----
     svc_by_ns: Dict[str, List[Obj]] = {}
@@ -897,7 +933,10 @@ def compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[ClusterC
         flags = c.flags | (CLS_IPA_SELF_MATCH if L["self"] else 0)
         w[SCW_FLAGS] = flags
         nn = c.spec.get("nodeName") or ""
-        w[SCW_NODE_NAME] = -1 if not nn else name_to_idx.get(nn, -2)
+        # A pod with spec.nodeName never reaches the scheduler (simulator.go:326-329): it sits on that node (pod_fixed carries
+        # the index per pod), so the class only records THAT the name is set: -3 = "fails NodeName on every node but the one
+        # the pod is bound to", which is what a candidate move of such a pod must see.  One class per template, not per node.
+        w[SCW_NODE_NAME] = -1 if not nn else -3
         w[SCW_STATIC_ROW] = class_row[c.cid]
         w[SCW_EXTRA_ROW] = class_extra[c.cid]
         gn = getattr(c.tmpl, "guard_node_name", "")

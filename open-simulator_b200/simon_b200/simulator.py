@@ -95,6 +95,11 @@ class Plan:
 
 def plan(cluster: ResourceTypes, apps: List[AppResource]) -> Plan:
     """Host-side expansion + ordering; everything the reference does before/between schedulePods calls."""
+    with O.gc_paused():
+        return _plan(cluster, apps)
+
+
+def _plan(cluster: ResourceTypes, apps: List[AppResource]) -> Plan:
     nodes = list(cluster.Nodes)
     pods: List[PodRec] = get_valid_pod_exclude_daemonset(cluster)
     for ds in cluster.DaemonSets:
@@ -122,17 +127,13 @@ _DYNAMIC_REASONS = {
 }
 
 
-def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active: Optional[List[int]] = None,
-                     gpu_nodes: Optional[List[str]] = None) -> str:
-    """FitError.Error() (generic_scheduler.go:72-90) + the wrapper of Simulator.update (simulator.go:465).
-    gpu_nodes: names of the nodes the Open-Gpu-Share filter rejected - its status message is "Node:<name>"
-    (pkg/simulator/plugin/open-gpu-share.go:66-79), so every such node contributes its own reason string with count 1."""
+def _static_reasons(compiled: Compiled, rec: PodRec, idxs) -> dict:
+    """Reason histogram of the node-static filters (NodeUnschedulable, NodeName, TaintToleration, NodeAffinity), evaluated on the
+    objects: the taint reason names the first untolerated taint of each node, which the device's verdict code does not carry."""
     from .selectors import pod_matches_node_selector_and_affinity, tolerations_tolerate_taint
     reasons = {}
     spec = rec.tmpl.spec
     tols = spec.get("tolerations") or []
-    idxs = range(compiled.n_nodes) if active is None else active
-    n_static = 0
     for i in idxs:
         node = compiled.node_objs[i]
         r = None
@@ -151,7 +152,23 @@ def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active
                 r = "node(s) didn't match Pod's node affinity"
         if r is not None:
             reasons[r] = reasons.get(r, 0) + 1
-            n_static += 1
+    return reasons
+
+
+def format_fit_error(compiled: Compiled, rec: PodRec, counts: np.ndarray, active: Optional[List[int]] = None,
+                     gpu_nodes: Optional[List[str]] = None, static_memo: Optional[dict] = None) -> str:
+    """FitError.Error() (generic_scheduler.go:72-90) + the wrapper of Simulator.update (simulator.go:465).
+    gpu_nodes: names of the nodes the Open-Gpu-Share filter rejected - its status message is "Node:<name>"
+    (pkg/simulator/plugin/open-gpu-share.go:66-79), so every such node contributes its own reason string with count 1."""
+    idxs = range(compiled.n_nodes) if active is None else active
+    # the node-static reasons depend on the pod's template and the node list alone: failing replicas of one workload share them
+    mkey = (id(rec.tmpl), None if active is None else tuple(active))
+    static = static_memo.get(mkey) if static_memo is not None else None
+    if static is None:
+        static = _static_reasons(compiled, rec, idxs)
+        if static_memo is not None:
+            static_memo[mkey] = static
+    reasons = dict(static)
     for code, strs in _DYNAMIC_REASONS.items():
         c = int(counts[code])
         if c:
@@ -179,16 +196,19 @@ def build_result(compiled: Compiled, p: Plan, out_node: np.ndarray, fail_counts,
     statuses = [NodeStatus(Node=n) for n in p.nodes]
     by_sorted = {i: statuses[compiled.node_orig_index[i]] for i in range(compiled.n_nodes)}
     fail_idx = {int(pod): j for j, pod in enumerate(fail_pod)}
-    for i, rec in enumerate(p.pods):
-        n = int(out_node[i])
+    static_memo: dict = {}
+    names = compiled.node_names
+    lists = [by_sorted[i].Pods for i in range(compiled.n_nodes)]
+    for i, (rec, n) in enumerate(zip(p.pods, np.asarray(out_node).tolist())):
         if n >= 0:
-            rec.node_name = compiled.node_names[n]
+            rec.node_name = names[n]
             rec.phase = "Running"
-            by_sorted[n].Pods.append(rec)
+            lists[n].append(rec)
         elif n == -1:
             j = fail_idx.get(i)
             counts = fail_counts[j] if j is not None and j < len(fail_counts) else np.zeros(24, np.uint32)
-            res.UnscheduledPods.append(UnscheduledPod(rec, format_fit_error(compiled, rec, counts, gpu_nodes=(gpu_fail_nodes or {}).get(i))))
+            res.UnscheduledPods.append(UnscheduledPod(rec, format_fit_error(compiled, rec, counts, gpu_nodes=(gpu_fail_nodes or {}).get(i),
+                                                                              static_memo=static_memo)))
     res.NodeStatus = statuses
     return res
 

@@ -20,6 +20,7 @@ ReplicaSets, StatefulSets, Jobs, CronJobs.
 """
 from __future__ import annotations
 
+import marshal
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -63,9 +64,16 @@ class PodRec:
     phase: str = ""
     app_name: str = ""
 
+    @property
+    def workload_name(self) -> str:
+        """Name of the owning workload; a bare pod is its own workload (bare pods with identical content share one template -
+        make_valid_pod_by_pod - so their identity lives here, not on the template)."""
+        t = self.tmpl
+        return self.name if t.workload_kind == "Pod" else t.workload_name
+
     def key(self):
         t = self.tmpl
-        return (t.workload_kind, t.workload_namespace, t.workload_name, self.ordinal)
+        return (t.workload_kind, t.workload_namespace, self.workload_name, self.ordinal)
 
 
 def make_valid_pod(old: Obj) -> Obj:
@@ -207,11 +215,33 @@ def make_valid_pod_by_cronjob(cj: Obj) -> List[PodRec]:
     return _replicated(cj, "Job", jt.get("template") or {}, _replicas(jt, "completions"), "Job")
 
 
-def make_valid_pod_by_pod(pod: Obj) -> PodRec:
+def make_valid_pod_by_pod(pod: Obj, memo: Optional[Dict] = None) -> PodRec:
+    """utils.MakeValidPodByPod.  A cluster snapshot lists tens of thousands of bare / running pods that differ only in
+    metadata.name and spec.nodeName (both kept per PodRec): with `memo`, pods whose remaining content is identical share one
+    validated template, so MakeValidPod runs once per distinct content instead of once per pod."""
+    md = pod.get("metadata") or {}
+    spec = pod.get("spec") or {}
+    if memo is not None and isinstance(md, dict) and isinstance(spec, dict):
+        try:
+            ck = marshal.dumps(({k: v for k, v in md.items() if k != "name"},
+                                {k: v for k, v in spec.items() if k != "nodeName"},
+                                {k: v for k, v in pod.items() if k not in ("metadata", "spec", "status")},
+                                bool(spec.get("nodeName"))))
+        except ValueError:
+            ck = None
+        tmpl = memo.get(ck) if ck is not None else None
+        if tmpl is not None:
+            rec = PodRec(tmpl, md.get("name", "") or "", 0)
+            rec.node_name = spec.get("nodeName", "") or ""
+            return rec
+    else:
+        ck = None
     valid = make_valid_pod(pod)
     tmpl = PodTemplate(valid, "Pod", O.name_of(valid), valid["metadata"]["namespace"])
     rec = PodRec(tmpl, O.name_of(valid), 0)
     rec.node_name = (valid.get("spec") or {}).get("nodeName", "") or ""
+    if ck is not None:
+        memo[ck] = tmpl
     return rec
 
 
@@ -273,8 +303,9 @@ def make_valid_pods_by_daemonset(ds: Obj, nodes: List[Obj]) -> List[PodRec]:
 def get_valid_pod_exclude_daemonset(res: ResourceTypes) -> List[PodRec]:
     """simulator.GetValidPodExcludeDaemonSet (pkg/simulator/utils.go:79-230)."""
     pods: List[PodRec] = []
+    memo: Dict = {}
     for p in res.Pods:
-        pods.append(make_valid_pod_by_pod(p))
+        pods.append(make_valid_pod_by_pod(p, memo))
     for d in res.Deployments:
         pods.extend(make_valid_pods_by_deployment(d))
     for rs in res.ReplicaSets:

@@ -59,7 +59,7 @@ def derive(case):
     assert np.array_equal(o_nodes, py), f"{case}: C oracle and object-level restatement disagree"
     wl = {}
     for i, rec in enumerate(p.pods):
-        k = "/".join((rec.tmpl.workload_kind, rec.tmpl.workload_namespace, rec.tmpl.workload_name))
+        k = "/".join((rec.tmpl.workload_kind, rec.tmpl.workload_namespace, rec.workload_name))
         e = wl.setdefault(k, [0, 0])
         e[0] += 1
         e[1] += int(o_nodes[i] >= 0)

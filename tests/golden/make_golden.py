@@ -60,7 +60,7 @@ def main():
     out, _, fc, fp = Oracle(c).schedule()
     ref = run_pyref(p, c)
     assert np.array_equal(out, ref), "the two CPU restatements disagree on the simple scenario"
-    placements = [{"workload": [r.tmpl.workload_kind, r.tmpl.workload_namespace, r.tmpl.workload_name], "ordinal": r.ordinal,
+    placements = [{"workload": [r.tmpl.workload_kind, r.tmpl.workload_namespace, r.workload_name], "ordinal": r.ordinal,
                    "node": c.node_names[n] if n >= 0 else None} for r, n in zip(p.pods, out)]
     json.dump({"node_order": c.node_names, "placements": placements}, open(os.path.join(HERE, "simple_placements.json"), "w"), indent=1)
     json.dump(KAT, open(os.path.join(HERE, "kat_scores.json"), "w"), indent=1)

@@ -65,7 +65,7 @@ def test_simple_scenario_matches_golden_and_reference_pinned_facts():
     assert (out == -1).sum() == 0
     counts = {}
     for r in p.pods:
-        k = (r.tmpl.workload_kind, r.tmpl.workload_name)
+        k = (r.tmpl.workload_kind, r.workload_name)
         counts[k] = counts.get(k, 0) + 1
     assert counts[("ReplicaSet", "busybox-deploy")] == 4
     assert counts[("StatefulSet", "busybox-sts")] == 4
@@ -116,7 +116,7 @@ def test_simulate_api_on_simple_scenario_gpu():
     got = {}
     for st in res.NodeStatus:
         for rec in st.Pods:
-            got[((rec.tmpl.workload_kind, rec.tmpl.workload_namespace, rec.tmpl.workload_name), rec.ordinal)] = st.Node["metadata"]["name"]
+            got[((rec.tmpl.workload_kind, rec.tmpl.workload_namespace, rec.workload_name), rec.ordinal)] = st.Node["metadata"]["name"]
     assert got == want
 
 
