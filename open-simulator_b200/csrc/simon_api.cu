@@ -289,9 +289,10 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
             return SIMON_OK;
         }
     }
+    if (want_cs > SK_MAX_CS) return fail(ctx, SIMON_ERR_LIMIT, "CTAs per scenario must be <= %u (got %u)", (unsigned)SK_MAX_CS, want_cs);
     for (uint32_t ci = 0; ci < 5; ci++) {
         uint32_t cs = cs_opts[ci];
-        if (want_cs) { if (cs != want_cs) continue; }
+        if (want_cs) { if (ci) break; cs = want_cs; }      // an explicit cluster size need not be a power of two (10 = half of a 20-SM GPC)
         else if (cs > 1 && (uint64_t)(cs / 2) * 256 * 3 >= n_active) continue;   // smallest cluster with <= 3 nodes/thread at 256 threads
         for (uint32_t npt = 1; npt <= 64; npt++) {
             uint32_t t;

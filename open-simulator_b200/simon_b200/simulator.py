@@ -215,6 +215,11 @@ def build_result(compiled: Compiled, p: Plan, out_node: np.ndarray, fail_counts,
 
 def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> SimulateResult:
     """simulator.Simulate (pkg/simulator/core.go:67). Errors are exceptions; per-pod failures are data."""
+    with O.gc_paused():         # the whole call is one burst of acyclic allocations (expansion, columns, result lists)
+        return _simulate(cluster, apps, *opts)
+
+
+def _simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> SimulateResult:
     options = SimulatorOptions()
     for o in opts:
         o(options)
@@ -236,11 +241,22 @@ def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> 
         raise NotImplementedError("WithKubeConfig: importing a live cluster needs an API server; pass the cluster as "
                                   "ResourceTypes (objects.create_cluster_resource_from_cluster_config)")
     from .engine import Engine     # raises if libsimon_gpu.so / CUDA is unavailable: no CPU fallback
+    import time
+    tm = {}
+    t0 = time.perf_counter()
     p = plan(cluster, apps)
+    tm["plan_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     compiled = compile_cluster(p.nodes, p.pods, p.ctx, extra_plugins=extra_plugins or None)
+    tm["compile_s"] = time.perf_counter() - t0
     gpu_fail_nodes = {}
+    t0 = time.perf_counter()
     with Engine(compiled, device=options.device, record_scores=options.record_scores) as eng:
+        tm["engine_create_upload_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         out_node, _scores, fail_counts, fail_pod = eng.schedule()
+        tm["schedule_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         # Open-Gpu-Share's failure reason names the node, so the histogram needs the node LIST of such pods, not a count:
         # re-evaluate those pods with the per-node verdict dump (a bounded number of them - each costs a partial re-run)
         gpu_bit = 1 << 19
@@ -248,4 +264,11 @@ def Simulate(cluster: ResourceTypes, apps: List[AppResource], *opts: Option) -> 
         for pod in todo:
             _o, _t, code = eng.dump_pod(pod)
             gpu_fail_nodes[pod] = [compiled.node_names[g] for g in np.nonzero(code & gpu_bit)[0]]
-    return build_result(compiled, p, out_node, fail_counts, fail_pod, gpu_fail_nodes)
+        tm["gpu_fail_detail_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+    tm["engine_close_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res = build_result(compiled, p, out_node, fail_counts, fail_pod, gpu_fail_nodes)
+    tm["build_result_s"] = time.perf_counter() - t0
+    Simulate.last_timing = tm       # where the wall clock of the last call went (bench.py reports it beside e2e_api)
+    return res

@@ -57,7 +57,7 @@ def test_parity_mixed_features(seed):
         np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
 
 
-@pytest.mark.parametrize("cs,tpb", [(1, 256), (2, 128), (4, 64), (8, 128), (16, 64), (16, 320), (4, 320)])
+@pytest.mark.parametrize("cs,tpb", [(1, 256), (2, 128), (4, 64), (8, 128), (16, 64), (16, 320), (4, 320), (9, 96), (5, 160), (3, 320)])
 def test_parity_cluster_geometries(cs, tpb):
     p, c = make_case("c3", n_nodes=700, n_workloads=80, replicas=12, n_apps=2, seed_no=13)
     (ref, _, rfc, _), _ = run_oracle(c)
