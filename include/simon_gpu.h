@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define SIMON_ABI_VERSION 2
+#define SIMON_ABI_VERSION 3
 
 #define SIMON_MAX_SCALARS 8     /* extended/scalar resource columns (K) */
 #define SIMON_MAX_GPU_DEV 8     /* GPU-share devices per node */
@@ -116,7 +116,8 @@ enum simon_class_word {
     SCW_STATIC_ROW,     /* row of simon_raw (>=0) */
     SCW_EXTRA_ROW,      /* row of extra_score or -1 (ImageLocality 0, NodePreferAvoidPods 100) */
     SCW_GUARD_NODE,     /* -1, or the node a DaemonSet pod was generated for: in a scenario where that node is
-                           inactive the pod does not exist (pkg/utils/utils.go:337-351) */
+                           inactive the pod does not exist (pkg/utils/utils.go:337-351); -3: per pod = its pod_pin_node
+                           (SIMON_CLS_PINNED classes); -2: names no node */
     SCW_STATIC_SIG,     /* id of the class's static signature (tolerations, node selection + preference programs,
                            nodeName, topology keys): classes sharing it share the per-node static verdicts */
     SCW_OFF_SCALARS,    /* K words: dense scalar requests */
@@ -159,6 +160,8 @@ enum simon_class_word {
 #define SIMON_CLS_TOL_UNSCHED 2u        /* tolerates node.kubernetes.io/unschedulable:NoSchedule */
 #define SIMON_CLS_IPA_SELF_MATCH 4u     /* pod matches all of its own required affinity terms (filtering.go:361-372) */
 #define SIMON_CLS_SIMON_NOREQ 8u        /* len(PodRequestsAndLimits)==0 -> Simon raw score 100 (simon.go:46-49) */
+#define SIMON_CLS_PINNED 16u            /* DaemonSet pods (utils.go:337-351, 770-815): the pods of the class differ only in the node their
+                                           required matchFields term names; the programs say "pin" (-3) and pod_pin_node says which */
 
 /* Node-selection program at SCW_OFF_SEL (int64 words):
  *   [n_ns]  then n_ns requirements           pod.Spec.NodeSelector, ANDed   helper/node_affinity.go:30-36
@@ -169,7 +172,8 @@ enum simon_class_word {
 enum simon_req_op {
     SIMON_REQ_ANY = 1,       /* matches iff any masked atom is set   (In, Exists, Gt, Lt)         labels/selector.go:200-244 */
     SIMON_REQ_NONE = 2,      /* matches iff no masked atom is set    (NotIn, DoesNotExist) */
-    SIMON_REQ_NODE_IS = 3,   /* matchFields metadata.name In [v]     nodeaffinity.go:229-257 */
+    SIMON_REQ_NODE_IS = 3,   /* matchFields metadata.name In [v]     nodeaffinity.go:229-257; payload = node index, -1 (names no
+                                node), or -3 = the pod's own pin node (simon_podset.pod_pin_node): classes with SIMON_CLS_PINNED */
     SIMON_REQ_NODE_ISNOT = 4
 };
 
@@ -185,6 +189,8 @@ typedef struct simon_podset {
     const int32_t *pod_class;      /* [P] */
     const int32_t *pod_fixed_node; /* [P] -1: schedule; >=0: spec.nodeName preset -> bypass scheduling, account only
                                            (eventhandlers.go:223 addPodToCache; simulator.go:329) */
+    const int32_t *pod_pin_node;   /* [P] or NULL: pin of a pod of a SIMON_CLS_PINNED class (>=0 node index, -2: names no node of
+                                           the cluster); -1 for every other pod */
     const uint32_t *counter_topo;  /* [n_counters] topology each counter is keyed on */
     const int64_t *simon_raw;      /* [n_static_rows][n_node_classes]  Simon.Score raw value  simon.go:45-68 */
     const int32_t *extra_score;    /* [n_extra_rows][N] ImageLocality + 10000*NodePreferAvoidPods, weighted sum */
@@ -320,7 +326,7 @@ int simon_debug_dump_read(simon_ctx *ctx, int64_t *out_total, int32_t *out_code)
  * (device time by CUDA events). */
 #define SIMON_MOVE_NOOP (1u << 24)         /* target is the pod's current node */
 #define SIMON_MOVE_NOT_PLACED (1u << 25)   /* the pod is not running on a node of the snapshot */
-#define SIMON_MOVE_NOT_MOVABLE (1u << 26)  /* class with DoNotSchedule spread constraints or a GPU-share request */
+#define SIMON_MOVE_NOT_MOVABLE (1u << 26)  /* class with DoNotSchedule spread constraints, a GPU-share request, or pinned (DaemonSet pod) */
 #define SIMON_MOVE_BAD_INDEX (1u << 27)
 #define SIMON_MOVE_GAIN_BIAS 1000
 

@@ -489,7 +489,12 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
     for (uint32_t i = 0; i < p->n_pods; i++) {
         int32_t c = p->pod_class[i];
         if (c < 0 || (uint32_t)c >= p->n_classes) return fail(ctx, SIMON_ERR_INVALID, "pod %u: bad class", i);
-        guard[i] = (int32_t)p->class_blob[p->class_off[c] + SCW_GUARD_NODE];
+        int64_t g = p->class_blob[p->class_off[c] + SCW_GUARD_NODE];
+        if (g == -3) {          // per pod: the pin of a DaemonSet pod (simon_podset.pod_pin_node)
+            g = p->pod_pin_node ? p->pod_pin_node[i] : -1;
+            if (g >= (int64_t)ctx->N || g < -2) return fail(ctx, SIMON_ERR_INVALID, "pod %u: bad pin node %lld", i, (long long)g);
+        }
+        guard[i] = (int32_t)g;
     }
     ctx->max_blob_words = max_words;
     ctx->emax = emax;
@@ -573,7 +578,7 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
             k.req_mcpu = cw[SCW_REQ_MCPU]; k.req_mem = cw[SCW_REQ_MEM]; k.req_eph = cw[SCW_REQ_EPH];
             k.sig = (uint32_t)cw[SCW_STATIC_SIG];
             uint32_t bits = (uint32_t)cw[SCW_FLAGS] & 0xffu;
-            if (cw[SCW_N_PTS_HARD] > 0 || cw[SCW_GPU_MEM] > 0) bits |= SMC_NOT_MOVABLE;
+            if (cw[SCW_N_PTS_HARD] > 0 || cw[SCW_GPU_MEM] > 0 || (cw[SCW_FLAGS] & SIMON_CLS_PINNED)) bits |= SMC_NOT_MOVABLE;
             const int64_t *sc = cw + cw[SCW_OFF_SCALARS];
             for (uint32_t q = 0; q < ctx->K; q++) if (sc[q] != 0) bits |= SMC_HAS_SCALAR;
             const uint32_t n_filt = (uint32_t)(cw[SCW_N_IPA_AFF] + cw[SCW_N_IPA_ANTI] + cw[SCW_N_IPA_EXIST]);

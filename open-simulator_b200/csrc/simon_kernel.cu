@@ -57,6 +57,7 @@ __device__ __forceinline__ int64_t div_by(int64_t x, int64_t d, double inv) {
 struct ReqCtx {
     const uint64_t *label_bits;
     uint32_t N;
+    int32_t pin;        // pin node of the pod being evaluated (simon_podset.pod_pin_node), -1 none: what REQ_NODE_IS payload -3 means
 };
 
 __device__ inline bool req_eval(const int64_t *&p, const ReqCtx &c, uint32_t g) {
@@ -64,6 +65,7 @@ __device__ inline bool req_eval(const int64_t *&p, const ReqCtx &c, uint32_t g) 
     int op = (int)(head & 0xff);
     if (op == SIMON_REQ_NODE_IS || op == SIMON_REQ_NODE_ISNOT) {
         int64_t idx = *p++;
+        if (idx == -3) idx = c.pin;          // the pod's own pin (DaemonSet pods, pkg/utils/utils.go:770-815)
         return op == SIMON_REQ_NODE_IS ? ((int64_t)g == idx) : ((int64_t)g != idx);
     }
     int nw = (int)((head >> 8) & 0xff);
@@ -152,6 +154,7 @@ struct ClassState {
     uint32_t e_hard, e_soft, e_aff, e_anti, e_exist, e_isc;
     uint32_t cflags;
     bool any_table, has_gpu;
+    bool pinned;         // SIMON_CLS_PINNED: the static verdict of the pin node depends on the pod, nothing is carried from pod to pod
     int64_t aff_total;
     // summary of the feasible set
     bool sum_valid;      // exact for the current feasibility bits
@@ -189,7 +192,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
     long long owner_cyc = 0, owner_n = 0;     // profiling variants: cycles the committing thread spends in its commit block
     SkRed R{&S, &cluster, crank, CS, 0, PROF ? rprof : nullptr};
     sk_red_init(R);
-    const ReqCtx RC{P.label_bits, N};
+    ReqCtx RC{P.label_bits, N, -1};
     const bool leader = (gtid == 0);
     unsigned long long st_class = 0, st_sum = 0, st_redo = 0, st_slow = 0, st_fast = 0;
     uint32_t last_win_r = 0xffffffffu;     // scenario rank of the last winner while its class stays current
@@ -416,6 +419,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         const int32_t cls = nx_cls, fixed = nx_fixed;
         const uint64_t cls_off = nx_off;
         const int64_t guard = nx_guard;
+        RC.pin = (int32_t)guard;            // pods of pinned classes: the node their REQ_NODE_IS(-3) requirements name
         if (i + 1 < end) {
             nx_cls = P.pod_class[i + 1]; nx_fixed = P.pod_fixed[i + 1]; nx_guard = P.pod_guard[i + 1];
             if (SIMON_OPT & 32) nx_off = P.class_off[nx_cls];
@@ -488,7 +492,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             // remember the summary of the class we leave: it is the prediction for its next visit
             // remember the class we leave: its summary AND the feasibility bits it is exact for.  On the next visit the
             // bits are restored and P1 detects any change against them, exactly as between two pods of one class.
-            if (cur_class >= 0 && C.sum_valid && SC.csum && SC.fbits && !C.any_table) {
+            if (cur_class >= 0 && C.sum_valid && SC.csum && SC.fbits && !C.any_table && !C.pinned) {
                 if (leader) {
                     long long *rec = SC.csum + (uint64_t)cur_class * SK_CSUM_W;
 #pragma unroll
@@ -551,7 +555,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             C.sum_valid = false;
             C.snorm_valid = false;
             C.any_table = cw[SCW_ANY_TABLE] != 0;
-            C.have_pred = pred[0] == 1;
+            C.pinned = (C.cflags & SIMON_CLS_PINNED) != 0;
+            C.have_pred = pred[0] == 1 && !C.pinned;
             const bool restore = C.have_pred && !C.any_table && SC.fbits;
             last_win_r = 0xffffffffu;
             bits_dirty = !restore;
@@ -667,6 +672,10 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     // record = {code:8, flags:8, tt:8, valid:1 (bit 24), na:32 (bits 32..63)}; 8-byte loads/stores are atomic, so a
                     // record is either absent (computed here and published) or complete, also across concurrent scenarios
                     unsigned long long rec = rec4[u];
+                    // pinned class: the cached record is the verdict of a node that is NOT the pod's pin; the pin node's own
+                    // verdict is computed for this pod and never published
+                    const bool is_pin = C.pinned && (int32_t)g == RC.pin;
+                    if (is_pin) rec = 0;
                     if (rec & (1ull << 24)) {
                         code = (uint8_t)rec; fl = (uint8_t)(rec >> 8); tt = (int32_t)((rec >> 16) & 0xff); na = (int32_t)(rec >> 32);
                     } else {
@@ -696,7 +705,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                         for (uint32_t js = 0; js < C.n_soft; js++) if (DOM(ENT(ER_T, C.e_soft + js), idx) < 0) ign = true;
                         if (hk) fl |= NF_HARDKEYS;
                         if (ign) fl |= NF_IGNORED;
-                        if (P.use_scache && tt < 256)
+                        if (P.use_scache && tt < 256 && !is_pin)
                             P.scache[(uint64_t)sig * N + g] = (unsigned long long)code | ((unsigned long long)fl << 8) |
                                                              ((unsigned long long)(uint32_t)tt << 16) | (1ull << 24) |
                                                              ((unsigned long long)(uint32_t)na << 32);
@@ -780,7 +789,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             #pragma unroll 1
             for (uint32_t e = C.e_aff; e < C.e_anti; e++) C.aff_total += ldcg32(&SC.cnt_total[ENT(ER_K, e)]);
             if (C.have_pred) set_weights();
-            cur_class = cls;
+            cur_class = C.pinned ? -1 : cls;        // a pinned class is re-entered for every pod (its static verdicts move with the pin)
             TICK(2);
         }
 
@@ -1244,7 +1253,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
 // one thread per pod with atomics instead of one pod at a time inside the placement kernel.  Single scenario only.
 extern "C" __global__ void __launch_bounds__(256) simon_import_kernel(const __grid_constant__ SkParams P, uint32_t first, uint32_t count) {
     const SkScenario &SC = P.scen[0];
-    const ReqCtx RC{P.label_bits, P.N};
+    const ReqCtx RC{P.label_bits, P.N, -1};
     const uint32_t N = P.N, K = P.K;
     for (uint32_t q = first + blockIdx.x * blockDim.x + threadIdx.x; q < first + count; q += gridDim.x * blockDim.x) {
         const int32_t f2 = P.pod_fixed[q];

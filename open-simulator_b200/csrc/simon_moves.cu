@@ -49,7 +49,7 @@ struct __align__(16) SmvPod {
 #define SMV_OK 0u
 #define SMV_NOOP (1u << 24)            // target == current node
 #define SMV_NOT_PLACED (1u << 25)      // the pod is not running anywhere (unscheduled / absent / bound outside the cluster)
-#define SMV_NOT_MOVABLE (1u << 26)     // class with DoNotSchedule spread constraints or a GPU-share request: not a candidate
+#define SMV_NOT_MOVABLE (1u << 26)     // class with DoNotSchedule spread constraints, a GPU-share request or a pin (DaemonSet pod): not a candidate
 #define SMV_BAD_INDEX (1u << 27)
 #define SMV_GAIN_BIAS 1000
 #define SMV_NBINS 401                  // gains lie in [-200, 200]

@@ -45,7 +45,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "%s: not a SIMC1 dump\n", argv[1]);
         return 65;
     }
-    Blob sa[16], pa[7];
+    Blob sa[16], pa[8];
     for (auto &b : sa) if (!read_blob(f, b)) { fprintf(stderr, "truncated dump\n"); return 65; }
     for (auto &b : pa) if (!read_blob(f, b)) { fprintf(stderr, "truncated dump\n"); return 65; }
     fclose(f);
@@ -65,7 +65,7 @@ int main(int argc, char **argv) {
     p.n_classes = pd[0]; p.n_pods = pd[1]; p.n_counters = pd[2]; p.n_static_rows = pd[3]; p.n_extra_rows = pd[4]; p.n_static_sigs = pd[5];
     p.class_off = (const uint64_t *)pa[0].ptr(); p.class_blob = (const int64_t *)pa[1].ptr(); p.pod_class = (const int32_t *)pa[2].ptr();
     p.pod_fixed_node = (const int32_t *)pa[3].ptr(); p.counter_topo = (const uint32_t *)pa[4].ptr(); p.simon_raw = (const int64_t *)pa[5].ptr();
-    p.extra_score = (const int32_t *)pa[6].ptr();
+    p.extra_score = (const int32_t *)pa[6].ptr(); p.pod_pin_node = (const int32_t *)pa[7].ptr();
 
     simon_ctx_opts opts;
     memset(&opts, 0, sizeof(opts));

@@ -27,7 +27,7 @@ class SimonPodset(C.Structure):
         ("n_classes", C.c_uint32), ("n_pods", C.c_uint32), ("n_counters", C.c_uint32),
         ("n_static_rows", C.c_uint32), ("n_extra_rows", C.c_uint32), ("n_static_sigs", C.c_uint32),
         ("class_off", C.c_void_p), ("class_blob", C.c_void_p), ("pod_class", C.c_void_p),
-        ("pod_fixed_node", C.c_void_p), ("counter_topo", C.c_void_p), ("simon_raw", C.c_void_p),
+        ("pod_fixed_node", C.c_void_p), ("pod_pin_node", C.c_void_p), ("counter_topo", C.c_void_p), ("simon_raw", C.c_void_p),
         ("extra_score", C.c_void_p),
     ]
 
@@ -64,8 +64,9 @@ _SNAP_DTYPES = {
 }
 _PODS_DTYPES = {
     "class_off": np.uint64, "class_blob": np.int64, "pod_class": np.int32, "pod_fixed_node": np.int32,
-    "counter_topo": np.uint32, "simon_raw": np.int64, "extra_score": np.int32,
+    "counter_topo": np.uint32, "simon_raw": np.int64, "extra_score": np.int32, "pod_pin_node": np.int32,
 }
+_PODS_OPTIONAL = ("pod_pin_node",)       # NULL when the pod list has no pinned class (columns stored before ABI 3)
 
 
 def ptr(a: np.ndarray) -> int:
@@ -86,6 +87,9 @@ def marshal(compiled):
     for k, v in compiled.pods_dims.items():
         setattr(pods, k, int(v))
     for k, dt in _PODS_DTYPES.items():
+        if k in _PODS_OPTIONAL and compiled.pods.get(k) is None:
+            setattr(pods, k, None)
+            continue
         a = np.ascontiguousarray(compiled.pods[k], dtype=dt)
         keep.append(a)
         setattr(pods, k, ptr(a))

@@ -55,6 +55,7 @@ CLS_HAS_REQUEST = 1
 CLS_TOL_UNSCHED = 2
 CLS_IPA_SELF_MATCH = 4
 CLS_SIMON_NOREQ = 8
+CLS_PINNED = 16            # node-selection programs refer to the pod's own pin node (REQ_NODE_IS payload -3): DaemonSet pods
 REQ_ANY, REQ_NONE, REQ_NODE_IS, REQ_NODE_ISNOT = 1, 2, 3, 4
 EK_PORT, EK_HARD, EK_SOFT, EK_AFF, EK_ANTI, EK_EXIST, EK_SCORE = range(7)
 SK_MAXW = 6      # domain-bitmask words the engine reduces per decision (csrc/simon_kernel.cuh)
@@ -155,6 +156,7 @@ class ClassInfo:
     aff_pref: list = field(default_factory=list)    # [(nsset, reqs, key, weight)]
     anti_pref: list = field(default_factory=list)
     parse_error: Optional[str] = None
+    pinned: bool = False      # every required node-affinity term names the pod's pin node (DaemonSet pods): <= 1 feasible node
 
 
 @dataclass
@@ -359,6 +361,10 @@ def _parse_class(cid: int, tmpl: PodTemplate) -> ClassInfo:
 
 
 def _class_key(tmpl: PodTemplate) -> str:
+    if getattr(tmpl, "pin_group", None) is not None:
+        # the pods of one DaemonSet differ only in the node name of their required matchFields term, which the class expresses
+        # as "the pod's pin" (pod_pin_node): one class per DaemonSet, not one per node
+        return ("pin", id(tmpl.pin_group))
     pod = tmpl.pod
     spec = pod.get("spec") or {}
     md = pod.get("metadata") or {}
@@ -447,6 +453,9 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
     pod_class = np.fromiter((r.tmpl.class_id for r in pods), dtype=np.int32, count=len(pods))
     nget = name_to_idx.get
     pod_fixed = np.fromiter((nget(r.node_name, -2) if r.node_name else -1 for r in pods), dtype=np.int32, count=len(pods))
+    # pin of the pods of pinned classes (DaemonSet pods): the node their class's REQ_NODE_IS(-3) requirements stand for
+    pod_pin = np.fromiter((nget(r.tmpl.guard_node_name, -2) if r.tmpl.pin_group is not None else -1 for r in pods),
+                          dtype=np.int32, count=len(pods))
     C = len(classes)
     # DefaultPreemption (PL/defaultpreemption/default_preemption.go:91-167) only ever evicts pods of strictly lower priority
     # than the pod that failed to schedule.  Priorities come from spec.priority alone (no admission controller resolves
@@ -570,6 +579,7 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
     class_sel = []   # per class: (ns_reqs, has_required, terms, prefs) in atom form
     for c in classes:
         spec = c.spec
+        pin_name = c.tmpl.guard_node_name if getattr(c.tmpl, "pin_group", None) is not None else None
         ns_reqs = []
         for k, v in sorted((spec.get("nodeSelector") or {}).items()):
             ns_reqs.append((REQ_ANY, _req_atoms(str(k), "In", (str(v),))))
@@ -584,7 +594,7 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
                 for term in req.get("nodeSelectorTerms") or []:
                     if is_empty_node_selector_term(term):
                         continue
-                    terms.append(_compile_term(term, _req_atoms, name_to_idx))
+                    terms.append(_compile_term(term, _req_atoms, name_to_idx, pin_name))
             for p in na.get("preferredDuringSchedulingIgnoredDuringExecution") or []:
                 w = int(p.get("weight") or 0)
                 pref = p.get("preference") or {}
@@ -598,6 +608,7 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
         # weights are 1..100, so the sum fits unless the input is not a valid PodSpec - refuse instead of narrowing silently
         if sum(abs(w) for w, _t in prefs) >= (1 << 31):
             raise CompileError("preferred node affinity weights sum to 2^31 or more")
+        c.pinned = pin_name is not None and len(terms) > 0 and all(any(r == (REQ_NODE_IS, -3) for r in t) for t in terms)
         class_sel.append((ns_reqs, has_required, terms, prefs))
     n_atoms = len(atoms.items)
     WL = max(1, (n_atoms + 63) // 64)
@@ -689,6 +700,10 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
         return tuple(reqs)
 
     # ---- spread constraints per class ----
+    # A pinned class (DaemonSet pods) has at most one feasible node, and Schedule returns before PreScore / Score when one node is
+    # left (generic_scheduler.go:150-157): its ScheduleAnyway constraints can never be evaluated, so they are not compiled
+    # (their node eligibility would also depend on the pod, not on the class).  Its preferred pod (anti)affinity terms stay: as
+    # terms held by EXISTING pods they weigh in the scores of other incoming pods.
     for c in classes:
         tsc = c.spec.get("topologySpreadConstraints") or []
         if len(tsc) > 0:
@@ -697,9 +712,9 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
                 ent = (t.get("topologyKey", ""), int(t.get("maxSkew") or 0), None if reqs is None else tuple(reqs))
                 if t.get("whenUnsatisfiable") == "DoNotSchedule":
                     c.hard.append(ent)
-                elif t.get("whenUnsatisfiable") == "ScheduleAnyway":
+                elif t.get("whenUnsatisfiable") == "ScheduleAnyway" and not c.pinned:
                     c.soft.append(ent)
-        else:
+        elif not c.pinned:
             sel = default_selector(c)
             if len(sel) > 0:
                 c.soft.append((O.LABEL_HOSTNAME, 3, sel))
@@ -785,6 +800,8 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
     elig_rep: Dict[str, int] = {}
 
     def elig_sig(c: ClassInfo):
+        if c.pinned:
+            return None         # at most one feasible node: Schedule returns before scoring (generic_scheduler.go:150-157)
         soft_topos = sorted({topo.ids[k] for (k, _, _) in c.soft})
         na = ((c.spec.get("affinity") or {}).get("nodeAffinity") or {})
         restricted = bool(c.spec.get("nodeSelector")) or na.get("requiredDuringSchedulingIgnoredDuringExecution") is not None
@@ -940,7 +957,11 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
         w[SCW_STATIC_ROW] = class_row[c.cid]
         w[SCW_EXTRA_ROW] = class_extra[c.cid]
         gn = getattr(c.tmpl, "guard_node_name", "")
-        w[SCW_GUARD_NODE] = name_to_idx.get(gn, -2) if gn else -1
+        grouped = getattr(c.tmpl, "pin_group", None) is not None
+        # -3: per pod (pod_pin_node) - the pods of a DaemonSet's class exist in a scenario iff their own node does
+        w[SCW_GUARD_NODE] = -3 if grouped else (name_to_idx.get(gn, -2) if gn else -1)
+        if c.pinned:
+            w[SCW_FLAGS] |= CLS_PINNED
         body: List[int] = []
 
         def put(off_word):
@@ -1072,7 +1093,7 @@ def _compile_cluster(nodes: List[Obj], pods: List[PodRec], ctx: Optional[Cluster
                  "n_node_classes": max(1, NC), "n_log": n_log}
     podset = {
         "class_off": np.array(class_off, np.uint64), "class_blob": np.array(blob or [0], np.int64),
-        "pod_class": pod_class, "pod_fixed_node": pod_fixed, "counter_topo": counter_topo,
+        "pod_class": pod_class, "pod_fixed_node": pod_fixed, "pod_pin_node": pod_pin, "counter_topo": counter_topo,
         "simon_raw": np.ascontiguousarray(simon_raw), "extra_score": np.ascontiguousarray(extra_score.astype(np.int32)),
     }
     pods_dims = {"n_classes": C, "n_pods": len(pods), "n_counters": n_counters, "n_static_sigs": max(1, len(static_sigs.items)),
@@ -1085,8 +1106,9 @@ def _i64(x: int) -> int:
     return x - (1 << 64) if x >= (1 << 63) else x
 
 
-def _compile_term(term: Obj, req_atoms, name_to_idx):
-    """-> list of requirements [(op, payload)] or a never-matching term for an invalid one."""
+def _compile_term(term: Obj, req_atoms, name_to_idx, pin_name: Optional[str] = None):
+    """-> list of requirements [(op, payload)] or a never-matching term for an invalid one.
+    pin_name: the node name that stands for "the pod's pin" in this class (payload -3, resolved per pod from pod_pin_node)."""
     lab, fld, ok = node_selector_term_requirements(term)
     if not ok:
         return [(REQ_ANY, [])]       # parse error: the term never matches (LazyErrorNodeSelector.Match)
@@ -1096,7 +1118,7 @@ def _compile_term(term: Obj, req_atoms, name_to_idx):
         reqs.append((REQ_ANY if op in ("In", "Exists", "Gt", "Lt") else REQ_NONE, aids))
     for (key, op, val) in fld or []:
         if key == "metadata.name":
-            idx = name_to_idx.get(val, -1)
+            idx = -3 if (pin_name is not None and val == pin_name) else name_to_idx.get(val, -1)
             reqs.append((REQ_NODE_IS if op == "In" else REQ_NODE_ISNOT, idx))
         else:
             # fields.Set only knows metadata.name; other keys read as "": In matches iff val == ""

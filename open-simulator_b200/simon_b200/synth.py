@@ -471,6 +471,7 @@ class LiveSnapshot:
         self.pods = dict(base.pods)
         self.pods["pod_class"] = np.ascontiguousarray(pod_class, dtype=np.int32)
         self.pods["pod_fixed_node"] = np.ascontiguousarray(pod_fixed, dtype=np.int32)
+        self.pods["pod_pin_node"] = np.full(len(pod_class), -1, dtype=np.int32)
         self.pods_dims = dict(base.pods_dims)
         self.pods_dims["n_pods"] = len(pod_class)
         self.n_nodes = base.n_nodes

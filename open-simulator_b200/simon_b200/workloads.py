@@ -40,6 +40,8 @@ class PodTemplate:
     workload_namespace: str = ""
     class_id: int = -1          # filled by the snapshot compiler
     guard_node_name: str = ""   # DaemonSet pods: the node this pod was generated for
+    pin_group: object = None    # DaemonSet pods: shared by the pods of one DaemonSet, which differ ONLY in the node name of the
+                                # required matchFields term (the "pin"); the snapshot compiler gives the group one class
 
     @property
     def namespace(self) -> str:
@@ -280,22 +282,36 @@ def node_should_run_pod(node: Obj, pod: Obj) -> bool:
     return True
 
 
+class PinGroup:
+    """Identity of one DaemonSet's pod set (see PodTemplate.pin_group)."""
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+
 def make_valid_pods_by_daemonset(ds: Obj, nodes: List[Obj]) -> List[PodRec]:
     """utils.MakeValidPodsByDaemonset (pkg/utils/utils.go:337-351): one pod per eligible node, in node order,
-    each pinned with a required matchFields metadata.name node affinity."""
+    each pinned with a required matchFields metadata.name node affinity.
+    MakeValidPod runs once on the template; the per-node pods share everything but metadata and spec.affinity."""
     spec = ds.get("spec") or {}
     template = spec.get("template") or {}
+    base = make_valid_pod({"metadata": _object_meta_from(ds, template, "DaemonSet"), "spec": deep_copy(template.get("spec") or {})})
+    _add_workload_info(base, "DaemonSet", O.name_of(ds), O.namespace_of(ds))
+    base_aff = base["spec"].get("affinity")
+    group = PinGroup(O.name_of(ds))
     recs = []
     ordinal = 0
     for node in nodes:
-        pod = {"metadata": _object_meta_from(ds, template, "DaemonSet"), "spec": deep_copy(template.get("spec") or {})}
-        pod["spec"]["affinity"] = _daemon_affinity(pod["spec"].get("affinity"), O.name_of(node))
-        valid = make_valid_pod(pod)
-        _add_workload_info(valid, "DaemonSet", O.name_of(ds), O.namespace_of(ds))
+        nname = O.name_of(node)
+        valid = dict(base)
+        valid["metadata"] = deep_copy(base["metadata"])
+        valid["spec"] = dict(base["spec"])
+        valid["spec"]["affinity"] = _daemon_affinity(base_aff, nname)
         if node_should_run_pod(node, valid):
             tmpl = PodTemplate(valid, "DaemonSet", O.name_of(ds), valid["metadata"]["namespace"],
-                               guard_node_name=O.name_of(node))
-            recs.append(PodRec(tmpl, f"{O.name_of(ds)}-{O.name_of(node)}", ordinal))
+                               guard_node_name=nname, pin_group=group)
+            recs.append(PodRec(tmpl, f"{O.name_of(ds)}-{nname}", ordinal))
             ordinal += 1
     return recs
 

@@ -83,6 +83,7 @@ typedef struct simon_oracle {
     void *pool_args;
     int64_t plugin_dump_enabled;
     int64_t *dump; /* [N][10] optional */
+    int64_t cur_pin;   /* pin node of the pod being evaluated (simon_podset.pod_pin_node), -1 none: what REQ_NODE_IS payload -3 means */
 } simon_oracle;
 
 #define CW(o, c) ((o)->p.class_blob + (o)->p.class_off[c])
@@ -94,6 +95,7 @@ static int req_eval(const int64_t **pp, const simon_oracle *o, uint32_t n) {
     int res;
     if (op == SIMON_REQ_NODE_IS || op == SIMON_REQ_NODE_ISNOT) {
         int64_t idx = *p++;
+        if (idx == -3) idx = o->cur_pin;     /* the pod's own pin (DaemonSet pods, pkg/utils/utils.go:770-815) */
         res = (op == SIMON_REQ_NODE_IS) ? ((int64_t)n == idx) : ((int64_t)n != idx);
     } else {
         int nw = (int)((head >> 8) & 0xff);
@@ -668,6 +670,7 @@ simon_oracle *simon_oracle_create(const simon_snapshot *s, const simon_podset *p
     if (!o) return NULL;
     o->s = *s;
     o->p = *p;
+    o->cur_pin = -1;
     uint32_t N = s->n_nodes;
     o->N = N;
     uint32_t K = s->n_scalars ? s->n_scalars : 1;
@@ -784,6 +787,9 @@ int simon_oracle_schedule(simon_oracle *o, uint32_t first, uint32_t count, int32
         const int64_t *cw = CW(o, cls);
         int32_t fixed = o->p.pod_fixed_node[pod];
         int64_t guard = cw[SCW_GUARD_NODE];
+        int64_t pin = o->p.pod_pin_node ? o->p.pod_pin_node[pod] : -1;
+        if (guard == -3) guard = pin;
+        o->cur_pin = pin;
         int64_t score = 0;
         if (guard == -2 || (guard >= 0 && !o->active[guard])) {       /* pod does not exist in this scenario */
             out_node[i] = -3;
@@ -875,7 +881,7 @@ int simon_oracle_moves_score(simon_oracle *o, uint32_t n_moves, const uint32_t *
         }
         if (!code) {
             const int64_t *cw = CW(o, o->p.pod_class[pod]);
-            if (cw[SCW_N_PTS_HARD] > 0 || cw[SCW_GPU_MEM] > 0) code = SMV_NOT_MOVABLE;
+            if (cw[SCW_N_PTS_HARD] > 0 || cw[SCW_GPU_MEM] > 0 || (cw[SCW_FLAGS] & SIMON_CLS_PINNED)) code = SMV_NOT_MOVABLE;
             else {
                 uint32_t flags = (uint32_t)cw[SCW_FLAGS];
                 const int64_t *tol = cw + cw[SCW_OFF_TOL];

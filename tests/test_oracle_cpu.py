@@ -87,7 +87,7 @@ def test_abi_library_exports():
     for name in declared:
         assert hasattr(L, name), name
     assert set(engine.EXPORTS) == declared
-    assert L.simon_gpu_version() == 2
+    assert L.simon_gpu_version() == 3
 
 
 def test_open_local_pods_are_refused_at_compile_time():

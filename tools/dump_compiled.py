@@ -27,7 +27,7 @@ def dump(compiled, path: str) -> None:
             f.write(struct.pack("<Q", a.nbytes))
             f.write(a.tobytes())
         for k, dt in abi._PODS_DTYPES.items():
-            a = np.ascontiguousarray(compiled.pods[k], dtype=dt)
+            a = np.ascontiguousarray(compiled.pods[k] if compiled.pods.get(k) is not None else np.zeros(0), dtype=dt)    # absent: empty blob = NULL
             f.write(struct.pack("<Q", a.nbytes))
             f.write(a.tobytes())
 
