@@ -222,6 +222,8 @@ typedef struct simon_ctx_opts {
     uint32_t flags;            /* SIMON_OPT_* */
 } simon_ctx_opts;
 #define SIMON_OPT_RECORD_SCORES 1u   /* also produce the winning total score per pod */
+#define SIMON_OPT_NO_PIN_FAST 2u     /* place the pods of pinned classes (DaemonSet pods) one decision at a time through the general
+                                        path instead of evaluating a run of them in one pass (same results; for verification) */
 
 /* One what-if scenario of the capacity-planning search (pkg/apply/apply.go:203-259):
  * the uploaded snapshot holds the base nodes plus a pool of candidate new nodes; a scenario

@@ -143,6 +143,7 @@ struct simon_ctx {
     DevBuf<SmvClass> d_mv_classes;
     DevBuf<SmvPod> d_mv_pods;
     uint32_t mv_n = 0, mv_base = 0;
+    uint32_t n_pin_fast = 0;            // pods marked for the pinned-run fast path (-4 in the device copy of pod_fixed_node)
     std::vector<uint8_t> bypass;        // per pod: never reaches the scheduler in a single-scenario run (pre-bound or absent)
     DevBuf<unsigned char> d_gnode;      // large-cluster variant: per-node arrays in global memory
     bool big = false;                   // set by choose_geometry for the next launch
@@ -516,7 +517,26 @@ int simon_pods_upload(simon_ctx *ctx, const simon_podset *p) {
         CU(ctx->d_class_blob.upload(padded.data(), padded.size(), st));
         CU(cudaStreamSynchronize(st));
     }
-    CU(ctx->d_pod_class.upload(p->pod_class, p->n_pods, st)); CU(ctx->d_pod_fixed.upload(p->pod_fixed_node, p->n_pods, st));
+    // Device copy of pod_fixed_node with one more value: -4 = "pinned pod on the fast path".  A pod of a pinned class whose only
+    // dynamic filters are node-local (host ports on the node itself, NodeResourcesFit) can only land on its pin node, and its
+    // outcome depends on that node's state alone: the kernel evaluates a whole run of such pods in one pass, each by the thread
+    // that owns the pin node (simon_kernel.cu, "run of pinned pods").  Classes with DoNotSchedule constraints, required pod
+    // (anti)affinity of their own or matched by existing pods' anti-affinity, or a GPU-share request read state beyond the
+    // node and take the general path.
+    std::vector<int32_t> fixed_dev(p->pod_fixed_node, p->pod_fixed_node + p->n_pods);
+    ctx->n_pin_fast = 0;
+    if (!(ctx->opt_flags & SIMON_OPT_NO_PIN_FAST)) {
+        std::vector<uint8_t> fast(p->n_classes, 0);
+        for (uint32_t c = 0; c < p->n_classes; c++) {
+            const int64_t *cw = p->class_blob + p->class_off[c];
+            fast[c] = (cw[SCW_FLAGS] & SIMON_CLS_PINNED) && cw[SCW_N_PTS_HARD] == 0 && cw[SCW_N_IPA_AFF] == 0 && cw[SCW_N_IPA_ANTI] == 0 &&
+                      cw[SCW_N_IPA_EXIST] == 0 && cw[SCW_GPU_MEM] == 0 && cw[SCW_GPU_COUNT] == 0 && cw[SCW_NODE_NAME] == -1;
+        }
+        for (uint32_t i = 0; i < p->n_pods; i++)
+            if (fixed_dev[i] == -1 && guard[i] >= 0 && fast[p->pod_class[i]]) { fixed_dev[i] = -4; ctx->n_pin_fast++; }
+    }
+    CU(ctx->d_pod_class.upload(p->pod_class, p->n_pods, st)); CU(ctx->d_pod_fixed.upload(fixed_dev.data(), p->n_pods, st));
+    CU(cudaStreamSynchronize(st));
     CU(ctx->d_pod_guard.upload(guard.data(), p->n_pods, st)); CU(ctx->d_cnt_off.upload(cnt_off.data(), cnt_off.size(), st));
     CU(ctx->d_simon_raw.upload(p->simon_raw, (size_t)std::max(1u, p->n_static_rows) * ctx->NC, st));
     ctx->simon32 = 1;

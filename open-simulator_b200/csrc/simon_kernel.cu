@@ -429,14 +429,143 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         else if (guard >= 0) exists = SC.rank_of ? (SC.rank_of[guard] >= 0) : true;
 
         TICK(0);
-        if (!exists || fixed != -1) {
+        if (exists && fixed == -4 && i != P.dump_pod) {
+            // ---- run of pinned pods (DaemonSet pods whose dynamic filters are node-local; marked -4 by simon_pods_upload) ----
+            // Such a pod can only land on its pin node (every other node fails NodeAffinity at the latest), and whether it does
+            // depends on that node alone: NodeUnschedulable, TaintToleration and NodeAffinity of the pin, NodePorts on the node's own
+            // counters, NodeResourcesFit.  The thread that owns the pin node evaluates the pod, commits it and writes the result; a
+            // thread that owns the pins of several pods of the run handles them in pod order, so pods pinned to the same node see
+            // each other exactly as in a sequential pass.  With one feasible node there is no scoring (generic_scheduler.go:150-157).
+            uint32_t j = i;
+            while (j < end && P.pod_fixed[j] == -4 && j != P.dump_pod) j++;
+            #pragma unroll 1
+            for (uint32_t q = i; q < j; q++) {
+                const int64_t g2 = P.pod_guard[q];
+                const int32_t r = SC.rank_of ? SC.rank_of[g2] : (int32_t)g2;
+                if (r < 0) {                                    // the pin node is not part of this scenario: the pod does not exist
+                    if (leader) { SC.out_node[q] = -3; if (SC.out_score) SC.out_score[q] = 0; if (SC.out_gpu) SC.out_gpu[q] = 0; }
+                    continue;
+                }
+                if ((uint32_t)r % CT != gtid) continue;
+                const uint32_t g = (uint32_t)g2, idx = ((uint32_t)r / CT) * TPB + tid;
+                const int64_t *cw2 = P.class_blob + P.class_off[P.pod_class[q]];
+                const uint32_t cfl = (uint32_t)cw2[SCW_FLAGS];
+                const ReqCtx rc2{P.label_bits, N, (int32_t)g2};
+                uint32_t rs = 0;
+                bool st_fail = (P.node_flags[g] & SIMON_NODE_UNSCHEDULABLE) && !(cfl & SIMON_CLS_TOL_UNSCHED);
+                if (!st_fail) {
+                    const int64_t *tol = cw2 + cw2[SCW_OFF_TOL];
+                    #pragma unroll 1
+                    for (uint32_t w = 0; w < WT; w++)
+                        if (P.taint_hard[(uint64_t)w * N + g] & ~(uint64_t)tol[w]) st_fail = true;
+                }
+                if (!st_fail && !selection_ok(cw2, rc2, g)) st_fail = true;
+                if (st_fail) rs = 1u << SFC_STATIC;
+                else {
+                    const int64_t *pp = cw2 + cw2[SCW_OFF_PORTS];
+                    const int32_t d0 = DOM(0, idx);
+                    #pragma unroll 1
+                    for (int64_t u = 0; u < cw2[SCW_N_PORTS]; u++)
+                        if (d0 >= 0 && ldcg32(&SC.cnt[P.cnt_off[pp[u]] + (uint32_t)d0]) > 0) { rs = 1u << SFC_PORTS; break; }
+                    if (!rs) {
+                        if (A32(B_NUM_PODS, idx) + 1 > A32(B_ALLOC_PODS, idx)) rs |= 1u << SFC_TOO_MANY_PODS;
+                        if (cfl & SIMON_CLS_HAS_REQUEST) {
+                            if (A64(A_ALLOC_MCPU, idx) < cw2[SCW_REQ_MCPU] + A64(A_REQ_MCPU, idx)) rs |= 1u << SFC_CPU;
+                            if (A64(A_ALLOC_MEM, idx) < cw2[SCW_REQ_MEM] + A64(A_REQ_MEM, idx)) rs |= 1u << SFC_MEM;
+                            if (A64(A_ALLOC_EPH, idx) < cw2[SCW_REQ_EPH] + A64(A_REQ_EPH, idx)) rs |= 1u << SFC_EPH;
+                            const int64_t *sc_req = cw2 + cw2[SCW_OFF_SCALARS];
+                            #pragma unroll 1
+                            for (uint32_t k = 0; k < K; k++)
+                                if (sc_req[k] != 0 && P.alloc_scalar[(uint64_t)k * N + g] < sc_req[k] + SC.req_scalar[(uint64_t)k * N + g])
+                                    rs |= 1u << (SFC_SCALAR0 + k);
+                        }
+                    }
+                }
+                if (rs == 0) {
+                    // AssumePod on the pin node (the accounting of the bypass path above, no GPU-share: such classes are not marked)
+                    A64(A_REQ_MCPU, idx) += cw2[SCW_REQ_MCPU]; A64(A_REQ_MEM, idx) += cw2[SCW_REQ_MEM]; A64(A_REQ_EPH, idx) += cw2[SCW_REQ_EPH];
+                    A64(A_NZ_MCPU, idx) += cw2[SCW_NZ_MCPU]; A64(A_NZ_MEM, idx) += cw2[SCW_NZ_MEM]; A32(B_NUM_PODS, idx) += 1;
+                    const int64_t *sc = cw2 + cw2[SCW_OFF_SCALARS];
+                    #pragma unroll 1
+                    for (uint32_t k = 0; k < K; k++) SC.req_scalar[(uint64_t)k * N + g] += sc[k];
+                    const int64_t *inc = cw2 + cw2[SCW_OFF_INC];
+                    #pragma unroll 1
+                    for (int64_t u = 0; u < cw2[SCW_N_INC]; u++) {
+                        int64_t k = inc[3 * u], t = inc[3 * u + 1], sig = inc[3 * u + 2];
+                        int32_t d = DOM(t, idx);
+                        if (d < 0) continue;
+                        if (sig >= 0 && !elig_eval(P, sig, rc2, g)) continue;
+                        atomicAdd(&SC.cnt[P.cnt_off[k] + d], 1);
+                        atomicAdd(&SC.cnt_total[k], 1);
+                    }
+                    SC.out_node[q] = (int32_t)g;
+                } else {
+                    SC.out_node[q] = (int32_t)(0xC0000000u | rs);      // reasons of the pin node, replaced by -1 once the record is written
+                }
+                if (SC.out_score) SC.out_score[q] = 0;
+                if (SC.out_gpu) SC.out_gpu[q] = 0;
+            }
+            // every CTA learns the outcomes (the per-thread pod counters stay replicated); CTA 0 writes the failure records in pod order
+            __threadfence();
+            cluster.sync();
+            uint32_t my_f = 0, my_s = 0;
+            #pragma unroll 1
+            for (uint32_t q = i + tid; q < j; q += TPB) {
+                const int32_t v = __ldcg(SC.out_node + q);
+                if (v >= 0) my_s++;
+                else if (v != -3) my_f++;
+            }
+            unsigned int *scr = reinterpret_cast<unsigned int *>(S.pred);         // free between classes (cur_class = -1 below)
+            my_f = __reduce_add_sync(0xffffffffu, my_f); my_s = __reduce_add_sync(0xffffffffu, my_s);
+            __syncthreads();
+            if ((tid & 31) == 0) { scr[(tid >> 5) * 2] = my_f; scr[(tid >> 5) * 2 + 1] = my_s; }
+            __syncthreads();
+            uint32_t run_f = 0, run_s = 0;
+            for (uint32_t w = 0; w < (TPB + 31) / 32; w++) { run_f += scr[w * 2]; run_s += scr[w * 2 + 1]; }
+            __syncthreads();
+            if (run_f && crank == 0) {
+                uint32_t at = n_fail;
+                #pragma unroll 1
+                for (uint32_t c0 = i; c0 < j; c0 += TPB) {                         // block-wide ordered compaction, TPB pods at a time
+                    const uint32_t q = c0 + tid;
+                    const int32_t v = q < j ? __ldcg(SC.out_node + q) : 0;
+                    const bool isf = v < 0 && v != -3;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, isf);
+                    if ((tid & 31) == 0) scr[tid >> 5] = __popc(bal);
+                    __syncthreads();
+                    uint32_t before = 0, chunk = 0;
+                    for (uint32_t w = 0; w < (TPB + 31) / 32; w++) { const uint32_t cw_ = scr[w]; if (w < (tid >> 5)) before += cw_; chunk += cw_; }
+                    if (isf) {
+                        const uint32_t slot = at + before + __popc(bal & ((1u << (tid & 31)) - 1u));
+                        if (slot < P.max_fail && SC.fail_counts) {
+                            uint32_t rs = (uint32_t)v & 0x00ffffffu;
+                            uint32_t *row = SC.fail_counts + (uint64_t)slot * SIMON_N_FAIL_CODES;
+                            // every other active node fails NodeAffinity at the latest: one count each in the static bin
+                            row[SFC_STATIC] = (NA - 1u) + (rs & 1u);
+                            rs &= ~1u;
+                            while (rs) { const int b = __ffs(rs) - 1; rs &= rs - 1; row[b] = 1u; }
+                            SC.fail_pod[slot] = q;
+                        }
+                        SC.out_node[q] = -1;
+                    }
+                    at += chunk;
+                    __syncthreads();
+                }
+            }
+            n_fail += run_f; n_sched += run_s;
+            cur_class = -1;
+            i = j;
+            if (i < end) { nx_cls = P.pod_class[i]; nx_fixed = P.pod_fixed[i]; nx_guard = P.pod_guard[i]; if (SIMON_OPT & 32) nx_off = P.class_off[nx_cls]; }
+            continue;
+        }
+        if (!exists || (fixed != -1 && fixed != -4)) {
             // ---- batch of pods that bypass scheduling (spec.nodeName preset) or do not exist in this scenario ----
             uint32_t j = i;
             while (j < end) {
                 int32_t f2 = P.pod_fixed[j];
                 int64_t g2 = P.pod_guard[j];
                 bool ex2 = g2 == -2 ? false : (g2 >= 0 ? (SC.rank_of ? SC.rank_of[g2] >= 0 : true) : true);
-                if (ex2 && f2 == -1) break;
+                if (ex2 && (f2 == -1 || f2 == -4)) break;
                 j++;
             }
             #pragma unroll 1

@@ -7,6 +7,7 @@ import numpy as np
 
 N_FAIL_CODES = 24
 OPT_RECORD_SCORES = 1
+OPT_NO_PIN_FAST = 2
 
 
 class SimonSnapshot(C.Structure):

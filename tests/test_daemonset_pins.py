@@ -130,18 +130,24 @@ def test_mixed_clusters_with_daemonsets_cpu(seed):
 
 
 def _gpu_cmp(c):
+    """Both device paths of pinned pods - the run-at-once fast path and the general decision path - against the oracle."""
     from simon_b200.engine import Engine
     (ref, rscore, rfc, rfp), rstate = run_oracle(c)
-    with Engine(c, device=0, record_scores=True) as eng:
-        out, score, fc, fp = eng.schedule()
-        st = eng.state()
-    np.testing.assert_array_equal(out, ref)
-    np.testing.assert_array_equal(fp, rfp)
-    np.testing.assert_array_equal(fc, rfc)
-    sched = ref >= 0
-    np.testing.assert_array_equal(score[sched & (rscore > 0)], rscore[sched & (rscore > 0)])
-    for k in rstate:
-        np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
+    for pin_fast in (True, False):
+        with Engine(c, device=0, record_scores=True, pin_fast=pin_fast) as eng:
+            out, score, fc, fp = eng.schedule()
+            st = eng.state()
+            eng.reset()
+            half = len(ref) // 2                                    # split calls: a run of pinned pods cut by the call boundary
+            out2 = np.concatenate([eng.schedule(0, half)[0], eng.schedule(half, len(ref) - half)[0]])
+        np.testing.assert_array_equal(out, ref, err_msg=f"pin_fast={pin_fast}")
+        np.testing.assert_array_equal(out2, ref, err_msg=f"pin_fast={pin_fast}, two calls")
+        np.testing.assert_array_equal(fp, rfp)
+        np.testing.assert_array_equal(fc, rfc, err_msg=f"pin_fast={pin_fast}")
+        sched = ref >= 0
+        np.testing.assert_array_equal(score[sched & (rscore > 0)], rscore[sched & (rscore > 0)])
+        for k in rstate:
+            np.testing.assert_array_equal(st[k], rstate[k], err_msg=k)
     return out
 
 
@@ -188,7 +194,8 @@ def test_pin_nodes_absent_from_a_scenario_gpu():
         o.set_active(act)
         ref = o.schedule()[0]
         o.close()
-        with Engine(c, device=0) as eng:
-            _res, nodes = eng.run_scenarios([act], want_nodes=True)
-        np.testing.assert_array_equal(nodes[0], ref)
+        for pin_fast in (True, False):
+            with Engine(c, device=0, pin_fast=pin_fast) as eng:
+                _res, nodes = eng.run_scenarios([act], want_nodes=True)
+            np.testing.assert_array_equal(nodes[0], ref, err_msg=f"pin_fast={pin_fast}")
         assert (ref == -3).sum() > 0
