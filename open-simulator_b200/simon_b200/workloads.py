@@ -300,18 +300,45 @@ def make_valid_pods_by_daemonset(ds: Obj, nodes: List[Obj]) -> List[PodRec]:
     _add_workload_info(base, "DaemonSet", O.name_of(ds), O.namespace_of(ds))
     base_aff = base["spec"].get("affinity")
     group = PinGroup(O.name_of(ds))
+    # NodeShouldRunPod of the pod pinned to `node` depends on the node through its taints and the labels the template's
+    # nodeSelector / required matchExpressions mention (the pin term itself always matches its own node; matchFields of the
+    # template are overwritten by the pin, utils.go:806-811): nodes that agree on those share the verdict.
+    bspec = base["spec"]
+    keys = set((bspec.get("nodeSelector") or {}).keys())
+    req = (((base_aff or {}).get("nodeAffinity") or {}).get("requiredDuringSchedulingIgnoredDuringExecution") or {})
+    for term in req.get("nodeSelectorTerms") or []:
+        for e in term.get("matchExpressions") or []:
+            keys.add(e.get("key"))
+    keys = sorted(k for k in keys if isinstance(k, str))
+    use_memo = not bspec.get("nodeName")
+    memo: Dict = {}
+    missing = object()
     recs = []
     ordinal = 0
+    ds_name = O.name_of(ds)
+    ns = base["metadata"]["namespace"]
     for node in nodes:
         nname = O.name_of(node)
-        valid = dict(base)
-        valid["metadata"] = deep_copy(base["metadata"])
-        valid["spec"] = dict(base["spec"])
+        valid = dict(base)                 # metadata is shared by the DaemonSet's pods (identical: the pod's own name lives in PodRec)
+        valid["spec"] = dict(bspec)
         valid["spec"]["affinity"] = _daemon_affinity(base_aff, nname)
-        if node_should_run_pod(node, valid):
-            tmpl = PodTemplate(valid, "DaemonSet", O.name_of(ds), valid["metadata"]["namespace"],
-                               guard_node_name=nname, pin_group=group)
-            recs.append(PodRec(tmpl, f"{O.name_of(ds)}-{nname}", ordinal))
+        ok = None
+        mk = None
+        if use_memo:
+            labels = (node.get("metadata") or {}).get("labels") or {}
+            try:
+                mk = (tuple(labels.get(k, missing) for k in keys),
+                      tuple((t.get("key"), t.get("value"), t.get("effect")) for t in ((node.get("spec") or {}).get("taints") or [])))
+                ok = memo.get(mk)
+            except TypeError:
+                mk = None
+        if ok is None:
+            ok = node_should_run_pod(node, valid)
+            if mk is not None:
+                memo[mk] = ok
+        if ok:
+            tmpl = PodTemplate(valid, "DaemonSet", ds_name, ns, guard_node_name=nname, pin_group=group)
+            recs.append(PodRec(tmpl, f"{ds_name}-{nname}", ordinal))
             ordinal += 1
     return recs
 
