@@ -247,6 +247,45 @@ def block_c2(args, local, flush, torch):
             "roofline_frac": v * ALGO_BYTES_PER_NODE_DECISION_C2 * 1000 / 1e9 / peak}
 
 
+def block_daemonsets(args, local, flush, torch):
+    """The headline cluster with 5 DaemonSets on top (one pinned pod per node each): pods of the reference's
+    MakeValidPodsByDaemonset (pkg/utils/utils.go:337-351).  One class per DaemonSet + a per-pod pin column; runs of pinned pods are
+    placed in one pass.  Both device paths are timed and must agree pod for pod (the oracle comparison lives in the tests)."""
+    from simon_b200 import simulator, synth
+    from simon_b200.compiler import compile_cluster
+    from simon_b200.engine import Engine
+    cluster, apps = synth.make_c3(n_nodes=args.nodes, n_workloads=args.workloads, replicas=args.replicas, n_apps=10, seed_no=3)
+    for k in range(5):
+        lab = {"ds": f"agent-{k}"}
+        cluster.DaemonSets.append({"apiVersion": "apps/v1", "kind": "DaemonSet", "metadata": {"name": f"agent-{k}", "namespace": "kube-system"},
+                                   "spec": {"selector": {"matchLabels": lab}, "template": {"metadata": {"labels": lab}, "spec": {
+                                       "tolerations": [{"operator": "Exists"}],
+                                       "containers": [{"name": "c", "image": f"agent:{k}", "resources": {"requests": {"cpu": "50m", "memory": "64Mi"}},
+                                                       "ports": [{"containerPort": 9100 + k, "hostPort": 9100 + k}]}]}}}})
+    t0 = time.perf_counter()
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    host_s = time.perf_counter() - t0
+    n_ds = int((c.pods["pod_pin_node"] >= 0).sum())
+    D = int((c.pods["pod_fixed_node"] == -1).sum())
+    res = {}
+    outs = {}
+    for name, fast in (("run_at_once", True), ("general_path", False)):
+        with Engine(c, device=local, pin_fast=fast) as eng:
+            for _ in range(2):
+                eng.replay(1)
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms = eng.replay(1)
+            eng.reset()
+            outs[name] = eng.schedule()[0]
+        res[name] = {"ms": ms, "pods_per_s": D / (ms * 1e-3)}
+    return {"workload": f"C3 cluster ({args.nodes} nodes) + 5 DaemonSets: {D} scheduled pods of which {n_ds} pinned DaemonSet pods",
+            "classes": int(c.pods_dims["n_classes"]), "host_compile_s": host_s, **res,
+            "paths_identical": bool(np.array_equal(outs["run_at_once"], outs["general_path"])),
+            "placed": int((outs["run_at_once"] >= 0).sum()), "unschedulable": int((outs["run_at_once"] == -1).sum())}
+
+
 def block_batch(args, c, D, P, placed, local, flush, torch):
     """Concurrent what-if replicas of the C3 workload on one GPU: one thread-block cluster each; report the best residency."""
     from simon_b200.engine import Engine
@@ -506,6 +545,7 @@ def main():
                 blocks[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1:
             guarded("c2", block_c2, args, local, flush, torch)
+            guarded("daemonsets", block_daemonsets, args, local, flush, torch)
             if not args.no_batch:
                 guarded("batch", block_batch, args, c, D, P, placed, local, flush, torch)
         guarded("capacity_search", block_capacity, args, rank, world, local, dist, torch)

@@ -12,7 +12,7 @@ timeout 1500 python bench.py 2>$OUT/bench_$TAG.err | tee $OUT/bench_$TAG.json | 
 import sys,json
 d=json.loads(sys.stdin.read())
 print('value', round(d['value']), 'ms', round(d['ms_per_step'],1), 'e2e', round(d['e2e']['value']), 'launches', d['gpu_launches'], 'cpu', d['cpu_baseline'] and (round(d['cpu_baseline']['value']), d['cpu_baseline']['placements_identical']))
-for k in ('c2','batch','capacity_search','move_scoring'):
+for k in ('c2','daemonsets','batch','capacity_search','move_scoring'):
     b=d.get(k); print(k, json.dumps(b)[:600])
 "
 tail -3 $OUT/bench_$TAG.err
