@@ -58,6 +58,9 @@ func (e *gpuEngine) err(rc C.int) error {
 
 // compiledCluster is what the (to-be-ported) Go snapshot compiler produces: every slice is laid out exactly
 // as include/simon_gpu.h documents (node-major, little-endian, nodes in nodeTree.list() order).
+// pods.pod_pin_node (ABI 3): for the pods utils.MakeValidPodsByDaemonset generates, the index of the node their
+// matchFields metadata.name term names (the DaemonSet's class stores that requirement once, as "the pin"); -1 otherwise.
+// pods.pod_fixed_node: the index of spec.nodeName for pods created bound (they share one class per template).
 type compiledCluster struct {
 	snap C.simon_snapshot
 	pods C.simon_podset
