@@ -54,6 +54,11 @@ __device__ __forceinline__ int64_t div_by(int64_t x, int64_t d, double inv) {
     return q;
 }
 
+// SIMON_PINRUN=0 compiles the run-of-pinned-pods pass out (A/B builds; simon_pods_upload must then not mark pods: SIMON_OPT_NO_PIN_FAST)
+#ifndef SIMON_PINRUN
+#define SIMON_PINRUN 1
+#endif
+
 struct ReqCtx {
     const uint64_t *label_bits;
     uint32_t N;
@@ -429,7 +434,7 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
         else if (guard >= 0) exists = SC.rank_of ? (SC.rank_of[guard] >= 0) : true;
 
         TICK(0);
-        if (exists && fixed == -4 && i != P.dump_pod) {
+        if (SIMON_PINRUN && exists && fixed == -4 && i != P.dump_pod) {
             // ---- run of pinned pods (DaemonSet pods whose dynamic filters are node-local; marked -4 by simon_pods_upload) ----
             // Such a pod can only land on its pin node (every other node fails NodeAffinity at the latest), and whether it does
             // depends on that node alone: NodeUnschedulable, TaintToleration and NodeAffinity of the pin, NodePorts on the node's own
