@@ -22,6 +22,7 @@
 //          device-wide __threadfence() before the arrive
 //   bit 1  (removed) log weights from shared-memory windows of the log table: measured 1.7 % slower
 //   bit 3  truncations whose argument is provably in range are plain casts (no Go out-of-range emulation)
+//   bit 7  the leaving class's summary / feasibility bits are stored after barrier.cluster.arrive (per-CTA identical stores)
 //   bit 4  with bit 0: one __syncthreads less in the class switch (nothing is transposed after the header is parsed)
 //   bit 5  the class record's offset is fetched one pod ahead and its length taken as the largest record's (no dependent
 //          global loads at the head of the class switch)
@@ -626,8 +627,11 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             // remember the summary of the class we leave: it is the prediction for its next visit
             // remember the class we leave: its summary AND the feasibility bits it is exact for.  On the next visit the
             // bits are restored and P1 detects any change against them, exactly as between two pods of one class.
+            auto save_class = [&]() {
             if (cur_class >= 0 && C.sum_valid && SC.csum && SC.fbits && !C.any_table && !C.pinned) {
-                if (leader) {
+                // (bit 7: every CTA's thread 0 writes the record - the values are replicated, so the stores are identical - and a CTA
+                //  reads back what its own thread 0 wrote, ordered by __syncthreads: no cluster-scope ordering of these stores is needed)
+                if ((SIMON_OPT & 128) ? tid == 0 : leader) {
                     long long *rec = SC.csum + (uint64_t)cur_class * SK_CSUM_W;
 #pragma unroll
                     for (int js = 0; js < SK_MAX_SOFT; js++) rec[1 + js] = (uint32_t)js < C.n_soft ? psz[js] : 0;
@@ -647,6 +651,8 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
                     }
                 }
             }
+            };
+            if (!(SIMON_OPT & 128)) save_class();
             TICK(10);
             // the previous commits' counter updates (owner-thread atomics) must be visible before the counters are read:
             // release here, acquire (barrier_wait) only where the first counter is loaded, so that the class blob, entry
@@ -656,6 +662,9 @@ __device__ __forceinline__ void simon_place_body(const SkParams &P) {
             if (!(SIMON_OPT & 4)) __threadfence();
             cluster.barrier_arrive();
             __syncthreads();          // every thread of this CTA is done with the previous class's blob and entry table
+            // bit 7: the leaving class's summary and feasibility bits are stored AFTER the arrive, so that its release does not wait
+            // for them (their only readers are this CTA's own threads, a class change later at the earliest)
+            if (SIMON_OPT & 128) save_class();
             TICK(11);
             // (bit 5: the record's offset came with the pod one iteration ago; copying the largest record's length instead of this
             //  one's reads into the next record - the upload pads the blob - and saves the dependent loads of the exact length)

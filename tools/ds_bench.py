@@ -39,6 +39,7 @@ print(f"schedule: {dt * 1e3:.1f} ms wall, kernel {eng.last_kernel_ms() if hasatt
 if a.check:
     from oracle.binding import Oracle
     o = Oracle(c, threads=16)
+    a.check = min(a.check, len(out))
     ref = o.schedule(0, a.check)[0]
     o.close()
     print("oracle prefix", a.check, "identical:", bool(np.array_equal(ref, out[:a.check])), flush=True)
