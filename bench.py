@@ -510,6 +510,7 @@ def main():
     # ---- the public API itself: Simulate(objects) -> SimulateResult, wall clock (plan + compile + engine creation + uploads +
     #      placement + result objects); one untimed call first (lazy imports), on fresh copies of the objects each time ----
     api_s = None
+    api_native = None
     if not args.no_blocks and rank == 0:
         from simon_b200 import simulator as _sim
         from simon_b200.objects import deep_copy as _dc
@@ -527,6 +528,46 @@ def main():
         api_s = min(api_times)
         api_parts = {k: round(v, 4) for k, v in getattr(_sim.Simulate, "last_timing", {}).items()}
         api_placed = sum(len(ns.Pods) for ns in res_api.NodeStatus)
+        # ---- the same call through the NATIVE host side (simon_host_simulate: JSON objects in -> placements + failure messages out,
+        #      C++ expansion / queue sorts / snapshot compiler / result; what the Go shim calls).  The request is marshalled once,
+        #      outside the timed region (the Go caller marshals its typed objects with encoding/json; Python's json.dumps of the
+        #      same objects is reported as request_encode_s for scale) ----
+        try:
+            from simon_b200 import native_host as _nh
+            t0 = time.perf_counter()
+            req = _nh.request_json(cl0, ap0)
+            enc_s = time.perf_counter() - t0
+            nat_times = []
+            for rep in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nat = _nh.simulate_native(None, None, device=local, req=req)
+                dt = time.perf_counter() - t0
+                if rep:
+                    nat_times.append(dt)
+            nat_s = min(nat_times)
+            nat_placed = sum(len(x) for x in nat["nodeStatus"])
+            # identical outcome: every pod on the same node as through the Python mirror, same failure messages
+            py_node = {}
+            for ns in res_api.NodeStatus:
+                for r in ns.Pods:
+                    py_node[r.key()] = (ns.Node.get("metadata") or {}).get("name")
+            tl = nat["templates"]
+            same = nat_placed == api_placed
+            for ti, name, o, nd in zip(nat["podTemplate"], nat["podName"], nat["podOrdinal"], nat["podNode"]):
+                tt = tl[ti]
+                k = (tt["kind"], tt["namespace"], name if tt["kind"] == "Pod" else tt["workload"], o)
+                if (nat["nodes"][nd] if nd >= 0 else None) != py_node.get(k):
+                    same = False
+                    break
+            same = same and [u["reason"] for u in nat["unscheduledPods"]] == [u.Reason for u in res_api.UnscheduledPods]
+            api_native = {"value": D / nat_s, "unit": "decisions/s", "simulate_s": nat_s, "request_bytes": len(req), "request_encode_s": enc_s,
+                          "last_call_parts": nat["timing"], "identical_to_python_simulate": bool(same),
+                          "path": "simon_host_simulate(request JSON) -> result JSON, wall clock of the C-ABI call + json.loads of the result on "
+                                  "rank 0, best of 2 after one untimed call: JSON parse + workload expansion + Go 1.18 queue sorts + snapshot "
+                                  "compiler (C++) + engine creation + uploads + placement + per-node lists and FitError messages"}
+        except Exception as e:       # noqa: BLE001
+            api_native = {"error": f"{type(e).__name__}: {e}"[:300]}
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -597,6 +638,7 @@ def main():
                             "path": "simulator.Simulate(cluster objects, app objects) -> SimulateResult, wall clock of the call on rank 0, best of 2 "
                                     "after one untimed call: workload expansion + queue sorts + snapshot compiler (Python, host_compile_s) + "
                                     "engine creation + uploads + placement + per-node result lists; estimate_from_parts = host_compile_s + one e2e pass"},
+                "e2e_api_native": api_native if api_s else None,
                 "gpu_launches": int(launches), "clocks": clocks, "decisions_per_step": D, "prebound_pods_per_step": P - D, "placed": placed,
                 "unschedulable": int((out_node == -1).sum()), "wall_s_timed_region": wall, "host_compile_s": host_s,
                 "kernel_stats": {k: stats[k] for k in ("class_switches", "summary_rebuilds", "redone", "single_flip_fast", "merged_decisions", "merged_redone")}}

@@ -478,10 +478,7 @@ struct PerClass {
     int self = 0;
 };
 
-inline double simon_share(const Quantity *pq, const Quantity &aq, std::unordered_map<std::string, double> &memo) {
-    std::string key = (pq ? pq->key() : std::string("-")) + "|" + aq.key();
-    auto it = memo.find(key);
-    if (it != memo.end()) return it->second;
+inline double simon_share(const Quantity *pq, const Quantity &aq, std::unordered_map<std::string, double> &) {
     Quantity zero;
     const Quantity &p = pq ? *pq : zero;
     Quantity avail = aq;
@@ -489,7 +486,6 @@ inline double simon_share(const Quantity *pq, const Quantity &aq, std::unordered
     double a = p.as_approximate_float64(), t = avail.as_approximate_float64(), v;
     if (t == 0) v = a == 0 ? 0.0 : 1.0;
     else v = a / t;
-    memo.emplace(key, v);
     return v;
 }
 // Simon.Score raw value (pkg/simulator/plugin/simon.go:45-68)
@@ -533,9 +529,9 @@ inline void compile_cluster(const Plan &plan, Compiled &out) {
     std::vector<ClassInfo> &classes = out.classes;
     {
         std::unordered_map<std::string, int> key_to_cid;
-        std::unordered_set<const PodTemplate *> seen;
+        for (auto &r : pods) r.tmpl->class_id = -1;
         for (auto &r : pods) {
-            if (!seen.insert(r.tmpl).second) continue;
+            if (r.tmpl->class_id >= 0) continue;
             std::string k = class_key(*r.tmpl);
             auto it = key_to_cid.find(k);
             int cid;

@@ -153,7 +153,7 @@ inline void dump(std::string &out, const J &j, bool sort_keys = false) {
 }
 inline void dump_opt(std::string &out, const J *p, bool sort_keys = false) { if (p) dump(out, *p, sort_keys); else out += "null"; }
 
-// ---- parser (RFC 8259; duplicate keys: the last one wins, at the first one's position, like json.loads) ----
+// ---- parser (RFC 8259; encoding/json never emits duplicate keys: were there one, lookups see the first) ----
 struct Parser {
     const char *p, *e;
     explicit Parser(const char *s, size_t n) : p(s), e(s + n) {}
@@ -234,11 +234,8 @@ struct Parser {
                 ws();
                 if (p >= e || *p != ':') fail("expected ':'");
                 p++;
-                J v = value(depth + 1);
-                bool dup = false;
-                if (j.o.size() < 64)
-                    for (auto &kv : j.o) if (kv.first == k) { kv.second = std::move(v); dup = true; break; }
-                if (!dup) j.o.emplace_back(std::move(k), std::move(v));
+                if (j.o.empty()) j.o.reserve(8);
+                j.o.emplace_back(std::move(k), value(depth + 1));
                 ws();
                 if (p < e && *p == ',') { p++; continue; }
                 if (p < e && *p == '}') { p++; return j; }

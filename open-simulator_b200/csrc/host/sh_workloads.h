@@ -168,7 +168,6 @@ struct Expander {
         std::string preset = field_str(spec_of(valid), "nodeName");
         PodTemplate *t = new_template(std::move(valid), wl_kind, name_of(owner), ns);
         std::string base = name_of(owner);
-        out.reserve(out.size() + (size_t)count);
         for (long long i = 0; i < count; i++) {
             PodRec r;
             r.tmpl = t;
