@@ -14,6 +14,7 @@
 // with SIMON_ERR_CUDA when no device opens.
 #include <chrono>
 #include <cstdio>
+#include <thread>
 
 #include "host/sh_compiler.h"
 
@@ -259,7 +260,21 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         std::vector<int32_t> out_node(std::max(P, 1u), -9);
         std::vector<uint32_t> fail_counts((size_t)std::max(P, 1u) * SIMON_N_FAIL_CODES, 0), fail_pod(std::max(P, 1u), 0);
         uint32_t n_fail = 0;
-        check(simon_schedule(ctx, 0, P, out_node.data(), nullptr, fail_counts.data(), fail_pod.data(), P, &n_fail));
+        // the host is idle while the placement kernel runs: the part of the result that does not depend on the placements (identity of
+        // every pod) is written meanwhile.  One call at a time per ctx: the worker thread is the only one touching it until join()
+        std::string pods_json;
+        {
+            int sched_rc = SIMON_OK;
+            std::thread worker([&] {
+                sched_rc = simon_schedule(ctx, 0, P, out_node.data(), nullptr, fail_counts.data(), fail_pod.data(), P, &n_fail);
+            });
+            try {
+                pods_json.reserve((size_t)P * 40 + 4096);
+                describe_pods(pods_json, p);
+            } catch (...) { worker.join(); throw; }
+            worker.join();
+            check(sched_rc);
+        }
         if (n_fail > P) n_fail = P;
         double t_sched = now_s();
         // Open-Gpu-Share's failure reason names the node, so the histogram needs the node LIST of such pods: re-evaluate a bounded
@@ -284,8 +299,10 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
                 gpu_fail_nodes.emplace(pod, std::move(names));
             }
         }
-        simon_ctx_destroy(ctx);
+        // releasing the device buffers (cudaFree synchronises) overlaps with building the result
+        std::thread closer([c2 = ctx] { simon_ctx_destroy(c2); });
         ctx = nullptr;
+        struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{closer};
         double t_close = now_s();
 
         // ---- SimulateResult ----
@@ -331,7 +348,8 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
             res.push_back(']');
         }
         res += "],\"unscheduledPods\":" + unsched + ",";
-        describe_pods(res, p);
+        res += pods_json;
+        closer.join();
         double t_result = now_s();
         char tb[512];
         snprintf(tb, sizeof tb,

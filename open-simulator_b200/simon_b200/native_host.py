@@ -141,10 +141,16 @@ def simulate_native(cluster: ResourceTypes, apps: List[AppResource], device: int
     opts = abi.SimonCtxOpts(device, 0, 0, 0)
     out = C.c_void_p()
     n = C.c_uint64(0)
+    import time
+    t0 = time.perf_counter()
     rc = L.simon_host_simulate(req, len(req), C.byref(opts), C.byref(out), C.byref(n))
+    simulate_native.last_call_s = time.perf_counter() - t0        # wall clock of the C-ABI call itself
     if rc != 0:
         raise NativeHostError(rc, (L.simon_host_last_error() or b"").decode())
     try:
-        return json.loads(C.string_at(out, n.value).decode())
+        t0 = time.perf_counter()
+        res = json.loads(C.string_at(out, n.value).decode())
+        simulate_native.last_decode_s = time.perf_counter() - t0
+        return res
     finally:
         L.simon_host_free(out)
