@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -16,19 +17,60 @@
 
 namespace {
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold raised, so the blocks a
+// destroyed context frees stay cached for the next one: a Simulate() call creates and destroys a context, and cudaMalloc / cudaFree of
+// its ~40 buffers (some of 10-100 MB) measured anywhere between 3 ms and 1.3 s per call.  The semantics the rest of the file relies on
+// are those of cudaMalloc / cudaFree: an allocation is usable on any stream when pool_alloc returns (the allocation stream is
+// synchronised), and pool_free waits for the device first, as cudaFree does implicitly.
+static cudaStream_t g_pool_stream[64];
+static bool g_pool_ready[64];
+static cudaError_t pool_stream(cudaStream_t *out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!g_pool_ready[dev]) {
+        e = cudaStreamCreateWithFlags(&g_pool_stream[dev], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        g_pool_ready[dev] = true;
+    }
+    *out = g_pool_stream[dev];
+    return cudaSuccess;
+}
+static cudaError_t pool_alloc(void **p, size_t bytes) {
+    cudaStream_t s;
+    cudaError_t e = pool_stream(&s);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocAsync(p, bytes, s);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);
+}
+static void pool_free(void *p) {
+    cudaStream_t s;
+    if (pool_stream(&s) != cudaSuccess) { cudaFree(p); return; }
+    cudaDeviceSynchronize();
+    if (cudaFreeAsync(p, s) != cudaSuccess) cudaFree(p);
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0, cap = 0;
-    // buffers are reused across uploads of the same (or a smaller) shape: cudaFree synchronises the device and
-    // cudaMalloc of the large per-(class, node) caches is slow, both would sit inside every end-to-end call
+    // buffers are reused across uploads of the same (or a smaller) shape
     cudaError_t alloc(size_t count) {
         const size_t want = count ? count : 1;
         if (p && want <= cap) { n = count; return cudaSuccess; }
         release();
         n = count;
         cap = want;
-        return cudaMalloc((void **)&p, want * sizeof(T));
+        return pool_alloc((void **)&p, want * sizeof(T));
     }
     cudaError_t upload(const T *h, size_t count, cudaStream_t st) {
         cudaError_t e = alloc(count);
@@ -37,7 +79,7 @@ struct DevBuf {
         return cudaSuccess;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
         cap = 0;

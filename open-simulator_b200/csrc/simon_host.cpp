@@ -253,7 +253,9 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         simon_podset ps;
         c.snapshot(snap);
         c.podset(ps);
+        double t_ctx = now_s();
         check(simon_snapshot_upload(ctx, &snap));
+        double t_snap = now_s();
         check(simon_pods_upload(ctx, &ps));
         double t_upload = now_s();
         const uint32_t P = c.P;
@@ -351,12 +353,13 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         res += pods_json;
         closer.join();
         double t_result = now_s();
-        char tb[512];
+        char tb[768];
         snprintf(tb, sizeof tb,
                  ",\"timing\":{\"parse_s\":%.6f,\"plan_s\":%.6f,\"compile_s\":%.6f,\"engine_create_upload_s\":%.6f,\"schedule_s\":%.6f,"
-                 "\"gpu_fail_detail_and_close_s\":%.6f,\"build_result_s\":%.6f,\"total_s\":%.6f,\"classes\":%u,\"pods\":%u,\"nodes\":%u}}",
+                 "\"gpu_fail_detail_s\":%.6f,\"build_result_and_close_s\":%.6f,\"total_s\":%.6f,\"ctx_create_s\":%.6f,\"snapshot_upload_s\":%.6f,"
+                 "\"pods_upload_s\":%.6f,\"classes\":%u,\"pods\":%u,\"nodes\":%u}}",
                  t_parse - t0, t_plan - t_parse, t_compile - t_plan, t_upload - t_compile, t_sched - t_upload, t_close - t_sched,
-                 t_result - t_close, t_result - t0, c.C, c.P, c.N);
+                 t_result - t_close, t_result - t0, t_ctx - t_compile, t_snap - t_ctx, t_upload - t_snap, c.C, c.P, c.N);
         res += tb;
         char *buf = (char *)malloc(res.size() + 1);
         if (!buf) throw Error("out of memory", SIMON_ERR_NOMEM);
