@@ -386,6 +386,10 @@ const char *simon_host_plan_describe(simon_host_plan *plan);
  *    templates / podTemplate / podName / podOrdinal / podApp / apps / segments, "timing": {seconds per phase}} */
 int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_opts *opts, char **out_json, uint64_t *out_len);
 void simon_host_free(void *p);
+/* parity instrumentation (no device): the FitError text (generic_scheduler.go:72-90 + simulator.go:465) simon_host_simulate reports for
+ * pod `pod` of the plan given the engine's failure histogram of that pod (counts[SIMON_N_FAIL_CODES]; NULL = node-static reasons only);
+ * *out is malloc'ed (simon_host_free). */
+int simon_host_plan_fit_error(simon_host_plan *plan, uint32_t pod, const uint32_t *counts, char **out);
 /* parity instrumentation: resource.ParseQuantity of `text` (vendor/k8s.io/apimachinery/pkg/api/resource/quantity.go:247-372) ->
  * Value(), MilliValue(), AsApproximateFloat64(); either output may be NULL.  No placement depends on it. */
 int simon_host_quantity_probe(const char *text, int64_t *value, int64_t *milli_value, double *approx);

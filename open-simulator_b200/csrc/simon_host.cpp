@@ -60,15 +60,58 @@ static void reason_add(Reasons &r, const std::string &k, long long v) {
 
 // reason histogram of the node-static filters (NodeUnschedulable, NodeName, TaintToleration, NodeAffinity), evaluated on the objects:
 // the taint reason names the first untolerated taint of each node, which the device's verdict code does not carry
-static Reasons static_reasons(const Compiled &c, const PodRec &rec) {
+struct NodeStaticKeys {      // per node, once per result: "unschedulable + taints" as a small id (what every template looks at)
+    std::vector<int> base;
+    bool ready = false;
+    void build(const Compiled &c) {
+        std::unordered_map<std::string, int> ids;
+        base.resize(c.N);
+        for (uint32_t i = 0; i < c.N; i++) {
+            const J &nspec = spec_of(*c.node_objs[i]);
+            std::string k;
+            const J *un = nspec.get("unschedulable");
+            k.push_back((un && un->truthy()) ? '1' : '0');
+            dump_opt(k, nspec.get("taints"));
+            base[i] = ids.emplace(std::move(k), (int)ids.size()).first->second;
+        }
+        ready = true;
+    }
+};
+
+static Reasons static_reasons(const Compiled &c, const PodRec &rec, NodeStaticKeys &nk) {
     Reasons out;
     const J &spec = rec.tmpl->spec();
     const J &tols = field_arr(spec, "tolerations");
     std::string pod_nn = field_str(spec, "nodeName");
-    // nodes that agree on (unschedulable, taints, referenced labels) share the verdict; evaluating per node is cheap enough in native code
+    // The verdict of a node depends on its unschedulable flag, its taints and the labels the pod's nodeSelector / required node-affinity
+    // expressions mention: nodes that agree on those share it.  matchFields (node names) and spec.nodeName defeat the grouping.
+    std::vector<std::string> keys;
+    bool by_name = !pod_nn.empty();
+    for (auto &kv : field_obj(spec, "nodeSelector").o) keys.push_back(kv.first);
+    const J &req = field_obj(field_obj(field_obj(spec, "affinity"), "nodeAffinity"), "requiredDuringSchedulingIgnoredDuringExecution");
+    for (auto &term : field_arr(req, "nodeSelectorTerms").a) {
+        if (!field_arr(term, "matchFields").a.empty()) by_name = true;
+        for (auto &e : field_arr(term, "matchExpressions").a) { const J *k = e.get("key"); keys.push_back(k ? k->text() : std::string()); }
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    if (!nk.ready) nk.build(c);
+    std::unordered_map<std::string, int> memo;      // group key -> index into group_reason
+    std::vector<std::string> group_reason;
+    std::string gk;
     for (uint32_t i = 0; i < c.N; i++) {
         const J &node = *c.node_objs[i];
         const J &nspec = spec_of(node);
+        if (!by_name) {
+            gk.assign(std::to_string(nk.base[i]));
+            const J &labels = labels_of(node);
+            for (auto &k : keys) { gk.push_back('\x01'); const J *v = labels.get(k); if (v) dump(gk, *v); else gk.push_back('\x02'); }
+            auto it = memo.find(gk);
+            if (it != memo.end()) {
+                if (!group_reason[(size_t)it->second].empty()) reason_add(out, group_reason[(size_t)it->second], 1);
+                continue;
+            }
+        }
         std::string r;
         const J *un = nspec.get("unschedulable");
         if (un && un->truthy() && !tolerations_tolerate_taint(tols, Taint{"node.kubernetes.io/unschedulable", "", "NoSchedule"}))
@@ -87,15 +130,16 @@ static Reasons static_reasons(const Compiled &c, const PodRec &rec) {
             }
             if (r.empty() && !pod_matches_node_selector_and_affinity(spec, node)) r = "node(s) didn't match Pod's node affinity";
         }
+        if (!by_name) { memo.emplace(gk, (int)group_reason.size()); group_reason.push_back(r); }
         if (!r.empty()) reason_add(out, r, 1);
     }
     return out;
 }
 
 static std::string format_fit_error(const Compiled &c, const PodRec &rec, const uint32_t *counts, const std::vector<std::string> *gpu_nodes,
-                                    std::unordered_map<const PodTemplate *, Reasons> &static_memo) {
+                                    std::unordered_map<const PodTemplate *, Reasons> &static_memo, NodeStaticKeys &nk) {
     auto it = static_memo.find(rec.tmpl);
-    if (it == static_memo.end()) it = static_memo.emplace(rec.tmpl, static_reasons(c, rec)).first;
+    if (it == static_memo.end()) it = static_memo.emplace(rec.tmpl, static_reasons(c, rec, nk)).first;
     Reasons reasons = it->second;
     for (auto &d : kDynamicReasons) {
         long long n = counts[d.code];
@@ -211,6 +255,25 @@ const char *simon_host_plan_describe(simon_host_plan *p) {
 
 void simon_host_free(void *p) { free(p); }
 
+// Parity instrumentation (no device): the FitError text simon_host_simulate would report for pod `pod` of the plan, given the per-pod
+// failure histogram of the engine (counts[SIMON_N_FAIL_CODES]; NULL = all zero: node-static reasons only).  *out is malloc'ed.
+int simon_host_plan_fit_error(simon_host_plan *p, uint32_t pod, const uint32_t *counts, char **out) {
+    if (!p || !out || pod >= p->plan.pods.size()) { g_host_error = "bad argument"; return SIMON_ERR_INVALID; }
+    try {
+        static const uint32_t zero[SIMON_N_FAIL_CODES] = {0};
+        std::unordered_map<const PodTemplate *, Reasons> memo;
+        NodeStaticKeys nk;
+        std::string msg = format_fit_error(p->comp, p->plan.pods[pod], counts ? counts : zero, nullptr, memo, nk);
+        char *buf = (char *)malloc(msg.size() + 1);
+        if (!buf) return SIMON_ERR_NOMEM;
+        memcpy(buf, msg.c_str(), msg.size() + 1);
+        *out = buf;
+        return SIMON_OK;
+    } catch (const std::exception &e) {
+        return fail(e);
+    }
+}
+
 int simon_host_quantity_probe(const char *text, int64_t *value, int64_t *milli_value, double *approx) {
     if (!text) { g_host_error = "null argument"; return SIMON_ERR_INVALID; }
     try {
@@ -235,7 +298,13 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
     simon_ctx *ctx = nullptr;
     try {
         double t0 = now_s();
-        simon_host_plan hp;
+        // the object tree of a large request takes tens of milliseconds to tear down: the plan lives on the heap and is released by a
+        // background thread after the result has been handed over
+        struct PlanHolder {
+            simon_host_plan *p = new simon_host_plan();
+            ~PlanHolder() { if (p) { simon_host_plan *q = p; std::thread([q] { delete q; }).detach(); } }
+        } holder;
+        simon_host_plan &hp = *holder.p;
         hp.plan.request = parse_json(request_json, (size_t)len);
         double t_parse = now_s();
         make_plan(hp.plan);
@@ -314,6 +383,7 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         std::unordered_map<uint32_t, uint32_t> fail_idx;
         for (uint32_t j = 0; j < n_fail; j++) fail_idx[fail_pod[j]] = j;
         std::unordered_map<const PodTemplate *, Reasons> static_memo;
+        NodeStaticKeys node_keys;
         std::string res;
         res.reserve((size_t)P * 48 + 4096);
         res += "{\"nodes\":[";
@@ -336,7 +406,7 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
                     auto g = gpu_fail_nodes.find(i);
                     if (unsched.size() > 1) unsched.push_back(',');
                     unsched += "{\"pod\":" + std::to_string(i) + ",\"reason\":";
-                    dump_str(unsched, format_fit_error(c, p.pods[i], counts, g != gpu_fail_nodes.end() ? &g->second : nullptr, static_memo));
+                    dump_str(unsched, format_fit_error(c, p.pods[i], counts, g != gpu_fail_nodes.end() ? &g->second : nullptr, static_memo, node_keys));
                     unsched += "}";
                 }
             }

@@ -75,7 +75,7 @@ def _kat_inputs(kat):
 def test_native_host_symbols_are_exported():
     L = native_host.lib()
     for name in ("simon_host_compile", "simon_host_plan_free", "simon_host_plan_columns", "simon_host_plan_describe",
-                 "simon_host_simulate", "simon_host_free", "simon_host_last_error", "simon_host_quantity_probe"):
+                 "simon_host_simulate", "simon_host_free", "simon_host_last_error", "simon_host_quantity_probe", "simon_host_plan_fit_error"):
         assert hasattr(L, name)
 
 
@@ -199,6 +199,55 @@ def test_native_refusals_match_the_python_compiler():
     with pytest.raises(native_host.NativeHostError) as e:
         native_host.compile_native(cluster, [AppResource("x", ResourceTypes(Pods=[{"kind": "Pod", "metadata": {"name": "e"}, "spec": {}}]))])
     assert "spec.containers" in e.value.msg
+
+
+@pytest.mark.parametrize("seed", [5, 101, 104, 107, 110, 113])
+def test_native_failure_messages_match_the_python_mirror(seed):
+    """FitError text for every pod of a mixed cluster (taints, node selectors / affinity incl. matchFields, cordoned nodes), with an
+    empty and with a synthetic dynamic histogram: simon_host_plan_fit_error == simulator.format_fit_error."""
+    cluster, apps = synth.make_mix(seed_no=seed, n_nodes=40, n_workloads=25, max_replicas=3)
+    cluster.Nodes[3].setdefault("spec", {})["unschedulable"] = True
+    names = [n["metadata"]["name"] for n in cluster.Nodes]
+    base = {"containers": [{"name": "c", "image": "x", "resources": {"requests": {"cpu": "100m"}}}]}
+    R = "requiredDuringSchedulingIgnoredDuringExecution"
+    extra = [
+        # matchFields (node names) and spec.nodeName defeat the per-node-group memo of the native path
+        {"kind": "Pod", "metadata": {"name": "by-field", "namespace": "default"}, "spec": dict(base, affinity={"nodeAffinity": {R: {
+            "nodeSelectorTerms": [{"matchFields": [{"key": "metadata.name", "operator": "In", "values": [names[5]]}]},
+                                  {"matchExpressions": [{"key": "kubernetes.io/hostname", "operator": "NotIn", "values": names[:7]}]}]}}})},
+        {"kind": "Pod", "metadata": {"name": "by-name", "namespace": "default"}, "spec": dict(base, nodeName=names[2])},
+        {"kind": "Pod", "metadata": {"name": "tolerant", "namespace": "default"}, "spec": dict(
+            base, tolerations=[{"operator": "Exists"}], nodeSelector={"no-such-label": "x"})},
+        {"kind": "Pod", "metadata": {"name": "cordon-ok", "namespace": "default"}, "spec": dict(
+            base, tolerations=[{"key": "node.kubernetes.io/unschedulable", "operator": "Exists", "effect": "NoSchedule"}])},
+    ]
+    apps.append(AppResource("extra", ResourceTypes(Pods=extra)))
+    p = simulator.plan(cluster, apps)
+    c = compile_cluster(p.nodes, p.pods, p.ctx)
+    L = native_host.lib()
+    L.simon_host_plan_fit_error.restype = C.c_int
+    L.simon_host_plan_fit_error.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
+    req = native_host.request_json(cluster, apps)
+    h = C.c_void_p()
+    assert L.simon_host_compile(req, len(req), C.byref(h)) == 0
+    try:
+        counts = np.zeros(24, np.uint32)
+        counts[[1, 2, 3, 4, 5, 14, 15, 16, 17, 18]] = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+        for k in range(len(c.scalar_names)):
+            counts[6 + k] = 11 + k
+        seen = set()
+        for i, rec in enumerate(p.pods):
+            if id(rec.tmpl) in seen:
+                continue
+            seen.add(id(rec.tmpl))
+            for cnt in (np.zeros(24, np.uint32), counts):
+                out = C.c_void_p()
+                assert L.simon_host_plan_fit_error(h, i, cnt.ctypes.data, C.byref(out)) == 0
+                got = C.string_at(out).decode()
+                L.simon_host_free(out)
+                assert got == simulator.format_fit_error(c, rec, cnt)
+    finally:
+        L.simon_host_plan_free(h)
 
 
 def test_native_simulate_needs_a_device():
