@@ -349,10 +349,26 @@ def block_capacity(args, rank, world, local, dist, torch):
     dt, kernel_ms = float(tt[0].item()), float(tt[1].item())
     dec = capacity.decode_key(best)
     pods_per_scen = int((ss.compiled.pods["pod_fixed_node"] == -1).sum())
+    # the same search through the native host side (simon_host_capacity_search: objects as JSON in -> per-scenario results + packed key
+    # out; C++ superset expansion + compile + scenario lists + the launch), this rank's shard, wall clock of the whole call
+    native = None
+    try:
+        from simon_b200 import native_host as _nh
+        _nh.capacity_search_native(cluster, apps, specs, list(range(1, 33)), device=local, rank=rank, world=world)      # warm-up
+        t1 = time.perf_counter()
+        nat = _nh.capacity_search_native(cluster, apps, specs, list(range(1, 33)), device=local, rank=rank, world=world)
+        nat_s = time.perf_counter() - t1
+        key = nat["bestKey"]
+        if reduce_fn is not None:
+            key = reduce_fn(int(key))
+        native = {"call_s_incl_request_encoding": nat_s, "library_timing": nat["timing"], "same_answer": bool(int(key) == int(best))}
+    except Exception as e:       # noqa: BLE001
+        native = {"error": f"{type(e).__name__}: {e}"[:200]}
     return {"workload": "C4: 2000-node base ~85 % full, 5000 pending pods, 8 node specs x k = 1..32 -> 256 scenarios",
             "scenarios": len(ss.scenarios), "n_gpus": world, "search_s": dt, "kernel_ms_max_rank": kernel_ms, "host_build_s": t_build,
             "best": dec, "best_spec": (ss.scenarios[dec["scenario"]].spec if dec else None),
             "decisions_per_s": len(ss.scenarios) * pods_per_scen / dt, "scheduled_pods_per_scenario": pods_per_scen,
+            "native_host": native,
             "collective": "one all_reduce(MIN) of an int64 key (k << 32 | scenario) over NCCL, inside search_s" if world > 1 else "none (single process)",
             "timing": "best of 3 searches, wall clock per rank (includes the scenario-list uploads, the launch, the result download "
                       "and the collective), max over ranks"}

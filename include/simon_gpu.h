@@ -386,6 +386,14 @@ const char *simon_host_plan_describe(simon_host_plan *plan);
  *    templates / podTemplate / podName / podOrdinal / podApp / apps / segments, "timing": {seconds per phase}} */
 int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_opts *opts, char **out_json, uint64_t *out_len);
 void simon_host_free(void *p);
+/* Capacity planning: the add-node search of `simon apply` (pkg/apply/apply.go:203-259, one full Simulate() per candidate node count
+ * typed by the user) as ONE batch of what-if scenarios.  request = {"cluster", "apps", "newNodes": [Node spec...], "ks": [k...],
+ * "maxCPU", "maxMemory" (satisfyResourceSetting caps, apply.go:689-775), "rank", "world" (scenarios sid % world == rank run here),
+ * "dryRun"}: a superset cluster holds the base nodes + max(ks) copies of every spec (utils.NewFakeNodes, pkg/utils/utils.go:885-901);
+ * scenario (spec, k) activates base + the first k copies in its own nodeTree.list() order.  *out_json (malloc'ed): {"scenarios":
+ * [{sid, spec, k, n_unscheduled, n_scheduled, req/alloc sums, feasible} | {sid, spec, k, nodes} when dryRun], "bestKey": (k << 32 | sid)
+ * of the best local scenario or 2^62, "nodeNames", "nBase", "timing"}; ranks combine bestKey with ONE all-reduce(MIN). */
+int simon_host_capacity_search(const char *request_json, uint64_t len, const simon_ctx_opts *opts, char **out_json, uint64_t *out_len);
 /* parity instrumentation (no device): the FitError text (generic_scheduler.go:72-90 + simulator.go:465) simon_host_simulate reports for
  * pod `pod` of the plan given the engine's failure histogram of that pod (counts[SIMON_N_FAIL_CODES]; NULL = node-static reasons only);
  * *out is malloc'ed (simon_host_free). */

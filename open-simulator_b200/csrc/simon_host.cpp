@@ -14,6 +14,7 @@
 // with SIMON_ERR_CUDA when no device opens.
 #include <chrono>
 #include <cstdio>
+#include <memory>
 #include <thread>
 
 #include "host/sh_compiler.h"
@@ -436,6 +437,160 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         memcpy(buf, res.data(), res.size() + 1);
         *out_json = buf;
         if (out_len) *out_len = res.size();
+        return SIMON_OK;
+    } catch (const std::exception &e) {
+        if (ctx) simon_ctx_destroy(ctx);
+        return fail(e);
+    }
+}
+
+// ---- capacity planning: the add-node search of `simon apply` (pkg/apply/apply.go:203-259) as one batch of what-if scenarios ----------
+// request = {"cluster": ResourceTypes, "apps": [...], "newNodes": [Node spec, ...], "ks": [k, ...], "maxCPU": 0..100, "maxMemory": 0..100,
+//            "rank": r, "world": w, "dryRun": bool}
+// One compiled superset cluster holds the base nodes plus max(ks) copies of every candidate spec (utils.NewFakeNodes,
+// pkg/utils/utils.go:885-901, incl. its mutation of the template across copies); scenario (spec s, k) activates the base nodes and the
+// first k copies of spec s in ITS OWN nodeTree.list() order; DaemonSet pods exist only where their node does.  A trial is accepted when no
+// pod is left unscheduled and satisfyResourceSetting holds (apply.go:689-775, CPU and memory parts).  Scenarios sid % world == rank are
+// run on the device (one thread-block cluster each, simon_scenarios_run); the caller reduces "bestKey" = (k << 32 | sid), or 2^62 when no
+// local scenario is feasible, with ONE all-reduce(MIN) across ranks.  dryRun: no device work, the scenario node lists only.
+static J make_valid_node(J &work, const std::string &name) {     // utils.MakeValidNodeByNode: mutates AND returns the template
+    J *md = work.getm("metadata");
+    if (!md || !md->is_obj()) md = &work.set("metadata", J::obj());
+    md->set("name", J::str(name));
+    const J *lb = md->get("labels");
+    if (!present(lb)) md->set("labels", J::obj());
+    else md->getm("labels")->set(LABEL_HOSTNAME, J::str(name));      // the hostname label is set only when Labels != nil
+    const J *an = md->get("annotations");
+    if (!present(an)) md->set("annotations", J::obj());
+    md->erase("managedFields");
+    md->getm("labels")->set(LABEL_NEW_NODE, J::str(""));
+    return work;
+}
+
+int simon_host_capacity_search(const char *request_json, uint64_t len, const simon_ctx_opts *opts, char **out_json, uint64_t *out_len) {
+    if (!request_json || !out_json) { g_host_error = "null argument"; return SIMON_ERR_INVALID; }
+    *out_json = nullptr;
+    simon_ctx *ctx = nullptr;
+    try {
+        double t0 = now_s();
+        std::unique_ptr<simon_host_plan> hp(new simon_host_plan());
+        Plan &p = hp->plan;
+        p.request = parse_json(request_json, (size_t)len);
+        J *cl = p.request.getm("cluster");
+        if (!cl || !cl->is_obj()) throw Error("request: missing \"cluster\" object");
+        std::vector<long long> ks;
+        for (auto &k : field_arr(p.request, "ks").a) ks.push_back(k.as_int(0));
+        long long kmax = 0;
+        for (long long k : ks) { if (k < 0) throw Error("request: negative k"); kmax = std::max(kmax, k); }
+        const J &specs = field_arr(p.request, "newNodes");
+        auto cap = [&](const char *name) {
+            const J *v = p.request.get(name);
+            long long x = present(v) ? v->as_int(100) : 100;
+            return (x > 100 || x < 0) ? 100LL : x;          // EnvMaxCPU / EnvMaxMemory: out-of-range values fall back to 100
+        };
+        const long long max_cpu = cap("maxCPU"), max_mem = cap("maxMemory");
+        const J *rj = p.request.get("rank"), *wj = p.request.get("world"), *dj = p.request.get("dryRun");
+        long long world = present(wj) ? std::max<long long>(1, wj->as_int(1)) : 1, rank = present(rj) ? rj->as_int(0) : 0;
+        bool dry = dj && dj->truthy();
+        // superset node list: base + pool
+        J *nodes_j = cl->getm("Nodes");
+        if (!nodes_j || !nodes_j->is_arr()) nodes_j = &cl->set("Nodes", J::arr());
+        const size_t nb = nodes_j->a.size();
+        nodes_j->a.reserve(nb + specs.a.size() * (size_t)kmax);
+        for (size_t si = 0; si < specs.a.size(); si++) {
+            J work = specs.a[si];
+            for (long long i = 0; i < kmax; i++) {
+                char nm[64];
+                snprintf(nm, sizeof nm, "simon-%02zu-%05lld", si, i);
+                nodes_j->a.push_back(make_valid_node(work, nm));
+            }
+        }
+        make_plan(p);
+        compile_cluster(p, hp->comp);
+        const Compiled &c = hp->comp;
+        double t_compile = now_s();
+        std::vector<int> orig_to_compiled(p.nodes.size(), -1);
+        for (uint32_t ci = 0; ci < c.N; ci++) orig_to_compiled[(size_t)c.node_orig_index[ci]] = (int)ci;
+        struct Scen { uint32_t sid, spec; long long k; std::vector<uint32_t> nodes; };
+        std::vector<Scen> scen;
+        for (size_t si = 0; si < specs.a.size(); si++)
+            for (long long k : ks) {
+                std::vector<const J *> sub;
+                std::vector<size_t> members;
+                for (size_t m = 0; m < nb; m++) members.push_back(m);
+                for (long long i = 0; i < k; i++) members.push_back(nb + si * (size_t)kmax + (size_t)i);
+                for (size_t m : members) sub.push_back(p.nodes[m]);
+                Scen sc{(uint32_t)scen.size(), (uint32_t)si, k, {}};
+                for (int o : node_tree_list(sub)) {
+                    int ci = orig_to_compiled[members[(size_t)o]];
+                    if (ci < 0) throw Error("duplicate node name in the superset cluster");
+                    sc.nodes.push_back((uint32_t)ci);
+                }
+                scen.push_back(std::move(sc));
+            }
+        std::vector<const Scen *> shard;
+        for (auto &sc : scen) if ((long long)(sc.sid % world) == rank) shard.push_back(&sc);
+        std::vector<simon_scenario_result> res(std::max<size_t>(1, shard.size()));
+        double t_scen = now_s(), t_run = t_scen;
+        float kernel_ms = 0;
+        if (!dry && !shard.empty()) {
+            simon_ctx_opts o{};
+            if (opts) o = *opts;
+            int rc = simon_ctx_create(&o, &ctx);
+            if (rc != SIMON_OK || !ctx) throw Error("simon_ctx_create failed: no usable CUDA device; the engine has no CPU path", rc ? rc : SIMON_ERR_CUDA);
+            auto check = [&](int r) { if (r != SIMON_OK) throw Error(std::string("engine: ") + simon_last_error(ctx), r); };
+            simon_snapshot snap;
+            simon_podset ps;
+            c.snapshot(snap);
+            c.podset(ps);
+            check(simon_snapshot_upload(ctx, &snap));
+            check(simon_pods_upload(ctx, &ps));
+            std::vector<simon_scenario> sl(shard.size());
+            for (size_t i = 0; i < shard.size(); i++) { sl[i].n_nodes = (uint32_t)shard[i]->nodes.size(); sl[i].reserved = 0; sl[i].nodes = shard[i]->nodes.data(); }
+            check(simon_scenarios_run(ctx, sl.data(), (uint32_t)sl.size(), res.data(), nullptr));
+            kernel_ms = simon_last_kernel_ms(ctx);
+            simon_ctx_destroy(ctx);
+            ctx = nullptr;
+            t_run = now_s();
+        }
+        const unsigned long long INFEASIBLE = 1ull << 62;
+        unsigned long long best = INFEASIBLE;
+        std::string out = "{\"nBase\":" + std::to_string(nb) + ",\"nodeNames\":";
+        json_str_array(out, c.node_names);
+        out += ",\"scenarios\":[";
+        bool first = true;
+        for (size_t i = 0; i < shard.size(); i++) {
+            const Scen &sc = *shard[i];
+            if (!first) out.push_back(',');
+            first = false;
+            out += "{\"sid\":" + std::to_string(sc.sid) + ",\"spec\":" + std::to_string(sc.spec) + ",\"k\":" + std::to_string(sc.k);
+            if (dry) {
+                out += ",\"nodes\":[";
+                for (size_t q = 0; q < sc.nodes.size(); q++) { if (q) out.push_back(','); out += std::to_string(sc.nodes[q]); }
+                out += "]";
+            } else {
+                const simon_scenario_result &r = res[i];
+                bool ok = r.n_unscheduled == 0;
+                if (ok && r.alloc_mcpu > 0 && (long long)((double)r.req_mcpu / (double)r.alloc_mcpu * 100) > max_cpu) ok = false;
+                if (ok && r.alloc_mem > 0 && (long long)((double)r.req_mem / (double)r.alloc_mem * 100) > max_mem) ok = false;
+                unsigned long long key = ok ? (((unsigned long long)sc.k << 32) | sc.sid) : INFEASIBLE;
+                best = std::min(best, key);
+                out += ",\"n_unscheduled\":" + std::to_string(r.n_unscheduled) + ",\"n_scheduled\":" + std::to_string(r.n_scheduled) +
+                       ",\"req_mcpu\":" + std::to_string(r.req_mcpu) + ",\"alloc_mcpu\":" + std::to_string(r.alloc_mcpu) +
+                       ",\"req_mem\":" + std::to_string(r.req_mem) + ",\"alloc_mem\":" + std::to_string(r.alloc_mem) +
+                       ",\"feasible\":" + (ok ? "true" : "false");
+            }
+            out += "}";
+        }
+        char tb[384];
+        snprintf(tb, sizeof tb, "],\"bestKey\":%llu,\"nScenarios\":%zu,\"timing\":{\"compile_s\":%.6f,\"scenario_lists_s\":%.6f,\"run_s\":%.6f,"
+                 "\"kernel_ms\":%.3f,\"total_s\":%.6f}}", best, scen.size(), t_compile - t0, t_scen - t_compile, t_run - t_scen, (double)kernel_ms, now_s() - t0);
+        out += tb;
+        char *buf = (char *)malloc(out.size() + 1);
+        if (!buf) throw Error("out of memory", SIMON_ERR_NOMEM);
+        memcpy(buf, out.data(), out.size() + 1);
+        *out_json = buf;
+        if (out_len) *out_len = out.size();
         return SIMON_OK;
     } catch (const std::exception &e) {
         if (ctx) simon_ctx_destroy(ctx);

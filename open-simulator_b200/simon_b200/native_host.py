@@ -45,6 +45,8 @@ def lib():
     L.simon_host_simulate.restype = C.c_int
     L.simon_host_simulate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.simon_host_free.argtypes = [C.c_void_p]
+    L.simon_host_capacity_search.restype = C.c_int
+    L.simon_host_capacity_search.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _LIB = L
     return L
 
@@ -152,5 +154,26 @@ def simulate_native(cluster: ResourceTypes, apps: List[AppResource], device: int
         res = json.loads(C.string_at(out, n.value).decode())
         simulate_native.last_decode_s = time.perf_counter() - t0
         return res
+    finally:
+        L.simon_host_free(out)
+
+
+def capacity_search_native(cluster: ResourceTypes, apps: List[AppResource], specs: List[dict], ks: List[int], device: int = 0, rank: int = 0,
+                           world: int = 1, max_cpu: int = 100, max_mem: int = 100, dry_run: bool = False) -> Dict:
+    """The add-node search of `simon apply` (pkg/apply/apply.go:203-259) through simon_host_capacity_search: this rank's shard of the
+    (spec, k) scenarios; combine "bestKey" across ranks with one all-reduce(MIN) (capacity.torch_all_reduce_min)."""
+    L = lib()
+    req = json.loads(request_json(cluster, apps))
+    req.update({"newNodes": list(specs), "ks": [int(k) for k in ks], "maxCPU": int(max_cpu), "maxMemory": int(max_mem),
+                "rank": int(rank), "world": int(world), "dryRun": bool(dry_run)})
+    raw = json.dumps(req, separators=(",", ":")).encode("utf-8")
+    opts = abi.SimonCtxOpts(device, 0, 0, 0)
+    out = C.c_void_p()
+    n = C.c_uint64(0)
+    rc = L.simon_host_capacity_search(raw, len(raw), C.byref(opts), C.byref(out), C.byref(n))
+    if rc != 0:
+        raise NativeHostError(rc, (L.simon_host_last_error() or b"").decode())
+    try:
+        return json.loads(C.string_at(out, n.value).decode())
     finally:
         L.simon_host_free(out)

@@ -75,7 +75,7 @@ def _kat_inputs(kat):
 def test_native_host_symbols_are_exported():
     L = native_host.lib()
     for name in ("simon_host_compile", "simon_host_plan_free", "simon_host_plan_columns", "simon_host_plan_describe",
-                 "simon_host_simulate", "simon_host_free", "simon_host_last_error", "simon_host_quantity_probe", "simon_host_plan_fit_error"):
+                 "simon_host_simulate", "simon_host_free", "simon_host_last_error", "simon_host_quantity_probe", "simon_host_plan_fit_error", "simon_host_capacity_search"):
         assert hasattr(L, name)
 
 
@@ -306,3 +306,51 @@ def test_native_simulate_gpu_share_failure_names_the_nodes_gpu():
     apps[0].Resource.Pods.append(big)
     res, nat = _simulate_both(cluster, apps)
     assert any("Node:" in u["reason"] for u in nat["unscheduledPods"])
+
+
+def _c4_small():
+    cluster, apps, specs = synth.make_c4(n_nodes=60, n_workloads=6, replicas=12, seed_no=4)
+    specs = specs[:3]
+    # a spec WITHOUT labels: utils.NewFakeNodes mutates its template across copies (pkg/utils/utils.go:890-899), so the first copy has
+    # no hostname label and the later ones do - both host sides must reproduce that
+    bare = {"kind": "Node", "metadata": {"name": "bare-spec"}, "status": dict(specs[0]["status"])}
+    return cluster, apps, specs + [bare]
+
+
+def test_native_capacity_scenarios_match_python():
+    """simon_host_capacity_search (dryRun): superset cluster and per-scenario node lists == capacity.build_scenarios."""
+    import copy
+    from simon_b200 import capacity
+    cluster, apps, specs = _c4_small()
+    ks = [0, 1, 2, 4, 8]
+    ss = capacity.build_scenarios(copy.deepcopy(cluster), copy.deepcopy(apps), copy.deepcopy(specs), ks=ks)
+    nat = native_host.capacity_search_native(cluster, apps, specs, ks, dry_run=True)
+    assert nat["nodeNames"] == list(ss.compiled.node_names) and nat["nBase"] == ss.n_base and nat["nScenarios"] == len(ss.scenarios)
+    assert [(a["sid"], a["spec"], a["k"], a["nodes"]) for a in nat["scenarios"]] == [(b.sid, b.spec, b.k, b.nodes.tolist()) for b in ss.scenarios]
+    shard = native_host.capacity_search_native(cluster, apps, specs, ks, dry_run=True, rank=1, world=3)
+    assert [a["sid"] for a in shard["scenarios"]] == [b.sid for b in ss.scenarios if b.sid % 3 == 1]
+    assert shard["bestKey"] == 1 << 62
+
+
+@pytest.mark.gpu
+def test_native_capacity_search_matches_python_gpu():
+    """Same scenarios, same device results, same packed key as capacity.search with the GPU runner (and so as the oracle, which
+    tests/test_capacity.py pins that path to)."""
+    import copy
+    from simon_b200 import capacity
+    cluster, apps, specs = _c4_small()
+    ks = [0, 1, 2, 4, 8]
+    ss = capacity.build_scenarios(copy.deepcopy(cluster), copy.deepcopy(apps), copy.deepcopy(specs), ks=ks)
+    best, by_sid = capacity.search(ss, capacity.gpu_runner(0), max_cpu=100, max_mem=100)
+    nat = native_host.capacity_search_native(cluster, apps, specs, ks, max_cpu=100, max_mem=100)
+    assert nat["bestKey"] == best
+    for a in nat["scenarios"]:
+        r = by_sid[a["sid"]]
+        assert all(int(a[q]) == int(r[q]) for q in ("n_unscheduled", "n_scheduled", "req_mcpu", "alloc_mcpu", "req_mem", "alloc_mem")), a
+    # two ranks: the MIN of the local keys is the global key
+    k0 = native_host.capacity_search_native(cluster, apps, specs, ks, rank=0, world=2)["bestKey"]
+    k1 = native_host.capacity_search_native(cluster, apps, specs, ks, rank=1, world=2)["bestKey"]
+    assert min(k0, k1) == best
+    # occupancy caps (satisfyResourceSetting) move the answer the same way on both sides
+    best50, _ = capacity.search(ss, capacity.gpu_runner(0), max_cpu=50, max_mem=100)
+    assert native_host.capacity_search_native(cluster, apps, specs, ks, max_cpu=50, max_mem=100)["bestKey"] == best50
