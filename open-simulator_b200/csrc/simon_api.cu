@@ -333,6 +333,25 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
         }
     }
     if (want_cs > SK_MAX_CS) return fail(ctx, SIMON_ERR_LIMIT, "CTAs per scenario must be <= %u (got %u)", (unsigned)SK_MAX_CS, want_cs);
+    if (n_scen <= 1 && !want_cs && !want_t && n_active > 128) {
+        // One scenario alone is latency work, and the per-thread serial work (filter + totals + commit fold per node slot) outweighs
+        // the exchange: ONE node per thread on as many CTAs as that takes beats fewer, fuller CTAs at every size measured
+        // (tools/geom_sweep.py, decisions/s, auto rule before -> after: 600 nodes 157 k -> 210 k with 8 x 128; C2, 1,000 nodes
+        // 232 k -> 298 k with 8 x 128 / 4 x 256; 2,500 nodes 138 k -> 182 k with 16 x 256; 5,000 nodes 150 k -> 187 k with
+        // 16 x 320; a single CTA with CTA-local reductions is slower than 2 or more CTAs from 600 nodes up).  Past 16 x 320 nodes
+        // the slots per thread grow (C3, 10,000 nodes: 16 x 320 x 2, as before).
+        uint32_t cs_p = 0, t_p = 0, npt_p = 0;
+        for (uint32_t cs = 4; cs <= 16 && !cs_p; cs *= 2) {
+            const uint32_t per_cta = (n_active + cs - 1) / cs;
+            if (per_cta <= 256) { cs_p = cs; t_p = std::max(128u, ((per_cta + 31) / 32) * 32); npt_p = 1; }
+        }
+        if (!cs_p) {
+            const uint32_t per_cta = (n_active + 15) / 16, n256 = (per_cta + 255) / 256, n320 = (per_cta + 319) / 320;
+            cs_p = 16; t_p = n320 < n256 ? 320 : 256; npt_p = n320 < n256 ? n320 : n256;
+        }
+        const size_t b = sk_smem_bytes(npt_p * t_p, ctx->T, ctx->emax, ctx->max_blob_words, cs_p);
+        if (npt_p <= 64 && b <= (size_t)max_smem) { CS = cs_p; TPB = t_p; NPT = npt_p; smem = b; return SIMON_OK; }
+    }
     for (uint32_t ci = 0; ci < 5; ci++) {
         uint32_t cs = cs_opts[ci];
         if (want_cs) { if (ci) break; cs = want_cs; }      // an explicit cluster size need not be a power of two (10 = half of a 20-SM GPC)

@@ -513,19 +513,33 @@ int simon_host_capacity_search(const char *request_json, uint64_t len, const sim
         for (uint32_t ci = 0; ci < c.N; ci++) orig_to_compiled[(size_t)c.node_orig_index[ci]] = (int)ci;
         struct Scen { uint32_t sid, spec; long long k; std::vector<uint32_t> nodes; };
         std::vector<Scen> scen;
+        // nodeTree.list() of every scenario's node subset (node_tree_list: zones in first-appearance order, round-robin): the zone of a
+        // node is a property of the node, so it is interned once for the superset
+        for (int ci : orig_to_compiled) if (ci < 0) throw Error("duplicate node name in the superset cluster");
+        std::vector<int> zone_of(p.nodes.size());
+        {
+            Interner zones;
+            for (size_t m = 0; m < p.nodes.size(); m++) zone_of[m] = zones.get(get_zone_key(*p.nodes[m]));
+        }
+        std::vector<int> zslot;
+        std::vector<std::vector<uint32_t>> zlists;
         for (size_t si = 0; si < specs.a.size(); si++)
             for (long long k : ks) {
-                std::vector<const J *> sub;
-                std::vector<size_t> members;
-                for (size_t m = 0; m < nb; m++) members.push_back(m);
-                for (long long i = 0; i < k; i++) members.push_back(nb + si * (size_t)kmax + (size_t)i);
-                for (size_t m : members) sub.push_back(p.nodes[m]);
                 Scen sc{(uint32_t)scen.size(), (uint32_t)si, k, {}};
-                for (int o : node_tree_list(sub)) {
-                    int ci = orig_to_compiled[members[(size_t)o]];
-                    if (ci < 0) throw Error("duplicate node name in the superset cluster");
-                    sc.nodes.push_back((uint32_t)ci);
-                }
+                zslot.assign(p.nodes.size() ? (size_t)(*std::max_element(zone_of.begin(), zone_of.end())) + 1 : 1, -1);
+                zlists.clear();
+                size_t total = 0;
+                auto add = [&](size_t m) {
+                    int &slot = zslot[(size_t)zone_of[m]];
+                    if (slot < 0) { slot = (int)zlists.size(); zlists.emplace_back(); }
+                    zlists[(size_t)slot].push_back((uint32_t)orig_to_compiled[m]);
+                    total++;
+                };
+                for (size_t m = 0; m < nb; m++) add(m);
+                for (long long i = 0; i < k; i++) add(nb + si * (size_t)kmax + (size_t)i);
+                sc.nodes.reserve(total);
+                for (size_t idx = 0; sc.nodes.size() < total; idx++)
+                    for (auto &zl : zlists) if (idx < zl.size()) sc.nodes.push_back(zl[idx]);
                 scen.push_back(std::move(sc));
             }
         std::vector<const Scen *> shard;
