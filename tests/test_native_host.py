@@ -354,3 +354,39 @@ def test_native_capacity_search_matches_python_gpu():
     # occupancy caps (satisfyResourceSetting) move the answer the same way on both sides
     best50, _ = capacity.search(ss, capacity.gpu_runner(0), max_cpu=50, max_mem=100)
     assert native_host.capacity_search_native(cluster, apps, specs, ks, max_cpu=50, max_mem=100)["bestKey"] == best50
+
+
+def test_native_host_survives_malformed_requests():
+    """Truncated and corrupted requests come back as error codes with a message - no crash, no exception across the C boundary
+    (the cgo rule of include/simon_gpu.h) - and well-formed but odd JSON (escapes, nesting, number forms) parses like json.loads."""
+    import random
+    cluster, apps = synth.make_mix(seed_no=103, n_nodes=12, n_workloads=8, max_replicas=2)
+    req = native_host.request_json(cluster, apps)
+    L = native_host.lib()
+    rng = random.Random(7)
+    for _ in range(150):
+        cut = rng.randrange(1, len(req) - 1)
+        h = C.c_void_p()
+        rc = L.simon_host_compile(req[:cut], cut, C.byref(h))
+        assert rc != 0 and not h and L.simon_host_last_error()
+    ok = 0
+    for _ in range(150):
+        b = bytearray(req)
+        for _k in range(rng.randrange(1, 4)):
+            b[rng.randrange(len(b))] = rng.choice(b'{}[]",:0a\\ ')
+        h = C.c_void_p()
+        rc = L.simon_host_compile(bytes(b), len(b), C.byref(h))
+        if rc == 0:
+            ok += 1
+            L.simon_host_plan_free(h)
+        else:
+            assert L.simon_host_last_error()
+    # escapes / unicode / exponent numbers in names and quantities
+    node = {"kind": "Node", "metadata": {"name": "n\u00e9-\"q\"\\\t\U0001F600", "labels": {"k": "v"}},
+            "status": {"allocatable": {"cpu": 4, "memory": 8.0e9, "pods": "110"}, "capacity": {"cpu": 4, "memory": 8.0e9, "pods": "110"}}}
+    pod = {"kind": "Pod", "metadata": {"name": "p", "namespace": "default"},
+           "spec": {"containers": [{"name": "c", "image": "x", "resources": {"requests": {"cpu": 0.5, "memory": 1e9}}}]}}
+    cl, ap = ResourceTypes(Nodes=[node]), [AppResource("a", ResourceTypes(Pods=[pod]))]
+    assert _diff(cl, ap) == []
+    n = native_host.compile_native(cl, ap)
+    assert n.node_names == [node["metadata"]["name"]] and int(n.snap["alloc_mem"][0]) == 8_000_000_000
