@@ -292,7 +292,7 @@ def block_batch(args, c, D, P, placed, local, flush, torch):
     best = None
     tried = []
     act = np.arange(int(c.n_nodes), dtype=np.uint32)
-    for cs, tpb, nb in ((16, 320, 7), (8, 320, 14), (8, 320, 15), (9, 320, 15), (0, 0, 15), (8, 320, 16)):      # (0, 0): the engine's own choice for a batch
+    for cs, tpb, nb in ((16, 320, 7), (8, 320, 15), (9, 320, 15), (9, 384, 15), (0, 0, 15), (0, 0, 7), (9, 384, 16)):      # (0, 0): the engine's own choice for a batch
         try:
             with Engine(c, device=local, cluster_ctas=cs, threads_per_cta=tpb) as eng:
                 eng.run_scenarios([act] * nb)                                   # warm-up

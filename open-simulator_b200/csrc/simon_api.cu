@@ -293,8 +293,43 @@ void fill_params(simon_ctx *ctx, SkParams &P) {
     P.dump_pod = 0xffffffffu; P.dump_total = nullptr; P.dump_code = nullptr;
 }
 
-#define SIMON_MAX_TPB 320u       // largest compiled variant: 168 registers/thread, no spills (640 threads = 96 registers spilled and measured slower)
+#define SIMON_MAX_TPB 384u       // largest compiled variant: 12 warps, 168 registers/thread, no spills (640 threads = 96 registers spilled and measured slower)
 #define SIMON_AUTO_TPB 320u
+
+typedef void (*sk_kernel_fn)(const SkParams);
+// the compiled kernel variant for (threads per CTA, node slots per thread); nullptr: none
+sk_kernel_fn pick_kernel(uint32_t TPB, uint32_t npt, bool prof) {
+    if (TPB > 384) return nullptr;
+    if (TPB > 320) {
+        if (prof) return nullptr;
+        return npt == 1 ? simon_place_kernel_384_1 : npt == 2 ? simon_place_kernel_384_2 : npt == 3 ? simon_place_kernel_384_3 : simon_place_kernel_384_0;
+    }
+    if (TPB > 256) {
+        if (prof) return npt == 1 ? simon_prof_kernel_320_1 : npt == 2 ? simon_prof_kernel_320_2 : npt == 3 ? simon_prof_kernel_320_3 : npt == 4 ? simon_prof_kernel_320_4 : simon_prof_kernel_320_0;
+        return npt == 1 ? simon_place_kernel_320_1 : npt == 2 ? simon_place_kernel_320_2 : npt == 3 ? simon_place_kernel_320_3 : npt == 4 ? simon_place_kernel_320_4 : simon_place_kernel_320_0;
+    }
+    if (prof) return npt == 1 ? simon_prof_kernel_256_1 : npt == 2 ? simon_prof_kernel_256_2 : npt == 3 ? simon_prof_kernel_256_3 : npt == 4 ? simon_prof_kernel_256_4 : simon_prof_kernel_256_0;
+    return npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
+}
+
+// clusters of `cs` CTAs x `t` threads with `smem` bytes each that the device holds at once (GPC boundaries included)
+int max_active_clusters(sk_kernel_fn fn, uint32_t cs, uint32_t t, size_t smem) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cs, 1, 1);
+    cfg.blockDim = dim3(t, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 // choose cluster size / threads / nodes-per-thread for n_active nodes
 int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &TPB, uint32_t &NPT, size_t &smem, uint32_t n_scen = 1) {
@@ -304,8 +339,42 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
     const uint32_t want_cs = ctx->opt_cluster, want_t = ctx->opt_threads;
     if (n_active == 0) n_active = 1;
     ctx->big = false;
+    if (n_scen > 1 && !want_cs && !want_t && !getenv("SIMON_OLD_BATCH_GEOMETRY")) {
+        // Batches are throughput work.  For every cluster size 1..16 (any integer: clusters need not be powers of two) take the
+        // thread count with the fewest node slots per thread, ask the driver how many such clusters the device holds at once
+        // (shared memory, registers and GPC boundaries included), and minimise  waves x time of one scenario,  the latter from the
+        // measured dependence on the slots per thread (C3 replicas, ms per 100,000 decisions: 2 slots 704, 3 slots 852-900, 4 slots
+        // 1,027-1,059; 384-thread CTAs ~4 % slower than 320 at equal slots; larger clusters pay a little more per exchange).
+        // C3 x 15 scenarios: 9 CTAs x 384 threads x 3 slots, 1.64 M decisions/s (8 x 320 x 4, the former choice: 1.41 M).
+        double best_cost = 0;
+        uint32_t b_cs = 0, b_t = 0, b_npt = 0;
+        size_t b_smem = 0;
+        for (uint32_t cs = 1; cs <= 16; cs++) {
+            const uint32_t per_cta = (n_active + cs - 1) / cs;
+            uint32_t t = 0, npt = 0;
+            if (per_cta <= 256) { t = std::max(64u, ((per_cta + 31) / 32) * 32); npt = 1; }
+            else {
+                const uint32_t opts[3] = {256, 320, 384};
+                for (uint32_t q = 0; q < 3; q++) {
+                    const uint32_t k = (per_cta + opts[q] - 1) / opts[q];
+                    if (!t || k < npt) { t = opts[q]; npt = k; }
+                }
+            }
+            if (npt > 64) continue;
+            const size_t b = sk_smem_bytes(npt * t, ctx->T, ctx->emax, ctx->max_blob_words, cs);
+            if (b > (size_t)max_smem) continue;
+            sk_kernel_fn fn = pick_kernel(t, npt, false);
+            if (!fn) continue;
+            const int active = max_active_clusters(fn, cs, t, b);
+            if (active <= 0) continue;
+            const uint32_t waves = (n_scen + (uint32_t)active - 1) / (uint32_t)active;
+            const double cost = waves * (380.0 + 162.0 * npt + (t > 320 ? 30.0 : 0.0) + 2.0 * cs);
+            if (!b_cs || cost < best_cost) { best_cost = cost; b_cs = cs; b_t = t; b_npt = npt; b_smem = b; }
+        }
+        if (b_cs) { CS = b_cs; TPB = b_t; NPT = b_npt; smem = b_smem; return SIMON_OK; }
+    }
     if (n_scen > 1 && !want_cs && !want_t) {
-        // Batches are throughput work: small clusters waste the least on synchronisation (C4, 256 scenarios of ~2,000 nodes:
+        // (fallback: the rule used before cudaOccupancyMaxActiveClusters was consulted)  Batches are throughput work: small clusters waste the least on synchronisation (C4, 256 scenarios of ~2,000 nodes:
         // 2 CTAs x 256 threads 147 ms, 4 x 256 207 ms, 8 x 256 368 ms; C3, 10,000 nodes: 14 x 8 CTAs beat 7 x 16).  Take the
         // smallest cluster that fits shared memory while the batch still fills about half of the SMs; a batch too small for
         // that gets the largest cluster with which it still runs in one wave.
@@ -346,8 +415,11 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
             if (per_cta <= 256) { cs_p = cs; t_p = std::max(128u, ((per_cta + 31) / 32) * 32); npt_p = 1; }
         }
         if (!cs_p) {
-            const uint32_t per_cta = (n_active + 15) / 16, n256 = (per_cta + 255) / 256, n320 = (per_cta + 319) / 320;
-            cs_p = 16; t_p = n320 < n256 ? 320 : 256; npt_p = n320 < n256 ? n320 : n256;
+            // fewest slots per thread among 256 / 320 / 384 threads (12 warps share the register ceiling of 10), ties to the fewer threads
+            const uint32_t per_cta = (n_active + 15) / 16, n256 = (per_cta + 255) / 256, n320 = (per_cta + 319) / 320, n384 = (per_cta + 383) / 384;
+            cs_p = 16; t_p = 256; npt_p = n256;
+            if (n320 < npt_p) { t_p = 320; npt_p = n320; }
+            if (n384 < npt_p) { t_p = 384; npt_p = n384; }
         }
         const size_t b = sk_smem_bytes(npt_p * t_p, ctx->T, ctx->emax, ctx->max_blob_words, cs_p);
         if (npt_p <= 64 && b <= (size_t)max_smem) { CS = cs_p; TPB = t_p; NPT = npt_p; smem = b; return SIMON_OK; }
@@ -389,7 +461,6 @@ int choose_geometry(simon_ctx *ctx, uint32_t n_active, uint32_t &CS, uint32_t &T
     return fail(ctx, SIMON_ERR_LIMIT, "cluster of %u nodes exceeds the engine limit (16 CTAs x 320 threads x 64 node slots)", n_active);
 }
 
-typedef void (*sk_kernel_fn)(const SkParams);
 static_assert(sizeof(SkScenario) % 8 == 0, "SkScenario is copied in 8-byte words");
 
 int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t TPB, size_t smem, bool record = true) {
@@ -403,11 +474,10 @@ int launch(simon_ctx *ctx, SkParams &P, uint32_t n_scen, uint32_t CS, uint32_t T
         CU(ctx->d_gnode.alloc(ctx->gnode_stride * (size_t)n_scen * CS));
         P.gnode = ctx->d_gnode.p; P.gnode_stride = ctx->gnode_stride;
         fn = simon_place_kernel_big;
-    } else if (TPB > 256) {
-        if (prof) fn = npt == 1 ? simon_prof_kernel_320_1 : npt == 2 ? simon_prof_kernel_320_2 : npt == 3 ? simon_prof_kernel_320_3 : npt == 4 ? simon_prof_kernel_320_4 : simon_prof_kernel_320_0;
-        else fn = npt == 1 ? simon_place_kernel_320_1 : npt == 2 ? simon_place_kernel_320_2 : npt == 3 ? simon_place_kernel_320_3 : npt == 4 ? simon_place_kernel_320_4 : simon_place_kernel_320_0;
-    } else if (prof) fn = npt == 1 ? simon_prof_kernel_256_1 : npt == 2 ? simon_prof_kernel_256_2 : npt == 3 ? simon_prof_kernel_256_3 : npt == 4 ? simon_prof_kernel_256_4 : simon_prof_kernel_256_0;
-    else fn = npt == 1 ? simon_place_kernel_256_1 : npt == 2 ? simon_place_kernel_256_2 : npt == 3 ? simon_place_kernel_256_3 : npt == 4 ? simon_place_kernel_256_4 : simon_place_kernel_256_0;
+    } else {
+        fn = pick_kernel(TPB, npt, prof);
+        if (!fn) return fail(ctx, SIMON_ERR_LIMIT, "no kernel variant for %u threads per CTA%s", TPB, prof ? " with phase timers" : "");
+    }
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg;

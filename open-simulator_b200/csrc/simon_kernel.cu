@@ -1457,3 +1457,13 @@ SIMON_KERNEL(320, 1)
 SIMON_KERNEL(320, 2)
 SIMON_KERNEL(320, 3)
 SIMON_KERNEL(320, 4)
+// 384 threads = 12 warps = 3 per SM sub-partition, the same register ceiling (168) as 320 threads: one slot per thread less where the
+// nodes of a CTA fall between the two (scenario batches on 9-CTA clusters: 3 slots instead of 4).  No profiling variants.
+#define SIMON_KERNEL_PLAIN(MAXT, NPTT)                                                                   \
+    extern "C" __global__ void __launch_bounds__(MAXT, 1) simon_place_kernel_##MAXT##_##NPTT(const __grid_constant__ SkParams P) { \
+        simon_place_body<MAXT, NPTT, false>(P);                                                          \
+    }
+SIMON_KERNEL_PLAIN(384, 0)
+SIMON_KERNEL_PLAIN(384, 1)
+SIMON_KERNEL_PLAIN(384, 2)
+SIMON_KERNEL_PLAIN(384, 3)
