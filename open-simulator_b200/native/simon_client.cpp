@@ -30,9 +30,60 @@ static bool read_blob(FILE *f, Blob &b) {
     return read_exact(f, b.data.data(), n);
 }
 
+// --simulate request.json [device] [result.json]: the whole of simulator.Simulate (pkg/simulator/core.go:67-119) through
+// simon_host_simulate - the objects as JSON in, the SimulateResult as JSON out (written to result.json when given), a one-line
+// summary on stdout.  This is exactly what the Go shim does (open-simulator_b200/go/gpu_cgo.go), minus Go.
+static int simulate_main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s --simulate request.json [device] [result.json]\n", argv[0]); return 64; }
+    FILE *f = fopen(argv[2], "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", argv[2]); return 66; }
+    std::string req;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) req.append(buf, n);
+    fclose(f);
+    simon_ctx_opts opts;
+    memset(&opts, 0, sizeof(opts));
+    opts.device = argc > 3 ? atoi(argv[3]) : 0;
+    char *out = nullptr;
+    uint64_t out_len = 0;
+    int rc = simon_host_simulate(req.data(), req.size(), &opts, &out, &out_len);
+    if (rc != SIMON_OK) {
+        fprintf(stderr, "simon_host_simulate failed (rc=%d): %s%s\n", rc, simon_host_last_error(),
+                rc == SIMON_ERR_CUDA ? " - the engine has no CPU path" : "");
+        return rc == SIMON_ERR_CUDA ? 2 : 3;
+    }
+    if (argc > 4) {
+        FILE *o = fopen(argv[4], "wb");
+        if (!o || fwrite(out, 1, out_len, o) != out_len) { fprintf(stderr, "cannot write %s\n", argv[4]); return 74; }
+        fclose(o);
+    }
+    // placed / unschedulable counts and an FNV-1a hash of the podNode vector, read back from the result text
+    const char *pn = strstr(out, "\"podNode\":[");
+    uint64_t h = 1469598103934665603ull;
+    uint32_t pods = 0, placed = 0, unsched = 0;
+    if (pn) {
+        const char *q = pn + 11;
+        while (*q && *q != ']') {
+            char *e = nullptr;
+            long v = strtol(q, &e, 10);
+            if (e == q) break;
+            for (int b = 0; b < 4; b++) { h ^= (uint64_t)((uint32_t)(int32_t)v >> (8 * b) & 0xff); h *= 1099511628211ull; }
+            pods++; placed += v >= 0; unsched += v == -1;
+            q = *e == ',' ? e + 1 : e;
+        }
+    }
+    const char *tm = strstr(out, "\"timing\":");
+    printf("{\"pods\": %u, \"placed\": %u, \"unschedulable\": %u, \"fnv1a_pod_node\": \"%016llx\", \"result_bytes\": %llu, %s\n", pods, placed,
+           unsched, (unsigned long long)h, (unsigned long long)out_len, tm ? tm : "\"timing\":null}");
+    simon_host_free(out);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 2 && !strcmp(argv[1], "--simulate")) return simulate_main(argc, argv);
     if (argc < 2) {
-        fprintf(stderr, "usage: %s cluster.simc [device] [replay_steps]\n", argv[0]);
+        fprintf(stderr, "usage: %s cluster.simc [device] [replay_steps]\n       %s --simulate request.json [device] [result.json]\n", argv[0], argv[0]);
         return 64;
     }
     const int device = argc > 2 ? atoi(argv[2]) : 0;
