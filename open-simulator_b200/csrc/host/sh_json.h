@@ -4,9 +4,11 @@
 #pragma once
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -217,6 +219,72 @@ struct Parser {
             }
         }
     }
+    // ---- large arrays (cluster.Nodes, cluster.Pods: tens of thousands of objects) are parsed by several threads: one sequential
+    //      scan finds the element boundaries (strings and nesting only), then each thread parses a contiguous run of elements ----
+    void skip_string() {
+        p++;
+        while (true) {
+            if (p >= e) fail("unterminated string");
+            if (*p == '"') { p++; return; }
+            if (*p == '\\') { p++; if (p >= e) fail("bad escape"); }
+            p++;
+        }
+    }
+    void skip_value() {
+        ws();
+        if (p >= e) fail("unexpected end");
+        if (*p == '"') { skip_string(); return; }
+        if (*p == '{' || *p == '[') {
+            int nest = 0;
+            while (true) {
+                if (p >= e) fail("unexpected end");
+                const char ch = *p;
+                if (ch == '"') { skip_string(); continue; }
+                if (ch == '{' || ch == '[') nest++;
+                else if (ch == '}' || ch == ']') { nest--; if (nest == 0) { p++; return; } }
+                p++;
+            }
+        }
+        while (p < e && *p != ',' && *p != ']' && *p != '}' && *p != ' ' && *p != '\n' && *p != '\t' && *p != '\r') p++;     // literal / number
+    }
+    // p stands on the first element of an array; true: `j.a` holds every element and p stands after the closing bracket
+    bool parallel_array(J &j, int depth) {
+        const char *start = p;
+        std::vector<std::pair<const char *, const char *>> spans;
+        while (true) {
+            ws();
+            const char *b = p;
+            skip_value();
+            spans.emplace_back(b, p);
+            ws();
+            if (p < e && *p == ',') { p++; continue; }
+            if (p < e && *p == ']') { p++; break; }
+            fail("expected ',' or ']'");
+        }
+        unsigned hw = std::thread::hardware_concurrency();
+        const size_t nt = std::min<size_t>(8, std::min<size_t>(hw ? hw : 1, spans.size() / 64));
+        if (nt < 2) { p = start; return false; }
+        const char *after = p;
+        j.a.resize(spans.size());
+        std::vector<std::string> errors(nt);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                const size_t lo = spans.size() * t / nt, hi = spans.size() * (t + 1) / nt;
+                try {
+                    for (size_t i = lo; i < hi; i++) {
+                        Parser sub(spans[i].first, (size_t)(spans[i].second - spans[i].first));
+                        j.a[i] = sub.value(depth + 1);
+                        sub.ws();
+                        if (sub.p != sub.e) sub.fail("unexpected character");
+                    }
+                } catch (const std::exception &ex) { errors[t] = ex.what(); if (errors[t].empty()) errors[t] = "request JSON: error"; }
+            });
+        for (auto &x : th) x.join();
+        for (auto &m : errors) if (!m.empty()) throw Error(m);
+        p = after;
+        return true;
+    }
     J value(int depth = 0) {
         if (depth > 200) fail("nesting too deep");
         ws();
@@ -247,6 +315,7 @@ struct Parser {
             j.t = J::Arr;
             ws();
             if (p < e && *p == ']') { p++; return j; }
+            if (depth <= 3 && e - p > (1 << 18) && parallel_array(j, depth)) return j;
             while (true) {
                 j.a.push_back(value(depth + 1));
                 ws();

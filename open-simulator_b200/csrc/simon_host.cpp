@@ -385,6 +385,31 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         for (uint32_t j = 0; j < n_fail; j++) fail_idx[fail_pod[j]] = j;
         std::unordered_map<const PodTemplate *, Reasons> static_memo;
         NodeStaticKeys node_keys;
+        {
+            // node-static reasons of every failing template, several templates at a time (they only read the plan)
+            std::vector<const PodRec *> todo;
+            for (uint32_t j = 0; j < n_fail; j++) {
+                const PodRec &r = p.pods[fail_pod[j]];
+                if (static_memo.emplace(r.tmpl, Reasons()).second) todo.push_back(&r);
+            }
+            if (!todo.empty()) {
+                node_keys.build(c);
+                unsigned hw = std::thread::hardware_concurrency();
+                const size_t nt = std::max<size_t>(1, std::min<size_t>(8, std::min<size_t>(hw ? hw : 1, todo.size())));
+                std::vector<Reasons> out(todo.size());
+                std::vector<std::string> errors(nt);
+                std::vector<std::thread> th;
+                for (size_t t = 0; t < nt; t++)
+                    th.emplace_back([&, t] {
+                        try {
+                            for (size_t i = t; i < todo.size(); i += nt) out[i] = static_reasons(c, *todo[i], node_keys);
+                        } catch (const std::exception &ex) { errors[t] = ex.what(); if (errors[t].empty()) errors[t] = "error"; }
+                    });
+                for (auto &x : th) x.join();
+                for (auto &m : errors) if (!m.empty()) throw Error(m);
+                for (size_t i = 0; i < todo.size(); i++) static_memo[todo[i]->tmpl] = std::move(out[i]);
+            }
+        }
         std::string res;
         res.reserve((size_t)P * 48 + 4096);
         res += "{\"nodes\":[";

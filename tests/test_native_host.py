@@ -381,6 +381,27 @@ def test_native_host_survives_malformed_requests():
             L.simon_host_plan_free(h)
         else:
             assert L.simon_host_last_error()
+    # a request large enough for the multi-threaded array parser (elements parsed by worker threads): errors inside an element,
+    # between elements and truncation must all surface as error codes
+    big_cluster, big_apps = synth.make_c3(n_nodes=1500, n_workloads=30, replicas=5, n_apps=1, seed_no=9)
+    big = native_host.request_json(big_cluster, big_apps)
+    assert len(big) > (1 << 19)
+    h = C.c_void_p()
+    assert L.simon_host_compile(big, len(big), C.byref(h)) == 0
+    L.simon_host_plan_free(h)
+    for _ in range(40):
+        b = bytearray(big)
+        if rng.random() < 0.5:
+            b = b[:rng.randrange(1, len(b) - 1)]
+        else:
+            for _k in range(rng.randrange(1, 3)):
+                b[rng.randrange(len(b))] = rng.choice(b'{}[]",:\\')
+        h = C.c_void_p()
+        rc = L.simon_host_compile(bytes(b), len(b), C.byref(h))
+        if rc == 0:
+            L.simon_host_plan_free(h)
+        else:
+            assert L.simon_host_last_error()
     # escapes / unicode / exponent numbers in names and quantities
     node = {"kind": "Node", "metadata": {"name": "n\u00e9-\"q\"\\\t\U0001F600", "labels": {"k": "v"}},
             "status": {"allocatable": {"cpu": 4, "memory": 8.0e9, "pods": "110"}, "capacity": {"cpu": 4, "memory": 8.0e9, "pods": "110"}}}
