@@ -411,3 +411,98 @@ def test_native_host_survives_malformed_requests():
     assert _diff(cl, ap) == []
     n = native_host.compile_native(cl, ap)
     assert n.node_names == [node["metadata"]["name"]] and int(n.snap["alloc_mem"][0]) == 8_000_000_000
+
+
+def test_native_columns_match_python_on_rarely_used_object_shapes():
+    """Branches the synthetic generators seldom reach: init containers and pod overhead, host ports (incl. hostIP / protocol), extended and
+    hugepages resources, templates that preset spec.nodeName, Jobs and CronJobs (completions), a Service with an empty selector, ReplicaSet
+    / StatefulSet owners for the default spread selector, spread constraints with a null selector, (anti)affinity terms with explicit
+    namespaces, every node-selector operator incl. Gt / Lt and invalid ones, fractional / exponent / binary quantities, zone labels in
+    their beta spelling, nodes without labels, duplicate node names."""
+    R, P = "requiredDuringSchedulingIgnoredDuringExecution", "preferredDuringSchedulingIgnoredDuringExecution"
+
+    def node(name, cpu="8", mem="16Gi", labels=None, taints=None, extra_alloc=None, unsched=False):
+        alloc = {"cpu": cpu, "memory": mem, "pods": "110", "ephemeral-storage": "100Gi"}
+        alloc.update(extra_alloc or {})
+        n = {"kind": "Node", "metadata": {"name": name}, "status": {"allocatable": alloc, "capacity": dict(alloc)}}
+        if labels is not None:
+            n["metadata"]["labels"] = labels
+        if taints or unsched:
+            n["spec"] = {}
+            if taints:
+                n["spec"]["taints"] = taints
+            if unsched:
+                n["spec"]["unschedulable"] = True
+        return n
+
+    nodes = [
+        node("a", labels={"kubernetes.io/hostname": "a", "failure-domain.beta.kubernetes.io/zone": "z1", "failure-domain.beta.kubernetes.io/region": "r1",
+                          "tier": "gold", "gen": "7"}, extra_alloc={"example.com/fpga": "2", "hugepages-2Mi": "1Gi"}),
+        node("b", cpu="7500m", mem="15.5Gi", labels={"kubernetes.io/hostname": "b", "topology.kubernetes.io/zone": "z2", "tier": "silver", "gen": "12"},
+             taints=[{"key": "dedicated", "value": "x", "effect": "NoSchedule"}, {"key": "flaky", "effect": "PreferNoSchedule"}]),
+        node("c", cpu="16", mem="64e9", labels={"kubernetes.io/hostname": "c", "topology.kubernetes.io/zone": "z1", "gen": "abc"},
+             taints=[{"key": "evict", "value": "now", "effect": "NoExecute"}]),
+        node("d", cpu="4", mem="8Gi"),                                  # no labels at all
+        node("e", cpu="0.5", mem="512Mi", labels={"kubernetes.io/hostname": "e", "tier": "gold"}, unsched=True),
+        node("a", cpu="64", labels={"kubernetes.io/hostname": "dup"}),    # duplicate name: skipped by nodeTree
+    ]
+
+    def tmpl(labels, **spec):
+        s = {"containers": [{"name": "c", "image": "img", "resources": {"requests": {"cpu": "250m", "memory": "256Mi"}}}]}
+        s.update(spec)
+        return {"metadata": {"labels": labels}, "spec": s}
+
+    heavy = tmpl({"app": "heavy"},
+                 initContainers=[{"name": "i", "image": "init", "resources": {"requests": {"cpu": "2", "memory": "1Gi", "example.com/fpga": "1"}}}],
+                 containers=[{"name": "c1", "image": "img1", "resources": {"requests": {"cpu": "0.3", "memory": "1e8", "hugepages-2Mi": "128Mi"}},
+                              "ports": [{"containerPort": 80, "hostPort": 8080}, {"containerPort": 81, "hostPort": 8081, "hostIP": "10.0.0.1", "protocol": "UDP"}]},
+                             {"name": "c2", "image": "img2", "resources": {"requests": {"ephemeral-storage": "1Gi"}, "limits": {"cpu": "1"}}}],
+                 overhead={"cpu": "100m", "memory": "64Mi"})
+    sel = tmpl({"app": "sel", "team": "t"}, nodeSelector={"tier": "gold"}, tolerations=[{"key": "dedicated", "operator": "Equal", "value": "x"}],
+               affinity={"nodeAffinity": {
+                   R: {"nodeSelectorTerms": [
+                       {"matchExpressions": [{"key": "gen", "operator": "Gt", "values": ["5"]}, {"key": "tier", "operator": "NotIn", "values": ["bronze"]}]},
+                       {"matchExpressions": [{"key": "gen", "operator": "Lt", "values": ["10"]}, {"key": "nope", "operator": "DoesNotExist"}]},
+                       {"matchExpressions": [{"key": "gen", "operator": "Bogus", "values": ["1"]}]},
+                       {}]},
+                   P: [{"weight": 10, "preference": {"matchExpressions": [{"key": "tier", "operator": "Exists"}]}},
+                       {"weight": 0, "preference": {"matchExpressions": [{"key": "tier", "operator": "In", "values": ["gold"]}]}},
+                       {"weight": 5, "preference": {"matchFields": [{"key": "metadata.name", "operator": "NotIn", "values": ["b"]}]}}]}})
+    spread = tmpl({"app": "spread"}, topologySpreadConstraints=[
+        {"maxSkew": 1, "topologyKey": "topology.kubernetes.io/zone", "whenUnsatisfiable": "DoNotSchedule", "labelSelector": {"matchLabels": {"app": "spread"}}},
+        {"maxSkew": 2, "topologyKey": "kubernetes.io/hostname", "whenUnsatisfiable": "ScheduleAnyway", "labelSelector": None},
+        {"maxSkew": 3, "topologyKey": "tier", "whenUnsatisfiable": "ScheduleAnyway",
+         "labelSelector": {"matchExpressions": [{"key": "app", "operator": "In", "values": ["spread", "sel"]}]}}])
+    ipa = tmpl({"app": "ipa"}, tolerations=[{"operator": "Exists"}], affinity={
+        "podAffinity": {R: [{"labelSelector": {"matchLabels": {"app": "heavy"}}, "topologyKey": "topology.kubernetes.io/zone", "namespaces": ["default", "other"]}],
+                        P: [{"weight": 50, "podAffinityTerm": {"labelSelector": {"matchExpressions": [{"key": "team", "operator": "Exists"}]},
+                                                               "topologyKey": "kubernetes.io/hostname"}}]},
+        "podAntiAffinity": {R: [{"labelSelector": {"matchLabels": {"app": "ipa"}}, "topologyKey": "kubernetes.io/hostname"}],
+                            P: [{"weight": 7, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "spread"}}, "topologyKey": "tier",
+                                                                  "namespaces": ["other"]}}]}})
+    bound = tmpl({"app": "bound"}, nodeName="c")
+
+    def wl(kind, name, template, ns="default", **spec):
+        s = {"template": template}
+        s.update(spec)
+        return {"kind": kind, "metadata": {"name": name, "namespace": ns, "uid": "uid-" + name}, "spec": s}
+
+    cluster = ResourceTypes(
+        Nodes=nodes,
+        Pods=[{"kind": "Pod", "metadata": {"name": "static-1", "namespace": "kube-system", "labels": {"app": "heavy"}},
+               "spec": dict(heavy["spec"], nodeName="a")},
+              {"kind": "Pod", "metadata": {"name": "ghost", "namespace": "kube-system"}, "spec": dict(tmpl({})["spec"], nodeName="no-such-node")}],
+        Services=[{"kind": "Service", "metadata": {"name": "all", "namespace": "default"}, "spec": {"selector": {}}},
+                  {"kind": "Service", "metadata": {"name": "sel", "namespace": "default"}, "spec": {"selector": {"app": "sel", "team": "t"}}},
+                  {"kind": "Service", "metadata": {"name": "none", "namespace": "default"}, "spec": {}}],
+        ReplicaSets=[wl("ReplicaSet", "rs-heavy", heavy, replicas=2, selector={"matchLabels": {"app": "heavy"}})],
+        StatefulSets=[wl("StatefulSet", "sts-ipa", ipa, replicas=2, selector={"matchExpressions": [{"key": "app", "operator": "In", "values": ["ipa"]}]})],
+        DaemonSets=[wl("DaemonSet", "ds", tmpl({"app": "ds"}, tolerations=[{"operator": "Exists"}], nodeSelector={"tier": "gold"}))])
+    app = ResourceTypes(
+        Deployments=[wl("Deployment", "d-sel", sel, replicas=3), wl("Deployment", "d-spread", spread, replicas=4), wl("Deployment", "d-bound", bound, replicas=2),
+                     wl("Deployment", "d-zero", sel, replicas=0), wl("Deployment", "d-default", heavy)],
+        Jobs=[wl("Job", "job", tmpl({"job": "j"}), completions=2), wl("Job", "job1", tmpl({"job": "j1"}))],
+        CronJobs=[{"kind": "CronJob", "metadata": {"name": "cron", "namespace": "other"}, "spec": {"jobTemplate": {"spec": {"completions": 2, "template": ipa}}}}],
+        StatefulSets=[wl("StatefulSet", "sts", spread, ns="other", replicas=2, volumeClaimTemplates=[{"spec": {"storageClassName": "standard", "resources": {"requests": {"storage": "5Gi"}}}}])],
+        PodDisruptionBudgets=[{"kind": "PodDisruptionBudget", "metadata": {"name": "pdb"}, "spec": {"minAvailable": 1}}])
+    assert _diff(cluster, [AppResource("first", app), AppResource("second", ResourceTypes(Deployments=[wl("Deployment", "again", ipa, replicas=2)]))]) == []
