@@ -13,9 +13,11 @@
 // (pkg/simulator/utils.go:85-228); the order here is Pods, Deployments, ReplicaSets, StatefulSets, Jobs, CronJobs; generated pod names
 // carry an ordinal where the reference draws a random suffix (pkg/utils/utils.go:312).
 #pragma once
+#include <atomic>
 #include <deque>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -50,7 +52,7 @@ struct PodRec {
 
 struct Expander {
     std::deque<PodTemplate> templates;
-    int n_pin_groups = 0;
+    int n_pin_groups = 0;          // next pin-group id; every segment of a plan expands with its own Expander and its own id range
 
     PodTemplate *new_template(J pod, const char *kind, const std::string &name, const std::string &ns) {
         templates.emplace_back();
@@ -432,7 +434,7 @@ struct Segment { std::string name; uint32_t first, count; };
 
 struct Plan {
     J request;                                // owns every object the templates and node pointers refer to
-    Expander ex;
+    std::vector<std::unique_ptr<Expander>> exs;   // one per segment: the templates of its pods
     std::vector<const J *> nodes;             // cluster.Nodes, input order
     std::vector<PodRec> pods;                 // the ordered work list
     std::vector<Segment> segments;            // "cluster", then one per app
@@ -440,32 +442,68 @@ struct Plan {
     const J *cluster = nullptr;
 };
 
-// simulator.plan(): everything the reference does before / between its schedulePods calls
+// run fn(0..n-1) on up to 8 threads; the first failure (lowest index) is rethrown
+template <typename F>
+inline void parallel_for(size_t n, F fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(8, std::min<size_t>(hw ? hw : 1, n));
+    if (nt < 2) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::string> errors(n);
+    std::vector<int> codes(n, 0);
+    std::vector<std::thread> th;
+    std::atomic<size_t> next{0};
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+                try { fn(i); }
+                catch (const Error &e) { errors[i] = e.what(); codes[i] = e.code; if (errors[i].empty()) errors[i] = "error"; }
+                catch (const std::exception &e) { errors[i] = e.what(); codes[i] = -1; if (errors[i].empty()) errors[i] = "error"; }
+            }
+        });
+    for (auto &x : th) x.join();
+    for (size_t i = 0; i < n; i++) if (!errors[i].empty()) throw Error(errors[i], codes[i]);
+}
+
+// simulator.plan(): everything the reference does before / between its schedulePods calls.  The segments (the cluster's own pods, then
+// one per app) expand and sort independently of each other, so they do so on separate threads; the work list is their concatenation.
 inline void make_plan(Plan &p) {
     const J *cl = p.request.get("cluster");
     if (!cl || !cl->is_obj()) throw Error("request: missing \"cluster\" object");
     p.cluster = cl;
     for (auto &n : field_arr(*cl, "Nodes").a) p.nodes.push_back(&n);
-    p.ex.exclude_daemonset(p.pods, *cl);
-    for (auto &ds : field_arr(*cl, "DaemonSets").a) p.ex.by_daemonset(p.pods, ds, p.nodes);
-    p.segments.push_back(Segment{"cluster", 0, (uint32_t)p.pods.size()});
     const J &apps = field_arr(p.request, "apps");
-    for (auto &app : apps.a) {
+    const size_t n_seg = 1 + apps.a.size();
+    std::vector<std::vector<PodRec>> seg_pods(n_seg);
+    p.exs.resize(n_seg);
+    for (size_t i = 0; i < n_seg; i++) { p.exs[i].reset(new Expander()); p.exs[i]->n_pin_groups = (int)(i * 1000000); }
+    parallel_for(n_seg, [&](size_t i) {
+        Expander &ex = *p.exs[i];
+        std::vector<PodRec> &out = seg_pods[i];
+        if (i == 0) {
+            ex.exclude_daemonset(out, *cl);
+            for (auto &ds : field_arr(*cl, "DaemonSets").a) ex.by_daemonset(out, ds, p.nodes);
+            return;
+        }
+        const J &app = apps.a[i - 1];
         std::string name = field_str(app, "Name");
         const J &res = field_obj(app, "Resource");
-        int ai = (int)p.app_names.size();
+        ex.exclude_daemonset(out, res);
+        for (auto &ds : field_arr(res, "DaemonSets").a) ex.by_daemonset(out, ds, p.nodes);
+        // every pod gets the label simon/app-name=<appname> (the templates of this expander are exactly those of the app's pods)
+        for (auto &t : ex.templates) t.pod.getm("metadata")->getm("labels")->set(LABEL_APP_NAME, J::str(name));
+        for (auto &r : out) r.app = (int)(i - 1);
+        order_app_pods(out);
+    });
+    size_t total = 0;
+    for (auto &v : seg_pods) total += v.size();
+    p.pods.reserve(total);
+    p.segments.push_back(Segment{"cluster", 0, (uint32_t)seg_pods[0].size()});
+    for (auto &r : seg_pods[0]) p.pods.push_back(std::move(r));
+    for (size_t i = 1; i < n_seg; i++) {
+        std::string name = field_str(apps.a[i - 1], "Name");
         p.app_names.push_back(name);
-        std::vector<PodRec> ap;
-        size_t t0 = p.ex.templates.size();
-        p.ex.exclude_daemonset(ap, res);
-        for (auto &ds : field_arr(res, "DaemonSets").a) p.ex.by_daemonset(ap, ds, p.nodes);
-        // every pod gets the label simon/app-name=<appname> (the templates created for this app are exactly those of its pods)
-        for (size_t t = t0; t < p.ex.templates.size(); t++)
-            p.ex.templates[t].pod.getm("metadata")->getm("labels")->set(LABEL_APP_NAME, J::str(name));
-        for (auto &r : ap) r.app = ai;
-        order_app_pods(ap);
-        p.segments.push_back(Segment{name, (uint32_t)p.pods.size(), (uint32_t)ap.size()});
-        for (auto &r : ap) p.pods.push_back(std::move(r));
+        p.segments.push_back(Segment{name, (uint32_t)p.pods.size(), (uint32_t)seg_pods[i].size()});
+        for (auto &r : seg_pods[i]) p.pods.push_back(std::move(r));
     }
 }
 

@@ -303,7 +303,11 @@ int simon_host_simulate(const char *request_json, uint64_t len, const simon_ctx_
         // background thread after the result has been handed over
         struct PlanHolder {
             simon_host_plan *p = new simon_host_plan();
-            ~PlanHolder() { if (p) { simon_host_plan *q = p; std::thread([q] { delete q; }).detach(); } }
+            ~PlanHolder() {
+                if (!p) return;
+                simon_host_plan *q = p;
+                try { std::thread([q] { delete q; }).detach(); } catch (...) { delete q; }       // no thread to spare: release it here
+            }
         } holder;
         simon_host_plan &hp = *holder.p;
         hp.plan.request = parse_json(request_json, (size_t)len);
